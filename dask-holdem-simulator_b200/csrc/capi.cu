@@ -1,0 +1,376 @@
+// capi.cu -- the C ABI of include/holdem_b200.h: table upload, argument checking, error reporting and the
+// host-buffer entry points (pinned staging + chunked H2D / kernel / D2H pipeline).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/holdem_b200.h"
+#include "device_common.cuh"
+#include "launch.h"
+#include "tables.h"
+
+namespace {
+
+using namespace holdem;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(HOLDEM_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));     \
+    } while (0)
+
+struct DeviceState {
+    bool ready = false;
+    int sms = 0;
+    uint8_t *image = nullptr;
+    DevTables T;
+    // pinned staging + device scratch for the *_host entry points (grown on demand, guarded by host_mu)
+    std::mutex host_mu;
+    uint8_t *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+    uint8_t *d_buf = nullptr;
+    size_t d_buf_bytes = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    int *flags = nullptr;       // ring of device ints handed to the two-pass HP dispatch (one per call)
+    unsigned flag_next = 0;
+};
+constexpr unsigned kFlagRing = 1024;
+
+constexpr int kMaxDevices = 64;
+DeviceState g_dev[kMaxDevices];
+std::mutex g_init_mu;
+
+int current_state(DeviceState **out) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+        return fail(HOLDEM_ERR_NO_DEVICE, "no current CUDA device");
+    if (!g_dev[dev].ready) return fail(HOLDEM_ERR_NOT_INIT, "holdem_init(%d) has not been called", dev);
+    *out = &g_dev[dev];
+    return HOLDEM_OK;
+}
+
+int ensure_host_buffers(DeviceState &S, size_t pin_bytes, size_t dev_bytes) {
+    if (S.h_pin_bytes < pin_bytes) {
+        if (S.h_pin) cudaFreeHost(S.h_pin);
+        S.h_pin = nullptr;
+        S.h_pin_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&S.h_pin, pin_bytes));
+        S.h_pin_bytes = pin_bytes;
+    }
+    if (S.d_buf_bytes < dev_bytes) {
+        if (S.d_buf) cudaFree(S.d_buf);
+        S.d_buf = nullptr;
+        S.d_buf_bytes = 0;
+        CUDA_TRY(cudaMalloc(&S.d_buf, dev_bytes));
+        S.d_buf_bytes = dev_bytes;
+    }
+    for (auto &st : S.streams)
+        if (!st) CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    return HOLDEM_OK;
+}
+
+// Generic chunked host pipeline: rows of in_row bytes -> rows of out_row bytes, double-buffered over two streams so
+// that the H2D copy of chunk k+1 overlaps the kernel of chunk k and the D2H copy of chunk k-1.
+template <class Launch>
+int host_pipeline(const void *h_in, size_t in_row, void *h_out, size_t out_row, int64_t n, int64_t chunk_rows,
+                  Launch launch) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n == 0) return HOLDEM_OK;
+    std::lock_guard<std::mutex> lock(S->host_mu);
+    if (chunk_rows > n) chunk_rows = n;
+    const size_t in_chunk = (size_t)chunk_rows * in_row, out_chunk = (size_t)chunk_rows * out_row;
+    const size_t slot = ((in_chunk + out_chunk + 255) / 256) * 256;
+    rc = ensure_host_buffers(*S, 2 * slot, 2 * slot);
+    if (rc) return rc;
+    int64_t done = 0;
+    int64_t pending_rows[2] = {0, 0};
+    int64_t pending_off[2] = {0, 0};
+    int k = 0;
+    auto drain = [&](int b) -> int {
+        if (pending_rows[b] == 0) return HOLDEM_OK;
+        CUDA_TRY(cudaStreamSynchronize(S->streams[b]));
+        std::memcpy((uint8_t *)h_out + (size_t)pending_off[b] * out_row, S->h_pin + b * slot + in_chunk,
+                    (size_t)pending_rows[b] * out_row);
+        pending_rows[b] = 0;
+        return HOLDEM_OK;
+    };
+    while (done < n) {
+        int b = k & 1;
+        rc = drain(b);
+        if (rc) return rc;
+        int64_t rows = n - done < chunk_rows ? n - done : chunk_rows;
+        uint8_t *hp_in = S->h_pin + b * slot, *hp_out = hp_in + in_chunk;
+        uint8_t *d_in = S->d_buf + b * slot, *d_out = d_in + in_chunk;
+        std::memcpy(hp_in, (const uint8_t *)h_in + (size_t)done * in_row, (size_t)rows * in_row);
+        CUDA_TRY(cudaMemcpyAsync(d_in, hp_in, (size_t)rows * in_row, cudaMemcpyHostToDevice, S->streams[b]));
+        CUDA_TRY(launch(*S, d_in, rows, d_out, S->streams[b]));
+        CUDA_TRY(cudaMemcpyAsync(hp_out, d_out, (size_t)rows * out_row, cudaMemcpyDeviceToHost, S->streams[b]));
+        pending_rows[b] = rows;
+        pending_off[b] = done;
+        done += rows;
+        ++k;
+    }
+    rc = drain(0);
+    if (rc) return rc;
+    return drain(1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int holdem_abi_version(void) { return HOLDEM_ABI_VERSION; }
+
+const char *holdem_last_error(void) { return g_err; }
+
+int holdem_selftest_tables(void) {
+    char msg[256];
+    if (holdem::selftest(msg, sizeof msg)) return fail(HOLDEM_ERR_INTERNAL, "table self-check failed: %s", msg);
+    return HOLDEM_OK;
+}
+
+int holdem_init(int device) {
+    if (device < 0 || device >= kMaxDevices) return fail(HOLDEM_ERR_BAD_ARG, "device index %d out of range", device);
+    std::lock_guard<std::mutex> lock(g_init_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(HOLDEM_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device >= count) return fail(HOLDEM_ERR_NO_DEVICE, "device %d requested but only %d present", device, count);
+    DeviceState &S = g_dev[device];
+    CUDA_TRY(cudaSetDevice(device));
+    if (S.ready) return HOLDEM_OK;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(HOLDEM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    char msg[256];
+    if (holdem::selftest(msg, sizeof msg)) return fail(HOLDEM_ERR_INTERNAL, "table self-check failed: %s", msg);
+    const Tables &t = get_tables();
+    TableImage im = make_image(t);
+    CUDA_TRY(cudaMalloc(&S.image, im.bytes.size()));
+    CUDA_TRY(cudaMemcpy(S.image, im.bytes.data(), im.bytes.size(), cudaMemcpyHostToDevice));
+    S.T.flush = reinterpret_cast<const uint16_t *>(S.image + im.off_flush);
+    S.T.pairs = reinterpret_cast<const uint16_t *>(S.image + im.off_pairs);
+    for (int i = 0; i < 3; ++i) {
+        NfHash &h = S.T.nf[i];
+        h.disp = reinterpret_cast<const uint16_t *>(S.image + im.off_disp[i]);
+        h.val = reinterpret_cast<const uint16_t *>(S.image + im.off_val[i]);
+        h.mul_b = t.nf[i].mul_b;
+        h.mul_s = t.nf[i].mul_s;
+        h.bshift = 32 - t.nf[i].bucket_bits;
+        h.sshift = 32 - t.nf[i].slot_bits;
+        h.smask = (1u << t.nf[i].slot_bits) - 1u;
+        S.T.disp_entries[i] = (uint32_t)t.nf[i].disp.size();
+        S.T.val_entries[i] = (uint32_t)t.nf[i].val.size();
+    }
+    CUDA_TRY(cudaMalloc(&S.flags, kFlagRing * sizeof(int)));
+    CUDA_TRY(cudaMemset(S.flags, 0, kFlagRing * sizeof(int)));
+    S.sms = prop.multiProcessorCount;
+    S.ready = true;
+    return HOLDEM_OK;
+}
+
+int holdem_sm_count(int device) {
+    if (device < 0 || device >= kMaxDevices || !g_dev[device].ready)
+        return fail(HOLDEM_ERR_NOT_INIT, "holdem_init(%d) has not been called", device);
+    return g_dev[device].sms;
+}
+
+// ---- evaluator ---------------------------------------------------------------------------------------------------
+int holdem_eval_batch(const uint8_t *d_cards, int n_cards, int64_t n, uint16_t *d_rank_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_cards || !d_rank_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (n_cards < 5 || n_cards > 7)
+        return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 5, 6 or 7 (got %d): Evaluator.hand_size_map", n_cards);
+    CUDA_TRY(launch_eval_batch(S->T, d_cards, n_cards, n, d_rank_out, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_eval_batch_host(const uint8_t *h_cards, int n_cards, int64_t n, uint16_t *h_rank_out) {
+    if (n < 0 || (n > 0 && (!h_cards || !h_rank_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (n_cards < 5 || n_cards > 7) return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 5, 6 or 7 (got %d)", n_cards);
+    int rc = host_pipeline(h_cards, 8, h_rank_out, 2, n, 1 << 22,
+                           [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
+                               return launch_eval_batch(S.T, d_in, n_cards, rows, (uint16_t *)d_out, S.sms, st);
+                           });
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_rank_out[i] == 0) return fail(HOLDEM_ERR_BAD_INPUT, "row %lld is malformed", (long long)i);
+    return HOLDEM_OK;
+}
+
+int holdem_exhaustive7(uint64_t *d_hist, uint64_t *d_sums, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (!d_hist || !d_sums) return fail(HOLDEM_ERR_BAD_ARG, "null pointer");
+    CUDA_TRY(launch_exhaustive7(S->T, d_hist, d_sums, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_exhaustive7_host(uint64_t *h_hist, uint64_t *h_sums) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (!h_hist || !h_sums) return fail(HOLDEM_ERR_BAD_ARG, "null pointer");
+    std::lock_guard<std::mutex> lock(S->host_mu);
+    rc = ensure_host_buffers(*S, 256, 7465 * 8);
+    if (rc) return rc;
+    uint64_t *d = reinterpret_cast<uint64_t *>(S->d_buf);
+    CUDA_TRY(launch_exhaustive7(S->T, d, d + 7463, S->sms, S->streams[0]));
+    CUDA_TRY(cudaMemcpyAsync(h_hist, d, 7463 * 8, cudaMemcpyDeviceToHost, S->streams[0]));
+    CUDA_TRY(cudaMemcpyAsync(h_sums, d + 7463, 2 * 8, cudaMemcpyDeviceToHost, S->streams[0]));
+    CUDA_TRY(cudaStreamSynchronize(S->streams[0]));
+    return HOLDEM_OK;
+}
+
+// ---- literal ranker ------------------------------------------------------------------------------------------------
+int holdem_category_batch(const uint8_t *d_cards, int n_cards, int row_stride, int64_t n, uint8_t *d_cat_out,
+                          void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_cards || !d_cat_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (n_cards < 2 || n_cards > 9 || row_stride < n_cards)
+        return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 2..9 and row_stride >= n_cards (got %d, %d)", n_cards, row_stride);
+    CUDA_TRY(launch_category_batch(d_cards, n_cards, row_stride, n, d_cat_out, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_category_batch_host(const uint8_t *h_cards, int n_cards, int row_stride, int64_t n, uint8_t *h_cat_out) {
+    if (n < 0 || (n > 0 && (!h_cards || !h_cat_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (n_cards < 2 || n_cards > 9 || row_stride < n_cards)
+        return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 2..9 and row_stride >= n_cards (got %d, %d)", n_cards, row_stride);
+    int rc = host_pipeline(h_cards, (size_t)row_stride, h_cat_out, 1, n, 1 << 22,
+                           [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
+                               return launch_category_batch(d_in, n_cards, row_stride, rows, d_out, S.sms, st);
+                           });
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_cat_out[i] == 0xFF) return fail(HOLDEM_ERR_BAD_INPUT, "row %lld is malformed", (long long)i);
+    return HOLDEM_OK;
+}
+
+// ---- HS / HP ---------------------------------------------------------------------------------------------------------
+static int check_mode(int mode) {
+    if (mode != HOLDEM_MODE_TREYS && mode != HOLDEM_MODE_REFERENCE)
+        return fail(HOLDEM_ERR_BAD_ARG, "unknown mode %d", mode);
+    return HOLDEM_OK;
+}
+
+int holdem_hs_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if ((rc = check_mode(mode))) return rc;
+    CUDA_TRY(launch_hs_batch(S->T, d_sit, n, mode, d_out, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out) {
+    if (n < 0 || (n > 0 && (!h_sit || !h_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    rc = host_pipeline(h_sit, 8, h_out, 12, n, 1 << 20,
+                       [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
+                           return launch_hs_batch(S.T, d_in, rows, mode, (uint32_t *)d_out, S.sms, st);
+                       });
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_out[i * 3] == HOLDEM_BAD_ROW) return fail(HOLDEM_ERR_BAD_INPUT, "situation %lld is malformed", (long long)i);
+    return HOLDEM_OK;
+}
+
+// Treys mode: the deduplicating flop kernel takes every 3-card-board row; turn/river rows (if it saw any) are finished
+// by the plain-enumeration kernel.  Reference mode: plain enumeration only.
+static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out,
+                               cudaStream_t st) {
+    if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, nullptr, 0, st);
+    int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    cudaError_t e = launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, st);
+    if (e != cudaSuccess) return e;
+    return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
+}
+
+int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if ((rc = check_mode(mode))) return rc;
+    CUDA_TRY(hp_dispatch(*S, d_sit, n, mode, d_out, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if ((rc = check_mode(mode))) return rc;
+    CUDA_TRY(launch_hp_direct(S->T, d_sit, n, mode, d_out, S->sms, nullptr, 0, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out) {
+    if (n < 0 || (n > 0 && (!h_sit || !h_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    rc = host_pipeline(h_sit, 8, h_out, 64, n, 1 << 15,
+                       [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
+                           return hp_dispatch(S, d_in, rows, mode, (uint32_t *)d_out, st);
+                       });
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_out[i * 16 + 15] == HOLDEM_BAD_ROW) return fail(HOLDEM_ERR_BAD_INPUT, "situation %lld is malformed", (long long)i);
+    return HOLDEM_OK;
+}
+
+// ---- micro-benchmark ---------------------------------------------------------------------------------------------------
+int holdem_microbench_smem_gather(int table_bytes, int iters, int pattern, int blocks_per_sm, int threads,
+                                  float *elapsed_ms, double *lookups, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (table_bytes < 1024 || table_bytes > 200 * 1024 || (table_bytes & (table_bytes - 1)) || iters < 1 ||
+        threads < 32 || threads > 1024 || (threads & 31) || blocks_per_sm < 1 || !elapsed_ms || !lookups)
+        return fail(HOLDEM_ERR_BAD_ARG, "bad micro-benchmark arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int blocks = S->sms * blocks_per_sm;
+    CUDA_TRY(launch_smem_gather(table_bytes, iters, pattern, blocks, threads, st));  // warm-up
+    CUDA_TRY(cudaEventRecord(e0, st));
+    CUDA_TRY(launch_smem_gather(table_bytes, iters, pattern, blocks, threads, st));
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+    *lookups = 4.0 * (double)iters * (double)blocks * (double)threads;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HOLDEM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// kernels_eval.cu -- batched 5/6/7-card Treys evaluator, literal category ranker, exhaustive 7-card sweep and the
+// shared-memory gather micro-benchmark.  sm_100a only.
+//
+// Replaces treys.Evaluator.evaluate (reached from HandCalculations.py:229-240, pokerlib_to_treys.py:15-21) and
+// CalculateHandRankValue (HandCalculations.py:45-82) for batches of hands.
+#include "device_common.cuh"
+#include "launch.h"
+
+namespace holdem {
+
+// =====================================================================================================================
+// Batched evaluator.  One hand per thread per grid-stride step; the input is one coalesced 8-byte load per hand, the
+// output one 2-byte store: 10 algorithmic HBM bytes per evaluation.
+// kShared: the flush table, the displacement table and the value table of the hand size are staged in shared memory
+// (16 KB + 4..32 KB + 16..128 KB) once per persistent CTA; otherwise they are read through L1/L2 (small batches).
+// =====================================================================================================================
+template <int NC>
+__device__ __forceinline__ uint32_t eval_row(uint2 w, const uint32_t *cardkey, const uint16_t *flush,
+                                             const NfHash &h) {
+    uint32_t key = 0, lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        uint32_t c = (k < 4) ? ((w.x >> (8 * k)) & 0xFFu) : ((w.y >> (8 * (k - 4))) & 0xFFu);
+        key += cardkey[c & 63u];
+        lo |= shl_clamp(1u, c);
+        hi |= shl_clamp(1u, c - 32u);
+    }
+    // duplicates or cards > 51 leave fewer than NC bits below bit 52
+    bool bad = (__popc(lo) + __popc(hi & 0xFFFFFu) != NC) || (hi >> 20);
+    uint64_t cards = ((uint64_t)hi << 32) | lo;
+    uint32_t r = treys_rank(h, flush, key, cards);
+    return bad ? 0u : r;
+}
+
+template <int NC, bool kShared>
+__global__ void __launch_bounds__(kShared ? 1024 : 256, 1)
+eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const NfHash &g = T.nf[NC - 5];
+    NfHash h = g;
+    const uint16_t *flush = T.flush;
+    uint32_t *s_cardkey = reinterpret_cast<uint32_t *>(smem);                 // 64 entries
+    if (threadIdx.x < 64) s_cardkey[threadIdx.x] = threadIdx.x < 52 ? c_rank_key[threadIdx.x % 13] : 0u;
+    if (kShared) {
+        uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 256);
+        uint16_t *s_disp = s_flush + kFlushEntries;
+        uint16_t *s_val = s_disp + T.disp_entries[NC - 5];
+        // 16-byte vector copies; every section is 16-byte aligned and a multiple of 16 bytes long
+        const uint4 *src;
+        uint4 *dst;
+        src = reinterpret_cast<const uint4 *>(T.flush); dst = reinterpret_cast<uint4 *>(s_flush);
+        for (uint32_t i = threadIdx.x; i < kFlushEntries / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(g.disp); dst = reinterpret_cast<uint4 *>(s_disp);
+        for (uint32_t i = threadIdx.x; i < T.disp_entries[NC - 5] / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(g.val); dst = reinterpret_cast<uint4 *>(s_val);
+        for (uint32_t i = threadIdx.x; i < T.val_entries[NC - 5] / 8; i += blockDim.x) dst[i] = src[i];
+        h.disp = s_disp;
+        h.val = s_val;
+        flush = s_flush;
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint2 w = __ldg(cards + i);
+        out[i] = (uint16_t)eval_row<NC>(w, s_cardkey, flush, h);
+    }
+}
+
+size_t eval_smem_bytes(const DevTables &T, int nc) {
+    return 256 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
+}
+
+template <int NC>
+static cudaError_t launch_eval_nc(const DevTables &T, const uint8_t *cards, int64_t n, uint16_t *out, int sms,
+                                  cudaStream_t st) {
+    const uint2 *c2 = reinterpret_cast<const uint2 *>(cards);
+    if (n >= (int64_t)sms * 2048) {  // enough work to amortise staging ~50-180 KB per CTA
+        size_t smem = eval_smem_bytes(T, NC);
+        cudaError_t e = cudaFuncSetAttribute(eval_batch_kernel<NC, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        eval_batch_kernel<NC, true><<<sms, 1024, smem, st>>>(c2, n, out, T);
+    } else {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > sms * 8) blocks = sms * 8;
+        eval_batch_kernel<NC, false><<<blocks, 256, 256, st>>>(c2, n, out, T);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_batch(const DevTables &T, const uint8_t *cards, int n_cards, int64_t n, uint16_t *out,
+                              int sms, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    switch (n_cards) {
+        case 5: return launch_eval_nc<5>(T, cards, n, out, sms, st);
+        case 6: return launch_eval_nc<6>(T, cards, n, out, sms, st);
+        case 7: return launch_eval_nc<7>(T, cards, n, out, sms, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// =====================================================================================================================
+// Literal category ranker over rows of n_cards (2..9) cards, duplicates allowed.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+category_batch_kernel(const uint8_t *__restrict__ cards, int n_cards, int row_stride, int64_t n,
+                      uint8_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t *row = cards + i * row_stride;
+        LitHand h = {0, 0, 0, 0, 0};
+        bool bad = false;
+        for (int k = 0; k < n_cards; ++k) {
+            uint32_t c = row[k];
+            bad |= c > 51u;
+            lit_add_card(h, c > 51u ? 0u : c);
+        }
+        out[i] = bad ? 0xFFu : (uint8_t)lit_category(h);
+    }
+}
+
+cudaError_t launch_category_batch(const uint8_t *cards, int n_cards, int row_stride, int64_t n, uint8_t *out,
+                                  int sms, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > sms * 8) blocks = sms * 8;
+    category_batch_kernel<<<blocks, 256, 0, st>>>(cards, n_cards, row_stride, n, out);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Exhaustive sweep over all C(52,7) = 133,784,560 hands (BASELINE.json configs[1]), enumerated in-kernel in colex
+// order: hand number i <-> c0 < c1 < ... < c6 with i = sum_k C(c_k, k+1).  Each thread unranks the start of its
+// chunk once and then steps to the successor combination.  All three tables live in shared memory next to a
+// per-CTA rank histogram.
+// =====================================================================================================================
+constexpr int64_t kHands7 = 133784560;
+constexpr int kChunk = 512;  // hands per thread
+
+__device__ __forceinline__ uint32_t binom_dev(const uint32_t *bt, int n, int k) { return bt[n * 8 + k]; }
+
+__global__ void __launch_bounds__(1024, 1)
+exhaustive7_kernel(unsigned long long *__restrict__ hist, unsigned long long *__restrict__ sums, DevTables T) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *s_cardkey = reinterpret_cast<uint32_t *>(smem);           // 64
+    uint32_t *s_binom = s_cardkey + 64;                                 // [53][8]
+    uint32_t *s_hist = s_binom + 53 * 8;                                // [7464]
+    uint16_t *s_flush = reinterpret_cast<uint16_t *>(s_hist + 7464);
+    uint16_t *s_disp = s_flush + kFlushEntries;
+    uint16_t *s_val = s_disp + T.disp_entries[2];
+    if (threadIdx.x < 64) s_cardkey[threadIdx.x] = threadIdx.x < 52 ? c_rank_key[threadIdx.x % 13] : 0u;
+    if (threadIdx.x < 53) {  // Pascal row per thread
+        uint64_t v = 1;
+        int nrow = threadIdx.x;
+        for (int k = 0; k < 8; ++k) {
+            s_binom[nrow * 8 + k] = k > nrow ? 0u : (uint32_t)v;
+            v = v * (uint64_t)(nrow - k) / (uint64_t)(k + 1);
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < 7464; i += blockDim.x) s_hist[i] = 0;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(T.flush);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_flush);
+        for (uint32_t i = threadIdx.x; i < kFlushEntries / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(T.nf[2].disp); dst = reinterpret_cast<uint4 *>(s_disp);
+        for (uint32_t i = threadIdx.x; i < T.disp_entries[2] / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(T.nf[2].val); dst = reinterpret_cast<uint4 *>(s_val);
+        for (uint32_t i = threadIdx.x; i < T.val_entries[2] / 8; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    NfHash h = T.nf[2];
+    h.disp = s_disp;
+    h.val = s_val;
+
+    unsigned long long sum = 0, sumsq = 0;
+    const int64_t n_chunks = (kHands7 + kChunk - 1) / kChunk;
+    for (int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; chunk < n_chunks;
+         chunk += (int64_t)gridDim.x * blockDim.x) {
+        int64_t first = chunk * kChunk;
+        int64_t last = first + kChunk < kHands7 ? first + kChunk : kHands7;
+        // unrank `first` in the combinatorial number system
+        int c[7];
+        {
+            uint32_t rem = (uint32_t)first;
+            int hiC = 51;
+            for (int k = 6; k >= 0; --k) {
+                int v = hiC;
+                while (binom_dev(s_binom, v, k + 1) > rem) --v;
+                c[k] = v;
+                rem -= binom_dev(s_binom, v, k + 1);
+                hiC = v - 1;
+            }
+        }
+        for (int64_t i = first; i < last; ++i) {
+            uint32_t key = 0, lo = 0, hi = 0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                key += s_cardkey[c[k]];
+                lo |= shl_clamp(1u, (uint32_t)c[k]);
+                hi |= shl_clamp(1u, (uint32_t)c[k] - 32u);
+            }
+            uint32_t r = treys_rank(h, s_flush, key, ((uint64_t)hi << 32) | lo);
+            atomicAdd(&s_hist[r], 1u);
+            sum += r;
+            sumsq += (unsigned long long)r * r;
+            // successor in colex order: bump the lowest index that has room, reset everything below it
+            if (c[0] + 1 < c[1]) { c[0]++; }
+            else if (c[1] + 1 < c[2]) { c[1]++; c[0] = 0; }
+            else if (c[2] + 1 < c[3]) { c[2]++; c[0] = 0; c[1] = 1; }
+            else if (c[3] + 1 < c[4]) { c[3]++; c[0] = 0; c[1] = 1; c[2] = 2; }
+            else if (c[4] + 1 < c[5]) { c[4]++; c[0] = 0; c[1] = 1; c[2] = 2; c[3] = 3; }
+            else if (c[5] + 1 < c[6]) { c[5]++; c[0] = 0; c[1] = 1; c[2] = 2; c[3] = 3; c[4] = 4; }
+            else { c[6]++; c[0] = 0; c[1] = 1; c[2] = 2; c[3] = 3; c[4] = 4; c[5] = 5; }
+        }
+    }
+    // block reduction of the two checksums, then one global atomic each
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
+        sumsq += __shfl_down_sync(0xFFFFFFFFu, sumsq, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sums[0], sum);
+        atomicAdd(&sums[1], sumsq);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 7463; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, 7463 * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(sums, 0, 2 * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    size_t smem = (64 + 53 * 8 + 7464) * 4 + 2 * (size_t)(kFlushEntries + T.disp_entries[2] + T.val_entries[2]);
+    e = cudaFuncSetAttribute(exhaustive7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    exhaustive7_kernel<<<sms, 1024, smem, st>>>(reinterpret_cast<unsigned long long *>(hist),
+                                               reinterpret_cast<unsigned long long *>(sums), T);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// Shared-memory gather micro-benchmark: the measured "lookup roofline" (SURVEY.md section 8d).  Every lane of a full
+// grid issues `iters` x 4 independent chains of dependent uint16 gathers over a table of the production footprint.
+// =====================================================================================================================
+__global__ void __launch_bounds__(1024)
+smem_gather_kernel(int table_entries, int iters, int pattern, uint32_t *__restrict__ sink) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
+    uint32_t x = 0x9E3779B9u * (blockIdx.x + 1);
+    for (int i = threadIdx.x; i < table_entries; i += blockDim.x) {
+        uint32_t v = (uint32_t)i * 2654435761u + x;
+        v ^= v >> 15; v *= 0x2C1B3C6Du; v ^= v >> 12;
+        tab[i] = (uint16_t)v;
+    }
+    __syncthreads();
+    const uint32_t mask = (uint32_t)table_entries - 1;  // power of two
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t a0 = threadIdx.x * 7919u + 1, a1 = a0 * 31u + 7, a2 = a1 * 31u + 7, a3 = a2 * 31u + 7;
+    uint32_t acc = 0;
+    if (pattern == 0) {  // uniformly random indices: bank conflicts as they fall
+        for (int it = 0; it < iters; ++it) {
+            uint32_t v0 = tab[a0 & mask], v1 = tab[a1 & mask], v2 = tab[a2 & mask], v3 = tab[a3 & mask];
+            a0 = a0 * 1664525u + v0; a1 = a1 * 1664525u + v1; a2 = a2 * 1664525u + v2; a3 = a3 * 1664525u + v3;
+            acc += v0 ^ v1 ^ v2 ^ v3;
+        }
+    } else {             // conflict-free: warp-uniform random base, lane-strided 32-bit words
+        uint32_t w = (threadIdx.x >> 5) * 7919u + 1;
+        uint32_t b0 = w, b1 = w * 31u + 7, b2 = b1 * 31u + 7, b3 = b2 * 31u + 7;
+        for (int it = 0; it < iters; ++it) {
+            uint32_t v0 = tab[((b0 << 6) + 2 * lane) & mask], v1 = tab[((b1 << 6) + 2 * lane) & mask];
+            uint32_t v2 = tab[((b2 << 6) + 2 * lane) & mask], v3 = tab[((b3 << 6) + 2 * lane) & mask];
+            // keep the next base warp-uniform but data dependent
+            b0 = b0 * 1664525u + __shfl_sync(0xFFFFFFFFu, v0, 0);
+            b1 = b1 * 1664525u + __shfl_sync(0xFFFFFFFFu, v1, 0);
+            b2 = b2 * 1664525u + __shfl_sync(0xFFFFFFFFu, v2, 0);
+            b3 = b3 * 1664525u + __shfl_sync(0xFFFFFFFFu, v3, 0);
+            acc += v0 ^ v1 ^ v2 ^ v3;
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc;  // never true in practice; keeps the loop alive
+}
+
+cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int blocks, int threads, cudaStream_t st) {
+    static uint32_t *sink = nullptr;
+    if (!sink) {
+        cudaError_t e = cudaMalloc(&sink, 4);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaFuncSetAttribute(smem_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, table_bytes);
+    if (e != cudaSuccess) return e;
+    smem_gather_kernel<<<blocks, threads, table_bytes, st>>>(table_bytes / 2, iters, pattern, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace holdem

@@ -1,0 +1,29 @@
+// launch.h -- host-callable launchers of the kernels (internal to the library; the public surface is
+// include/holdem_b200.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace holdem {
+
+struct DevTables;
+
+constexpr uint32_t kFlushEntries = 8192;
+
+cudaError_t launch_eval_batch(const DevTables &T, const uint8_t *cards, int n_cards, int64_t n, uint16_t *out,
+                              int sms, cudaStream_t st);
+cudaError_t launch_category_batch(const uint8_t *cards, int n_cards, int row_stride, int64_t n, uint8_t *out,
+                                  int sms, cudaStream_t st);
+cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st);
+cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int blocks, int threads, cudaStream_t st);
+
+cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
+                            cudaStream_t st);
+// run_flag: optional device int; the kernel exits at once when *run_flag == 0.  skip_flops: leave 3-card-board rows alone.
+cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
+                             const int *run_flag, int skip_flops, cudaStream_t st);
+// Treys-mode flop rows only; sets *other_rows_flag when it met turn/river rows (left untouched for launch_hp_direct).
+cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
+                                 int *other_rows_flag, cudaStream_t st);
+
+}  // namespace holdem

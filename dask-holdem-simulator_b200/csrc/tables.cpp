@@ -1,0 +1,288 @@
+// tables.cpp -- see tables.h.  Host only (no CUDA): compiled by nvcc's host compiler into the same library.
+#include "tables.h"
+
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+
+namespace holdem {
+namespace {
+
+// Strength of a five-card class as one integer: category in the top digit, then up to five tie-break ranks,
+// most significant first (base 16).  Larger = stronger.  Categories: 8 straight flush, 7 quads, 6 full house,
+// 5 flush, 4 straight, 3 trips, 2 two pair, 1 pair, 0 high card.
+uint32_t straight_top(uint32_t mask) {  // 0 if the 5-bit mask is not a straight, else 1 + rank of its top card
+    if (mask == 0x100Fu) return 1 + 3;  // A-2-3-4-5: five high
+    for (int lo = 0; lo + 4 <= 12; ++lo)
+        if (mask == (0x1Fu << lo)) return 1 + lo + 4;
+    return 0;
+}
+
+uint32_t strength5(const int cnt[13], bool suited) {
+    // ranks ordered by (multiplicity, rank) descending
+    std::array<int, 5> order{};
+    int m = 0;
+    uint32_t mask = 0;
+    for (int c = 4; c >= 1; --c)
+        for (int r = 12; r >= 0; --r)
+            if (cnt[r] == c) order[m++] = r;
+    for (int r = 0; r < 13; ++r)
+        if (cnt[r]) mask |= 1u << r;
+    int top = cnt[order[0]], second = m > 1 ? cnt[order[1]] : 0;
+    uint32_t cat;
+    uint32_t tie = 0;
+    if (top == 1) {
+        uint32_t st = straight_top(mask);
+        if (st) {
+            cat = suited ? 8 : 4;
+            tie = (st - 1) << 16;
+            return (cat << 20) | tie;
+        }
+        cat = suited ? 5 : 0;
+    } else if (top == 4) cat = 7;
+    else if (top == 3) cat = second == 2 ? 6 : 3;
+    else cat = second == 2 ? 2 : 1;
+    for (int i = 0; i < m; ++i) tie |= (uint32_t)order[i] << (16 - 4 * i);
+    return (cat << 20) | tie;
+}
+
+struct Class5 {
+    uint32_t strength;
+    uint32_t key;   // additive key (unsuited) or 13-bit mask (suited)
+    bool suited;
+};
+
+bool build_hash(const std::vector<uint32_t> &keys, const std::vector<uint16_t> &vals, int bucket_bits,
+                int slot_bits, PerfectHash &ph) {
+    const uint32_t nb = 1u << bucket_bits, ns = 1u << slot_bits;
+    uint32_t mul = 0x9E3779B1u;
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        uint32_t mul_b = mul | 1u;
+        mul = mul * 0x2545F491u + 0x6B43A9B5u;
+        uint32_t mul_s = mul | 1u;
+        mul = mul * 0x2545F491u + 0x6B43A9B5u;
+        std::vector<std::vector<uint32_t>> buckets(nb);
+        for (uint32_t i = 0; i < keys.size(); ++i) buckets[(keys[i] * mul_b) >> (32 - bucket_bits)].push_back(i);
+        std::vector<uint32_t> order(nb);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint32_t a, uint32_t b) { return buckets[a].size() > buckets[b].size(); });
+        std::vector<uint16_t> val(ns, 0), disp(nb, 0);
+        std::vector<uint8_t> used(ns, 0);
+        bool ok = true;
+        for (uint32_t b : order) {
+            const auto &items = buckets[b];
+            if (items.empty()) break;
+            std::vector<uint32_t> h(items.size());
+            for (size_t k = 0; k < items.size(); ++k) h[k] = (keys[items[k]] * mul_s) >> (32 - slot_bits);
+            uint32_t d = 0;
+            for (; d < ns && d < 65536u; ++d) {
+                bool fits = true;
+                for (size_t k = 0; k < h.size() && fits; ++k) {
+                    uint32_t s = (h[k] + d) & (ns - 1);
+                    if (used[s]) fits = false;
+                    for (size_t q = 0; q < k && fits; ++q)
+                        if (((h[q] + d) & (ns - 1)) == s) fits = false;
+                }
+                if (fits) break;
+            }
+            if (d >= ns || d >= 65536u) { ok = false; break; }
+            disp[b] = (uint16_t)d;
+            for (size_t k = 0; k < h.size(); ++k) {
+                uint32_t s = (h[k] + d) & (ns - 1);
+                used[s] = 1;
+                val[s] = vals[items[k]];
+            }
+        }
+        if (!ok) continue;
+        ph.mul_b = mul_b; ph.mul_s = mul_s;
+        ph.bucket_bits = bucket_bits; ph.slot_bits = slot_bits;
+        ph.disp = std::move(disp); ph.val = std::move(val);
+        return true;
+    }
+    return false;
+}
+
+struct Builder {
+    Tables t;
+    bool ok = false;
+    char err[256] = {0};
+
+    void run() {
+        // ---- 1. the 7462 five-card classes -----------------------------------------------------------
+        std::vector<Class5> classes;
+        int cnt[13];
+        // unsuited rank multisets of size 5, at most 4 of a rank
+        std::vector<int> seq(5);
+        for (seq[0] = 0; seq[0] < 13; ++seq[0])
+            for (seq[1] = seq[0]; seq[1] < 13; ++seq[1])
+                for (seq[2] = seq[1]; seq[2] < 13; ++seq[2])
+                    for (seq[3] = seq[2]; seq[3] < 13; ++seq[3])
+                        for (seq[4] = seq[3]; seq[4] < 13; ++seq[4]) {
+                            if (seq[0] == seq[4]) continue;  // five of a rank
+                            std::memset(cnt, 0, sizeof cnt);
+                            uint32_t key = 0;
+                            for (int r : seq) { cnt[r]++; key += kRankKey[r]; }
+                            classes.push_back({strength5(cnt, false), key, false});
+                        }
+        // suited: 5 distinct ranks
+        for (uint32_t mask = 0; mask < 8192; ++mask) {
+            if (__builtin_popcount(mask) != 5) continue;
+            std::memset(cnt, 0, sizeof cnt);
+            for (int r = 0; r < 13; ++r)
+                if (mask >> r & 1) cnt[r] = 1;
+            classes.push_back({strength5(cnt, true), mask, true});
+        }
+        if ((int)classes.size() != kNumClasses) { std::snprintf(err, sizeof err, "class count %zu", classes.size()); return; }
+        std::sort(classes.begin(), classes.end(),
+                  [](const Class5 &a, const Class5 &b) { return a.strength > b.strength; });
+        for (size_t i = 1; i < classes.size(); ++i)
+            if (classes[i].strength == classes[i - 1].strength) { std::snprintf(err, sizeof err, "strength tie"); return; }
+
+        // ---- 2. dense scratch tables keyed directly by the additive key -----------------------------------
+        uint32_t max_key[3] = {0, 0, 0};
+        for (int n = 5; n <= 7; ++n) {  // largest sum: four aces + (n-4) kings
+            max_key[n - 5] = 4 * kRankKey[12] + (n - 4) * kRankKey[11];
+        }
+        std::vector<uint16_t> dense[3];
+        for (int i = 0; i < 3; ++i) dense[i].assign(max_key[i] + 1, 0);
+        t.flush.assign(kFlushTableSize, 0);
+        for (size_t i = 0; i < classes.size(); ++i) {
+            uint16_t rank = (uint16_t)(i + 1);
+            if (classes[i].suited) t.flush[classes[i].key] = rank;
+            else dense[0][classes[i].key] = rank;
+        }
+        // flush table for 6..13 suited cards: best five = minimum over dropping one card
+        for (uint32_t mask = 0; mask < 8192; ++mask) {  // ascending order: sub-masks are smaller numbers
+            if (__builtin_popcount(mask) <= 5) continue;
+            uint16_t best = 0xFFFF;
+            for (int r = 0; r < 13; ++r)
+                if (mask >> r & 1) best = std::min(best, t.flush[mask & ~(1u << r)]);
+            t.flush[mask] = best;
+        }
+        // ---- 3. 6- and 7-card multisets: drop-one-card dynamic programme ---------------------------------------
+        std::vector<uint32_t> keys[3];
+        std::vector<uint16_t> vals[3];
+        for (int n = 5; n <= 7; ++n) {
+            std::vector<int> s(n, 0);
+            // iterate non-decreasing sequences of length n over 0..12
+            while (true) {
+                std::memset(cnt, 0, sizeof cnt);
+                uint32_t key = 0;
+                bool valid = true;
+                for (int r : s) { if (++cnt[r] > 4) valid = false; key += kRankKey[r]; }
+                if (valid) {
+                    uint16_t v;
+                    if (n == 5) v = dense[0][key];
+                    else {
+                        v = 0xFFFF;
+                        for (int r = 0; r < 13; ++r)
+                            if (cnt[r]) v = std::min(v, dense[n - 6][key - kRankKey[r]]);
+                        if (dense[n - 5][key] != 0) { std::snprintf(err, sizeof err, "key collision n=%d", n); return; }
+                        dense[n - 5][key] = v;
+                    }
+                    if (v == 0 || v == 0xFFFF) { std::snprintf(err, sizeof err, "missing class n=%d", n); return; }
+                    keys[n - 5].push_back(key);
+                    vals[n - 5].push_back(v);
+                }
+                int i = n - 1;
+                while (i >= 0 && s[i] == 12) --i;
+                if (i < 0) break;
+                int v2 = s[i] + 1;
+                for (int j = i; j < n; ++j) s[j] = v2;
+            }
+            t.n_keys[n - 5] = (int)keys[n - 5].size();
+        }
+        // distinctness of the additive keys within each size
+        for (int i = 0; i < 3; ++i) {
+            std::vector<uint32_t> k = keys[i];
+            std::sort(k.begin(), k.end());
+            if (std::adjacent_find(k.begin(), k.end()) != k.end()) { std::snprintf(err, sizeof err, "duplicate key"); return; }
+        }
+        // ---- 4. perfect hashes --------------------------------------------------------------------------------
+        const int bucket_bits[3] = {11, 13, 14}, slot_bits[3] = {13, 15, 16};
+        for (int i = 0; i < 3; ++i)
+            if (!build_hash(keys[i], vals[i], bucket_bits[i], slot_bits[i], t.nf[i])) {
+                std::snprintf(err, sizeof err, "perfect hash failed n=%d", i + 5);
+                return;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (size_t k = 0; k < keys[i].size(); ++k)
+                if (t.nf[i].lookup(keys[i][k]) != vals[i][k]) { std::snprintf(err, sizeof err, "hash verify n=%d", i + 5); return; }
+        // ---- 5. colex pair table -------------------------------------------------------------------------------
+        t.pairs.resize(kMaxPairs);
+        int p = 0;
+        for (int j = 1; j < 52; ++j)
+            for (int i = 0; i < j; ++i) t.pairs[p++] = (uint16_t)(i | (j << 8));
+        ok = true;
+    }
+};
+
+Builder &builder() {
+    static Builder b;
+    static std::once_flag once;
+    std::call_once(once, [] { b.run(); });
+    return b;
+}
+
+uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+}  // namespace
+
+const Tables &get_tables() { return builder().t; }
+
+int selftest(char *msg, int msg_len) {
+    Builder &b = builder();
+    auto fail = [&](const char *m) {
+        if (msg && msg_len > 0) std::snprintf(msg, msg_len, "%s", m);
+        return 1;
+    };
+    if (!b.ok) return fail(b.err[0] ? b.err : "table build failed");
+    const Tables &t = b.t;
+    if (t.n_keys[0] != 6175 || t.n_keys[1] != 18395 || t.n_keys[2] != 49205) return fail("multiset counts");
+    // every rank 1..7462 appears exactly once among the 5-card flush masks and the 5-card unsuited multisets
+    std::vector<int> seen(kNumClasses + 1, 0);
+    int n_flush5 = 0;
+    for (uint32_t m = 0; m < 8192; ++m)
+        if (__builtin_popcount(m) == 5) { seen[t.flush[m]]++; n_flush5++; }
+    if (n_flush5 != 1287) return fail("flush count");
+    for (uint16_t v : t.nf[0].val)
+        if (v) seen[v]++;
+    for (int r = 1; r <= kNumClasses; ++r)
+        if (seen[r] != 1) return fail("classes are not a bijection onto 1..7462");
+    // category boundaries (sizes 10/156/156/1277/10/858/858/2860/1277)
+    if (t.flush[0x1F00] != 1 || t.flush[0x100F] != 10 || t.flush[0x1F00 >> 1] != 2) return fail("straight flush ranks");
+    if (t.flush[0x1E80] != 323 || t.flush[0x002F] != 1599) return fail("flush boundaries");
+    uint32_t k_quads_top = 4 * kRankKey[12] + kRankKey[11];   // AAAA K
+    uint32_t k_worst = kRankKey[5] + kRankKey[3] + kRankKey[2] + kRankKey[1] + kRankKey[0];  // 7 5 4 3 2
+    uint32_t k_broadway = kRankKey[12] + kRankKey[11] + kRankKey[10] + kRankKey[9] + kRankKey[8];
+    if (t.nf[0].lookup(k_quads_top) != 11) return fail("quads boundary");
+    if (t.nf[0].lookup(k_worst) != 7462) return fail("worst hand");
+    if (t.nf[0].lookup(k_broadway) != 1600) return fail("broadway");
+    if (t.pairs[0] != (0 | 1 << 8) || t.pairs[1] != (0 | 2 << 8) || t.pairs[2] != (1 | 2 << 8)) return fail("pairs");
+    if (msg && msg_len > 0) msg[0] = 0;
+    return 0;
+}
+
+TableImage make_image(const Tables &t) {
+    TableImage im;
+    auto append = [&](const void *src, size_t n) {
+        uint32_t off = align16((uint32_t)im.bytes.size());
+        im.bytes.resize(off + n);
+        std::memcpy(im.bytes.data() + off, src, n);
+        return off;
+    };
+    im.off_flush = append(t.flush.data(), t.flush.size() * 2);
+    im.off_pairs = append(t.pairs.data(), t.pairs.size() * 2);
+    for (int i = 0; i < 3; ++i) {
+        im.off_disp[i] = append(t.nf[i].disp.data(), t.nf[i].disp.size() * 2);
+        im.off_val[i] = append(t.nf[i].val.data(), t.nf[i].val.size() * 2);
+    }
+    im.bytes.resize(align16((uint32_t)im.bytes.size()));
+    return im;
+}
+
+}  // namespace holdem

@@ -1,0 +1,64 @@
+// tables.h -- host-side construction of the evaluator lookup tables (built once per process, uploaded per device).
+//
+// What the tables replace: treys.LookupTable (flush_lookup / unsuited_lookup keyed by prime products) and the
+// min-over-C(n,5) loops of treys.Evaluator._six/_seven, which the reference reaches through
+// HandCalculations.py:229-240 and pokerlib_to_treys.py:15-21.  Nothing here follows Treys' construction: the
+// 7462 five-card classes are produced by sorting explicit strength tuples (the standard poker total order, which
+// is the order Treys numbers), the 6/7-card tables are a dynamic programme over rank multisets, and the sparse
+// additive multiset keys are compressed with a hash-displace perfect hash sized for shared memory.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace holdem {
+
+// Additive rank keys: the sum over the cards of a hand identifies the rank multiset uniquely for every hand of
+// up to 7 cards with at most 4 cards per rank (checked by selftest()).  Largest 7-card sum: 7,825,759 (23 bits).
+constexpr uint32_t kRankKey[13] = {0,    1,     5,     22,     98,     453,    2031,
+                                   8698, 22854, 83661, 262349, 636345, 1479181};
+
+constexpr int kNumClasses = 7462;
+constexpr int kFlushTableSize = 8192;
+constexpr int kMaxPairs = 1326;  // C(52,2), colex order: pair p of (i<j) has p = j(j-1)/2 + i
+
+// Hash-displace perfect hash over the additive keys of one hand size:
+//   bucket = (key * mul_b) >> (32 - bucket_bits)
+//   slot   = (((key * mul_s) >> (32 - slot_bits)) + disp[bucket]) & (2^slot_bits - 1)
+//   rank   = val[slot]
+struct PerfectHash {
+    uint32_t mul_b = 0, mul_s = 0;
+    int bucket_bits = 0, slot_bits = 0;
+    std::vector<uint16_t> disp;  // [2^bucket_bits]
+    std::vector<uint16_t> val;   // [2^slot_bits], 0 = empty
+    uint32_t lookup(uint32_t key) const {
+        uint32_t b = (key * mul_b) >> (32 - bucket_bits);
+        uint32_t s = (((key * mul_s) >> (32 - slot_bits)) + disp[b]) & ((1u << slot_bits) - 1);
+        return val[s];
+    }
+};
+
+struct Tables {
+    // flush[mask]: rank of the best 5 cards of one suit whose ranks are the set bits of the 13-bit mask
+    // (straight flush 1..10 or flush 323..1599) for popcount >= 5, else 0.
+    std::vector<uint16_t> flush;
+    // nf[n-5]: rank multiset of an n-card hand (n = 5, 6, 7) -> best five-card rank ignoring suits.
+    PerfectHash nf[3];
+    // pairs[p] = i | j << 8 for the p-th pair in colex order (prefix-stable: the first C(m,2) entries are the
+    // pairs of {0..m-1} for every m).
+    std::vector<uint16_t> pairs;
+    // Statistics kept for selftest().
+    int n_keys[3] = {0, 0, 0};
+};
+
+const Tables &get_tables();  // thread-safe, builds on first use
+int selftest(char *msg, int msg_len);  // 0 = ok
+
+// Flat device image of the tables: one allocation, 16-byte aligned sections, offsets in bytes.
+struct TableImage {
+    std::vector<uint8_t> bytes;
+    uint32_t off_flush = 0, off_pairs = 0;
+    uint32_t off_disp[3] = {0, 0, 0}, off_val[3] = {0, 0, 0};
+};
+TableImage make_image(const Tables &t);
+
+}  // namespace holdem

@@ -1,0 +1,12 @@
+"""holdem_b200 -- B200-native hand-strength / hand-potential path of dask-holdem-simulator.
+
+Python mirror of the reference's interface for this path lives one directory up (HandCalculations.py,
+pokerlib_to_treys.py); this package holds the C-ABI binding and the batched / sharded entry points.
+"""
+from . import _lib  # noqa: F401
+from ._lib import HoldemError, LIB_PATH  # noqa: F401
+from .api import *  # noqa: F401,F403
+from .encoding import (pack_situations, random_situations, path_from_str, str_from_path,  # noqa: F401
+                       treys_from_path, path_from_treys, treys_from_str, path_from_poker_card,
+                       path_from_rank_major, rank_major_from_path)
+from .sharded import shard_bounds, hand_potential_counts_sharded  # noqa: F401

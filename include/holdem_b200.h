@@ -1,0 +1,128 @@
+/*
+ * holdem_b200.h -- C ABI of the B200-native hand-strength / hand-potential path.
+ *
+ * Drop-in boundary for dsowsy/dask-holdem-simulator's HandCalculations.py (reference file:line cited per
+ * entry point).  Plain pointers and sizes only: no torch, no C++ types.  The shared library is
+ * dask-holdem-simulator_b200/holdem_b200/libholdem_b200.so; the Python shim binds it with ctypes
+ * (INTEGRATION.md shows the stub).  There is NO CPU fallback: every compute entry point needs a CUDA
+ * device of compute capability 10.x and returns HOLDEM_ERR_NO_DEVICE otherwise.
+ *
+ * Card encoding (HandCalculations.py:53-54): card in [0,52), rank = card % 13 (0 = deuce .. 12 = ace),
+ * suit = card / 13 (0 c, 1 d, 2 h, 3 s).
+ *
+ * Situation row, uint8[8]:  h0 h1 b0 b1 b2 b3 b4 pad   -- absent board cards and pad are 0xFF; the board
+ * holds 3, 4 or 5 cards, contiguous from b0; all cards of a row are distinct.
+ *
+ * Result row of the HP entry points, uint32[16] (HOLDEM_HP_ROW):
+ *   [0..2]   ahead, tied, behind            HandStrength counts     (HandCalculations.py:168-173)
+ *   [3..11]  HP[3][3] row-major             HP[index][outcome]      (HandCalculations.py:213-218)
+ *   [12..14] HPTotal[3]                     per-index opponent count (HandCalculations.py:203)
+ *   [15]     number of board cards; 0xFFFFFFFF in every column marks a malformed input row
+ *
+ * mode: HOLDEM_MODE_TREYS      canonical Effective-Hand-Strength enumeration on Treys ranks (1..7462, lower
+ *                              is better): opponents C(47,2)/C(46,2)/C(45,2); runouts are the cards still to
+ *                              come drawn from the cards unseen by both players (flop 990 pairs per opponent,
+ *                              turn 44 rivers, river none).
+ *       HOLDEM_MODE_REFERENCE  HandCalculations.py exactly as written: 9-category ranker
+ *                              CalculateHandRankValue (:45-82), runouts = ALL pairs of deck \ board
+ *                              (:152-154; 1176/1128/1081), multiset semantics and quirks included.
+ *
+ * Every *_batch entry point is stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = the legacy
+ * default stream), takes DEVICE pointers and does not synchronise.  Every *_host entry point takes HOST
+ * pointers, performs the host<->device copies itself and returns after the results are in host memory.
+ * Return value: 0 on success, a negative HOLDEM_ERR_* otherwise; holdem_last_error() gives the message of the
+ * calling thread's last failure.  Nothing throws across this boundary.
+ */
+#ifndef HOLDEM_B200_H
+#define HOLDEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOLDEM_ABI_VERSION 1
+
+#define HOLDEM_MODE_TREYS 0
+#define HOLDEM_MODE_REFERENCE 1
+
+#define HOLDEM_HP_ROW 16
+#define HOLDEM_HS_ROW 3
+#define HOLDEM_BAD_ROW 0xFFFFFFFFu
+
+#define HOLDEM_OK 0
+#define HOLDEM_ERR_NO_DEVICE (-1)   /* no CUDA device / not sm_100 / driver error at init            */
+#define HOLDEM_ERR_BAD_ARG (-2)     /* null pointer, negative size, unknown mode, unsupported n_cards */
+#define HOLDEM_ERR_CUDA (-3)        /* a CUDA runtime call failed; see holdem_last_error()            */
+#define HOLDEM_ERR_NOT_INIT (-4)    /* holdem_init() has not succeeded on the current device          */
+#define HOLDEM_ERR_BAD_INPUT (-5)   /* *_host only: at least one malformed row (marked HOLDEM_BAD_ROW) */
+#define HOLDEM_ERR_INTERNAL (-6)    /* table self-check failed                                        */
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+
+int holdem_abi_version(void);
+const char *holdem_last_error(void);
+
+/* Builds the lookup tables on the host (once per process) and uploads them to `device` (once per device).
+ * Idempotent and thread-safe.  Replaces the module-level `evaluator = Evaluator()` of
+ * HandCalculations.py:268 and the per-call `Evaluator()` of :231 (Treys builds its tables there). */
+int holdem_init(int device);
+
+/* Host-only consistency check of the generated tables (7462 classes, perfect hashes collision-free,
+ * category sizes).  Needs no GPU.  Returns HOLDEM_OK or HOLDEM_ERR_INTERNAL. */
+int holdem_selftest_tables(void);
+
+/* Number of streaming multiprocessors of the initialised device (grid sizing for callers), or <0. */
+int holdem_sm_count(int device);
+
+/* ---- batched evaluator: Treys rank ------------------------------------------------------------------
+ * Replaces treys.Evaluator.evaluate as reached from evaluate_best_hand (HandCalculations.py:229-240) and
+ * CalculateHandValue (pokerlib_to_treys.py:15-21).  cards: uint8[n,8], the first n_cards (5, 6 or 7)
+ * columns of each row are the hand, the rest is ignored.  rank_out: uint16[n], 1..7462 (0 = malformed row). */
+int holdem_eval_batch(const uint8_t *d_cards, int n_cards, int64_t n, uint16_t *d_rank_out, void *stream);
+int holdem_eval_batch_host(const uint8_t *h_cards, int n_cards, int64_t n, uint16_t *h_rank_out);
+
+/* Exhaustive validation sweep (BASELINE.json configs[1]): enumerates all C(52,7) = 133,784,560 seven-card
+ * hands in-kernel.  d_hist: uint64[7463] (index = rank), d_sums: uint64[2] = {sum rank, sum rank^2}.
+ * Both are overwritten. */
+int holdem_exhaustive7(uint64_t *d_hist, uint64_t *d_sums, void *stream);
+int holdem_exhaustive7_host(uint64_t *h_hist, uint64_t *h_sums);
+
+/* ---- batched literal ranker ---------------------------------------------------------------------------
+ * Replaces CalculateHandRankValue (HandCalculations.py:45-82) on the concatenation ourcards + boardcards.
+ * cards: uint8[n,row_stride], first n_cards (2..9) columns used, duplicates allowed (multiset semantics).
+ * cat_out: uint8[n], 0..8, higher is better (0xFF = malformed row: a card > 51). */
+int holdem_category_batch(const uint8_t *d_cards, int n_cards, int row_stride, int64_t n, uint8_t *d_cat_out,
+                          void *stream);
+int holdem_category_batch_host(const uint8_t *h_cards, int n_cards, int row_stride, int64_t n,
+                               uint8_t *h_cat_out);
+
+/* ---- hand strength -------------------------------------------------------------------------------------
+ * Replaces the loop of HandStrength (HandCalculations.py:157-176).  sit: uint8[n,8] situation rows;
+ * out: uint32[n,3] = ahead, tied, behind.  The float is derived by the caller exactly as :175. */
+int holdem_hs_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
+int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out);
+
+/* ---- hand strength + hand potential ----------------------------------------------------------------------
+ * Replaces the loops of HandPotential (HandCalculations.py:178-226) and, as a by-product, HandStrength.
+ * sit: uint8[n,8]; out: uint32[n,HOLDEM_HP_ROW].  PPot/NPot are derived by the caller exactly as :221-224. */
+int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
+int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out);
+
+/* Same results as holdem_hp_batch computed by the plain (non-deduplicating) enumeration kernel: one opponent
+ * evaluation per (opponent holding, runout) pair.  Kept as the independent second implementation the parity
+ * tests cross-check against, and as the only path for HOLDEM_MODE_REFERENCE and turn/river boards. */
+int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
+
+/* ---- roofline micro-benchmarks (bench.py) ---------------------------------------------------------------
+ * Issues `iters` dependent uniformly-random uint16 gathers per thread over a shared-memory table of
+ * `table_bytes` from every lane of a full grid and returns the elapsed device time (CUDA events on `stream`).
+ * pattern 0: random indices (bank conflicts as they fall); 1: conflict-free (lane-strided) indices. */
+int holdem_microbench_smem_gather(int table_bytes, int iters, int pattern, int blocks_per_sm, int threads,
+                                  float *elapsed_ms, double *lookups, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOLDEM_B200_H */

@@ -1,0 +1,89 @@
+"""GPU parity: batched 5/6/7-card Treys evaluator and literal category ranker vs the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_hands(n, n_cards, seed):
+    rng = np.random.default_rng(seed)
+    cards = np.argsort(rng.random((n, 52)), axis=1)[:, :n_cards].astype(np.uint8)
+    rows = np.full((n, 8), 0xFF, dtype=np.uint8)
+    rows[:, :n_cards] = cards
+    return rows
+
+
+@pytest.mark.parametrize("n_cards", [5, 6, 7])
+@pytest.mark.parametrize("n", [1, 1000, 400_000])   # small -> L1/L2-table kernel, large -> shared-memory-table kernel
+def test_eval_matches_oracle(hb, oracle, n_cards, n):
+    rows = _random_hands(n, n_cards, seed=100 + n_cards)
+    got = hb.evaluate(torch.from_numpy(rows).cuda(), n_cards).cpu().numpy().astype(np.uint16)
+    assert np.array_equal(got, oracle.treys_evaluate_batch(rows, n_cards))
+
+
+def test_eval_all_five_card_hands(hb, oracle):
+    import itertools
+    rows = np.array([list(c) + [255, 255, 255] for c in itertools.combinations(range(52), 5)], dtype=np.uint8)
+    got = hb.evaluate(torch.from_numpy(rows).cuda(), 5).cpu().numpy().astype(np.uint16)
+    assert np.array_equal(got, oracle.treys_evaluate_batch(rows, 5))
+    assert len(np.unique(got)) == 7462
+
+
+def test_eval_edge_cases(hb):
+    rows = np.array([[0, 1, 2, 3, 4, 5, 6, 255],          # ok
+                     [0, 0, 2, 3, 4, 5, 6, 255],          # duplicate
+                     [0, 1, 2, 3, 4, 5, 52, 255],         # unknown card
+                     [0, 1, 2, 3, 4, 5, 255, 255]],       # too few cards for n=7
+                    dtype=np.uint8)
+    got = hb.evaluate(torch.from_numpy(rows).cuda(), 7).cpu().tolist()
+    assert got[0] > 0 and got[1:] == [0, 0, 0]
+    assert hb.evaluate(torch.empty((0, 8), dtype=torch.uint8, device="cuda"), 7).numel() == 0
+    with pytest.raises(KeyError):
+        hb.evaluate(torch.from_numpy(rows).cuda(), 4)
+    with pytest.raises(RuntimeError):
+        hb.evaluate(torch.from_numpy(rows), 7)            # CPU tensor: no fallback
+    with pytest.raises(hb.HoldemError):
+        hb.evaluate_host(rows, 7)                          # malformed rows are an error at the host boundary
+    assert hb.evaluate_host(rows[:1], 7).tolist() == [got[0]]
+
+
+def test_eval_host_entry(hb, oracle):
+    rows = _random_hands(300_000, 7, seed=3)
+    assert np.array_equal(hb.evaluate_host(rows, 7), oracle.treys_evaluate_batch(rows, 7))
+
+
+def test_exhaustive_seven_cards(hb):
+    """BASELINE.json configs[1]: all 133,784,560 hands, published class frequencies and checksums."""
+    hist, sums = hb.exhaustive7()
+    hist = hist.cpu().numpy()
+    assert int(hist.sum()) == 133784560
+    bounds = [0, 10, 166, 322, 1599, 1609, 2467, 3325, 6185, 7462]
+    per_class = [int(hist[bounds[i] + 1:bounds[i + 1] + 1].sum()) for i in range(9)]
+    assert per_class == [41584, 224848, 3473184, 4047644, 6180020, 6461620, 31433400, 58627800, 23294460]
+    assert int(hist[0]) == 0 and int(hist[1]) == 4324 and int(hist[10]) == 4140 and int(hist[11]) == 4052
+    assert int(hist[1600]) == 747980 and int(hist[7462]) == 0 and int((hist > 0).sum()) == 4824
+    assert sums.cpu().tolist() == [547965983972, 2665153084455708]
+
+
+def test_category_golden_and_random(hb, oracle):
+    g = load_golden("literal_category.json")["cases"]
+    for n_cards in range(5, 10):
+        cases = [c for c in g if len(c[0]) == n_cards]
+        rows = np.full((len(cases), 16), 0xFF, dtype=np.uint8)
+        for i, (cards, _) in enumerate(cases):
+            rows[i, :n_cards] = cards
+        got = hb.category(torch.from_numpy(rows).cuda(), n_cards).cpu().tolist()
+        assert got == [v for _, v in cases], n_cards
+    rng = np.random.default_rng(11)
+    for n_cards in range(2, 10):
+        rows = rng.integers(0, 52, size=(200_000, 9), dtype=np.uint8)   # duplicates on purpose
+        rows[::2, :] = rng.integers(0, 4, size=(100_000, 9), dtype=np.uint8) * 13 + \
+            rng.integers(0, 5, size=(100_000, 9), dtype=np.uint8)        # few ranks: quads/full houses/5-of-a-value
+        got = hb.category(torch.from_numpy(rows).cuda(), n_cards).cpu().numpy()
+        assert np.array_equal(got, oracle.lit_category_batch(rows, n_cards)), n_cards
+    bad = np.array([[0, 1, 2, 3, 60, 0, 0, 0, 0]], dtype=np.uint8)
+    assert hb.category(torch.from_numpy(bad).cuda(), 5).cpu().tolist() == [0xFF]
+    assert np.array_equal(hb.category_host(rows[:1000], 7), oracle.lit_category_batch(rows[:1000], 7))

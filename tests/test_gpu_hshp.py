@@ -1,0 +1,158 @@
+"""GPU parity: hand strength and hand potential counts vs the CPU oracle and vs the golden vectors produced by the
+unmodified reference, through the C ABI; plus size-independent properties at BASELINE.json's full sizes."""
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def f32hex(x):
+    return struct.pack(">f", float(x)).hex()
+
+
+def _u32(t):
+    return t.cpu().numpy().astype(np.uint32)
+
+
+@pytest.mark.parametrize("mode", ["treys", "reference"])
+@pytest.mark.parametrize("n_board", [3, 4, 5])
+def test_hs_matches_oracle(hb, oracle, mode, n_board):
+    sit = hb.random_situations(600, seed=40 + n_board, n_board=n_board)
+    got = _u32(hb.hand_strength_counts(torch.from_numpy(sit).cuda(), mode))
+    assert np.array_equal(got, oracle.hs_batch(sit, mode))
+    assert np.array_equal(hb.hand_strength_counts_host(sit, mode), got)
+
+
+def test_hs_reference_golden_floats(hb):
+    cases = load_golden("literal_hs.json")["cases"]
+    for nb in (3, 4, 5):
+        sub = [c for c in cases if len(c["board"]) == nb]
+        sit = hb.pack_situations([c["our"] for c in sub], [c["board"] for c in sub])
+        counts = hb.hand_strength_counts(torch.from_numpy(sit).cuda(), "reference")
+        hs = hb.hs_from_counts(counts).cpu().tolist()
+        for c, v, cnt in zip(sub, hs, counts.cpu().tolist()):
+            assert float(v).hex() == c["hs_hex"], c
+            a, t, b = cnt
+            assert ((a + t / 2) / (a + t + b)).hex() == c["hs_hex"]
+
+
+def test_hp_reference_golden(hb):
+    """HP[3][3], HPTotal[3] and the float32 PPot/NPot bit-identical to the unmodified reference (flop/turn/river)."""
+    cases = load_golden("literal_hp.json")["cases"]
+    for nb in (3, 4, 5):
+        sub = [c for c in cases if len(c["board"]) == nb]
+        sit = hb.pack_situations([c["our"] for c in sub], [c["board"] for c in sub])
+        rows = hb.hand_potential_counts(torch.from_numpy(sit).cuda(), "reference")
+        ppot, npot = hb.potentials_from_counts(rows)
+        assert ppot.dtype == torch.float32 and ppot.is_cuda
+        for c, row, p, q in zip(sub, rows.cpu().tolist(), ppot.cpu().tolist(), npot.cpu().tolist()):
+            assert [row[3:6], row[6:9], row[9:12]] == c["HP"], c
+            assert row[12:15] == c["HPTotal"] and row[0:3] == c["HPTotal"] and row[15] == nb
+            assert f32hex(p) == c["ppot_f32_hex"] and f32hex(q) == c["npot_f32_hex"]
+
+
+@pytest.mark.parametrize("mode,n_board,n", [("treys", 3, 48), ("treys", 4, 200), ("treys", 5, 200),
+                                            ("reference", 3, 48), ("reference", 4, 24), ("reference", 5, 24)])
+def test_hp_matches_oracle(hb, oracle, mode, n_board, n):
+    sit = hb.random_situations(n, seed=60 + n_board, n_board=n_board)
+    want = oracle.hp_batch(sit, mode)
+    d_sit = torch.from_numpy(sit).cuda()
+    assert np.array_equal(_u32(hb.hand_potential_counts(d_sit, mode)), want)
+    assert np.array_equal(_u32(hb.hand_potential_counts(d_sit, mode, direct=True)), want)
+
+
+def test_hp_treys_regression_vectors(hb):
+    sit = hb.pack_situations([[14, 1]], [[31, 32, 33]])
+    row = hb.hand_potential_counts(torch.from_numpy(sit).cuda(), "treys")[0].cpu().tolist()
+    assert row[0:3] == [564, 1, 516]
+    assert row[3:12] == [276753, 35790, 245817, 0, 658, 332, 28713, 33025, 449102]
+    ppot, npot = hb.potentials_from_counts(torch.tensor([row], dtype=torch.int32))
+    assert float(ppot[0]) == 87.47679138183594 and float(npot[0]) == 467.04071044921875
+
+
+def test_hp_host_entry_and_bad_rows(hb, oracle):
+    sit = hb.random_situations(40, seed=77)
+    assert np.array_equal(hb.hand_potential_counts_host(sit, "treys"), oracle.hp_batch(sit, "treys"))
+    bad = sit.copy()
+    bad[3, 1] = bad[3, 0]            # duplicate hole card
+    bad[5, 2] = 99                   # unknown card
+    bad[7, 2:7] = [1, 255, 2, 255, 255]  # hole in the board
+    bad[9, 2:7] = [1, 2, 255, 255, 255]  # two-card board
+    rows = hb.hand_potential_counts(torch.from_numpy(bad).cuda(), "treys").cpu().numpy()
+    hs = hb.hand_strength_counts(torch.from_numpy(bad).cuda(), "treys").cpu().numpy()
+    for i in (3, 5, 7, 9):
+        assert (rows[i] == -1).all() and (hs[i] == -1).all(), i
+    good = [i for i in range(40) if i not in (3, 5, 7, 9)]
+    assert np.array_equal(rows[good].astype(np.uint32), oracle.hp_batch(sit[good], "treys"))
+    with pytest.raises(hb.HoldemError):
+        hb.hand_potential_counts_host(bad, "treys")
+    assert hb.hand_potential_counts(torch.empty((0, 8), dtype=torch.uint8, device="cuda")).shape == (0, 16)
+    with pytest.raises(ValueError):
+        hb.hand_potential_counts(torch.from_numpy(sit).cuda(), "bogus")
+
+
+def test_hp_full_size_properties(hb):
+    """BASELINE.json configs[2]: 65,536 random flop situations.  Size-independent checks on every row plus equality of
+    the two independent GPU implementations (deduplicating vs plain enumeration) on a 4,096-row slice."""
+    n = 65536
+    sit = hb.random_situations(n, seed=20251019)
+    d_sit = torch.from_numpy(sit).cuda()
+    rows = hb.hand_potential_counts(d_sit, "treys")
+    r = rows.cpu().numpy().astype(np.int64)
+    hp = r[:, 3:12].reshape(n, 3, 3)
+    assert (r[:, 15] == 3).all()
+    assert (r[:, 12:15].sum(axis=1) == 1081).all()
+    assert (r[:, 0:3] == r[:, 12:15]).all()
+    assert (hp.sum(axis=2) == 990 * r[:, 12:15]).all()        # every opponent holding sees exactly C(45,2) runouts
+    hs = hb.hand_strength_counts(d_sit, "treys").cpu().numpy()
+    assert np.array_equal(hs, r[:, 0:3])                         # HS kernel agrees with the HP kernel's by-product
+    again = hb.hand_potential_counts(d_sit, "treys")
+    assert torch.equal(rows, again)                              # deterministic
+    sl = slice(0, 4096)
+    direct = hb.hand_potential_counts(d_sit[sl].contiguous(), "treys", direct=True)
+    assert torch.equal(rows[sl], direct)
+
+
+def test_dropin_handcalculations(hb):
+    import HandCalculations as HC
+    our_hs, board_hs = torch.tensor([0, 13]), torch.tensor([26, 27, 28, 29, 30])     # testing/ExampleHS.py:4-5
+    our_hp, board_hp = torch.tensor([14, 1]), torch.tensor([31, 32, 33])            # testing/ExampleHS.py:11-12
+    HC.set_mode("reference")
+    try:
+        hs = HC.HandStrength(our_hs, board_hs)
+        assert isinstance(hs, float) and hs == 0.5
+        hp = HC.HandPotential(our_hp, board_hp)
+        assert isinstance(hp, list) and len(hp) == 2
+        assert all(isinstance(x, torch.Tensor) and x.dim() == 0 and x.dtype == torch.float32 and x.is_cuda for x in hp)
+        assert [float(x) for x in hp] == [135.2781982421875, 327.26544189453125]
+        s = HC.HandStrength(torch.tensor([0, 1]), torch.tensor([2, 3, 4]))             # test_HandCalculations.py:49-52
+        assert s == 0.9995374653098983 and 0 <= s <= 1
+        assert our_hs.tolist() == [0, 13]                                              # inputs are not mutated
+    finally:
+        HC.set_mode("treys")
+    assert HC.HandStrength(our_hs, board_hs) == (0 + 946 / 2) / 990
+    hp = HC.HandPotential(our_hp, board_hp)
+    assert [float(x) for x in hp] == [87.47679138183594, 467.04071044921875]
+    assert HC.HandPotentialCounts(our_hp, board_hp)[1] == [564, 1, 516]
+    assert 0.0 <= HC.EffectiveHandStrength(our_hp, board_hp) <= 1.0
+    assert HC.CalculateHandRankValue(torch.tensor([0, 1]), torch.tensor([10, 11, 12, 13, 14])) == 8
+    assert HC.CalculateHandRankValue([0, 1], [10, 11, 12, 13, 14]) == 8                # test_HandCalculations.py:17-18
+
+    class _C:  # duck-typed poker.Card
+        def __init__(self, s):
+            self.rank = type("R", (), {"val": s[0]})()
+            self.suit = type("S", (), {"value": ("x", s[1])})()
+
+    assert HC.evaluate_best_hand([_C("Qs"), _C("Th")], [_C("Ah"), _C("Kd"), _C("Jc")]) == 1600
+    assert HC.evaluate_best_hand([_C("As"), _C("Ks")], [_C("Qs"), _C("Js"), _C("Ts"), _C("2c"), _C("2d")]) == 1
+    import pokerlib_to_treys as P2T
+    assert P2T.CalculateHandValue([_C("Ah"), _C("Kd"), _C("Jc")], [_C("Qs"), _C("Th")]) == 1 - 1600 / 7462
+    with pytest.raises(KeyError):
+        HC.evaluate_best_hand([_C("Qs"), _C("Th")], [_C("Ah"), _C("Kd")])
+    with pytest.raises(ValueError):
+        HC.HandStrength(torch.tensor([0, 0]), torch.tensor([2, 3, 4]))

@@ -1,0 +1,144 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the header declares,
+the generated tables pass their self-check, entry points fail loudly without a GPU, converters, sharding arithmetic,
+and the drop-in module's surface.  No compute call is made without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+import holdem_b200 as hb
+from holdem_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "holdem_b200.h")).read()
+    declared = set(re.findall(r"\b(holdem_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.holdem_abi_version() == 1
+
+
+def test_tables_selfcheck():
+    assert _lib.load().holdem_selftest_tables() == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.holdem_init(0) == _lib.ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.holdem_last_error()
+    with pytest.raises(_lib.HoldemError):
+        _lib.init(0)
+    with pytest.raises(RuntimeError):
+        hb.hand_potential_counts(torch.zeros((1, 8), dtype=torch.uint8), "treys")
+    import HandCalculations as HC
+    with pytest.raises(RuntimeError):
+        HC.HandStrength(torch.tensor([0, 1]), torch.tensor([2, 3, 4]))
+    with pytest.raises(RuntimeError):
+        HC.CalculateHandRankValue([0, 1], [10, 11, 12, 13, 14])
+
+
+def test_encoding_round_trips():
+    for c in range(52):
+        s = hb.str_from_path(c)
+        assert hb.path_from_str(s) == c
+        assert hb.path_from_treys(hb.treys_from_path(c)) == c
+        assert hb.path_from_rank_major(hb.rank_major_from_path(c)) == c
+    assert hb.treys_from_str("Kd") == 0x08004B25 and hb.treys_from_str("5s") == 0x00081307
+    assert hb.treys_from_str("Jc") == 0x0200891D
+    assert hb.path_from_str("2c") == 0 and hb.path_from_str("3d") == 14 and hb.path_from_str("As") == 51
+    with pytest.raises(ValueError):
+        hb.path_from_treys(12345)
+    # utils.card_to_int: rank * 4 + suit
+    assert hb.rank_major_from_path(hb.path_from_str("Ah")) == 12 * 4 + 2
+
+
+def test_pack_and_random_situations():
+    rows = hb.pack_situations([[14, 1]], [[31, 32, 33]])
+    assert rows.tolist() == [[14, 1, 31, 32, 33, 255, 255, 255]]
+    rows = hb.random_situations(1000, seed=20251019)
+    assert rows.shape == (1000, 8) and rows.dtype == np.uint8
+    assert (rows[:, 5:] == 255).all() and (rows[:, :5] < 52).all()
+    assert all(len(set(r[:5])) == 5 for r in rows.tolist())
+    assert np.array_equal(rows, hb.random_situations(1000, seed=20251019))
+    with pytest.raises(ValueError):
+        hb.pack_situations([[1, 2]], [[3, 4]])
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 8, 9, 1000, 65536, 1000000):
+        for w in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(w):
+                lo, hi, per = hb.shard_bounds(n, w, r)
+                assert 0 <= lo <= hi <= n and hi - lo <= per
+                seen.extend(range(lo, hi)) if n <= 1000 else seen.append((lo, hi))
+            if n <= 1000:
+                assert seen == list(range(n))
+            else:
+                assert seen[0][0] == 0 and seen[-1][1] == n
+                assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+
+
+def test_float_formulas_match_oracle_formulas():
+    from oracle import oracle as O
+    rows = torch.tensor([[558, 397, 126, 334713, 148530, 172965, 70272, 265983, 130617, 27162, 16905, 104109,
+                          558, 397, 126, 3],
+                         [0, 0, 990, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 990, 5]], dtype=torch.int32)
+    ppot, npot = hb.potentials_from_counts(rows)
+    assert ppot.dtype == torch.float32
+    assert float(ppot[0]) == 135.2781982421875 and float(npot[0]) == 327.26544189453125
+    assert float(ppot[1]) == 0.0 and torch.isnan(npot[1])
+    hs = hb.hs_from_counts(rows)
+    assert float(hs[0]) == O.hs_float(558, 397, 126)
+    pn, nn = hb.normalised_potentials(rows)
+    assert abs(float(pn[0]) - 135.2781982421875 / 1176) < 1e-6
+    ehs = hb.ehs_from_counts(rows)
+    assert 0.0 <= float(ehs[0]) <= 1.0 and float(ehs[1]) == 0.0
+
+
+def test_dropin_surface():
+    import HandCalculations as HC
+    import pokerlib_to_treys as P2T
+    for name in ("HandStrength", "HandPotential", "CalculateHandRankValue", "CalculateHandRank", "evaluate_best_hand",
+                 "remove_cards_from_deck", "generate_combinations", "generate_opponent_hands",
+                 "generate_possible_turns_and_rivers", "is_straight", "determine_flush", "device", "evaluator",
+                 "convert_to_treys", "CalculateHandValue", "Evaluator", "Card", "torch", "random", "Counter"):
+        assert hasattr(HC, name), name
+    assert HC.device in ("cuda", "cpu") and P2T.device in ("cuda:0", "cpu")
+    pins = __import__("json").load(open(os.path.join(ROOT, "tests", "golden", "helper_pins.json")))
+    assert len(HC.remove_cards_from_deck(torch.tensor([0, 1, 2]))) == pins["remove_3"]
+    assert len(HC.remove_cards_from_deck(torch.tensor([52, 53]))) == pins["remove_unknown"]
+    assert len(list(HC.generate_combinations(torch.tensor([0, 1, 2])))) == pins["comb_3"]
+    assert len(list(HC.generate_opponent_hands(torch.tensor([0, 1]), torch.tensor([2, 3])))) == pins["opp_4known"]
+    assert len(list(HC.generate_possible_turns_and_rivers(torch.tensor([0, 1, 2])))) == pins["runouts_flop"]
+    first = [t.tolist() for t in list(HC.generate_opponent_hands(torch.tensor([14, 1]), torch.tensor([31, 32, 33])))[:5]]
+    assert first == pins["first_opp_hands"]
+    for values, expect in pins["is_straight"]:
+        assert HC.is_straight(values) == expect
+    assert HC.determine_flush([0] * 5, {0: 5}) == (True, 0) and HC.determine_flush([], {1: 4}) == (False, None)
+    assert HC.CalculateHandRank([0, 1], [2, 3]) == (0,)
+    with pytest.raises(TypeError):
+        HC.CalculateHandRank([0, 1], [2, 3, 4])
+
+    class _R:  # duck-typed poker.Card
+        def __init__(self, s):
+            self.rank = type("R", (), {"val": s[0]})()
+            self.suit = type("S", (), {"value": ("x", s[1])})()
+
+    assert P2T.convert_to_treys([_R("Kd"), _R("5s")]) == [0x08004B25, 0x00081307]
+    assert P2T.Card.new("Jc") == 0x0200891D and P2T.Card.int_to_str(0x0200891D) == "Jc"
+    ev = P2T.Evaluator()
+    assert ev.get_rank_class(1) == 1 and ev.get_rank_class(1600) == 5 and ev.get_rank_class(7462) == 9
+    assert ev.class_to_string(5) == "Straight"
+    HC.set_mode("reference")
+    assert HC.get_mode() == "reference"
+    HC.set_mode("treys")
+    with pytest.raises(ValueError):
+        HC.set_mode("bogus")
