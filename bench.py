@@ -144,7 +144,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    per_step = max(16, 2 * cores)   # bounded sample of the 65,536-situation workload per step
+    per_step = max(64, 8 * cores)   # bounded sample of the 65,536-situation workload per step
     for _ in range(args.warmup):
         cpu_port_throughput(min(per_step, cores), cores)
     t_total = 0.0

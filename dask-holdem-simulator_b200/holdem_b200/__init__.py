@@ -4,7 +4,7 @@ Python mirror of the reference's interface for this path lives one directory up 
 pokerlib_to_treys.py); this package holds the C-ABI binding and the batched / sharded entry points.
 """
 from . import _lib  # noqa: F401
-from ._lib import HoldemError, LIB_PATH  # noqa: F401
+from ._lib import HoldemError, LIB_PATH, HP_ROW, HS_ROW, MODE_TREYS, MODE_REFERENCE  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .encoding import (pack_situations, random_situations, path_from_str, str_from_path,  # noqa: F401
                        treys_from_path, path_from_treys, treys_from_str, path_from_poker_card,
