@@ -2,6 +2,7 @@
 // host-buffer entry points (pinned staging + chunked H2D / kernel / D2H pipeline).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -169,6 +170,10 @@ int holdem_init(int device) {
     CUDA_TRY(cudaMemcpy(S.image, im.bytes.data(), im.bytes.size(), cudaMemcpyHostToDevice));
     S.T.flush = reinterpret_cast<const uint16_t *>(S.image + im.off_flush);
     S.T.pairs = reinterpret_cast<const uint16_t *>(S.image + im.off_pairs);
+    S.T.flop_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_task_hdr);
+    S.T.flop_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_lanes);
+    S.T.nf4_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf4);
+    S.T.n_flop_tasks = im.n_tasks;
     for (int i = 0; i < 3; ++i) {
         NfHash &h = S.T.nf[i];
         h.disp = reinterpret_cast<const uint16_t *>(S.image + im.off_disp[i]);
@@ -308,7 +313,8 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
                                cudaStream_t st) {
     if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, nullptr, 0, st);
     int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    cudaError_t e = launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, st);
+    static const int impl = (getenv("HOLDEM_FLOP_KERNEL") && atoi(getenv("HOLDEM_FLOP_KERNEL")) == 2) ? 2 : 3;
+    cudaError_t e = launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st);
     if (e != cudaSuccess) return e;
     return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
 }

@@ -28,6 +28,10 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint16_t *pairs;  // [1326] colex pairs, i | j << 8
     NfHash nf[3];           // 5, 6, 7 cards
     uint32_t disp_entries[3], val_entries[3];
+    const uint32_t *flop_task_hdr;  // [n_flop_tasks] k0 | iters << 8
+    const uint32_t *flop_lanes;     // [n_flop_tasks * 32] a | b<<8 | d<<16, 0xFFFFFFFF = padding lane
+    const uint16_t *nf4_ranks;      // [1820] four ascending ranks, 4 bits each
+    uint32_t n_flop_tasks;
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

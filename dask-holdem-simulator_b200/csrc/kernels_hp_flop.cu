@@ -252,10 +252,261 @@ hp_flop_treys_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__res
     if (saw_other && tid == 0) atomicOr(other_rows, 1);
 }
 
+// =====================================================================================================================
+// v3: lane = (a,b,d), walking c.  Same counts as the kernel above with ~half the instructions per 4-set:
+//   * a static, situation-independent work list (tables.h: flop_task_hdr / flop_lanes) assigns every lane one triple
+//     (a,b,d) of unseen positions; the 32 lanes of a warp task share the walk length d-b-1, so there is no ragged tail
+//     and no per-iteration activity predicate (padding lanes read all-zero words and therefore add nothing);
+//   * everything that depends on (a,b,d) only -- W[a][b], W[a][d], W[b][d], the multiset index prefix, the flush suit
+//     of the six fixed cards and its rank mask -- is hoisted out of the walk; per step the lane reads W[a][c], W[b][c],
+//     W[c][d] (constant strides), one packed word X[suit][c] = C(rc+2,3) | rank bit of c in that suit << 16, and NF;
+//   * the twelve conditional accumulations are issued as predicated IMADs (multiplier 1 from a kernel argument) so
+//     that they run on the FMA pipe while the compares run on the ALU pipe.
+// =====================================================================================================================
+namespace {
+
+constexpr int kPitch3 = 49;        // odd pitch: lanes with consecutive a and equal c hit distinct banks
+constexpr int kRows3 = 92;         // 47 real rows + zero rows so that padding lanes can walk 44 rows past row 47
+constexpr int kXPitch = 96;
+
+struct Flop3Smem {
+    uint16_t flush[kFlushEntries];
+    uint32_t W[kRows3 * kPitch3];      // [i][j], i<j<47: our7 << 19 | one-hot class; everything else stays zero
+    uint32_t X[4 * kXPitch];           // [suit][i]: C(r_i+2,3) | (suit_i == suit ? 1 << r_i : 0) << 16; i >= 47 zero
+    uint32_t I[48];                    // per position: r | C(r+1,2) << 4 | C(r+3,4) << 11 | suit << 22
+    uint16_t NF[kNf + 4];
+    uint32_t cardkey[64];
+    uint32_t cnt[12];
+    uint32_t bmask[4];                 // board rank mask per suit
+    uint8_t code[64];
+};
+
+__device__ __forceinline__ void add_if_lt(uint32_t &acc, uint32_t wq, uint32_t thr, uint32_t wp, uint32_t one) {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+        : "+r"(acc) : "r"(wq), "r"(thr), "r"(wp), "r"(one));
+}
+__device__ __forceinline__ void add_if_ge(uint32_t &acc, uint32_t wq, uint32_t thr, uint32_t wp, uint32_t one) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, %4, %0;\n\t}"
+        : "+r"(acc) : "r"(wq), "r"(thr), "r"(wp), "r"(one));
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads)
+hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
+                        int *__restrict__ other_rows, uint32_t one) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Flop3Smem &S = *reinterpret_cast<Flop3Smem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(T.flush);
+        uint4 *dst = reinterpret_cast<uint4 *>(S.flush);
+        for (uint32_t i = tid; i < kFlushEntries / 8; i += kThreads) dst[i] = src[i];
+        for (uint32_t i = tid; i < (uint32_t)(kRows3 * kPitch3); i += kThreads) S.W[i] = 0;   // pad rows stay zero
+        for (uint32_t i = tid; i < (uint32_t)(4 * kXPitch); i += kThreads) S.X[i] = 0;
+        if (tid < 64) S.cardkey[tid] = tid < 52 ? c_rank_key[tid % 13] : 0u;
+    }
+    const NfHash h5 = T.nf[0], h7 = T.nf[2];
+    const uint32_t n_tasks = T.n_flop_tasks;
+    bool saw_other = false;
+
+    for (int64_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        __syncthreads();
+        uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
+        uint32_t cb[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cb[k] = (w.x >> (8 * k)) & 0xFFu; cb[4 + k] = (w.y >> (8 * k)) & 0xFFu; }
+        const bool flop = cb[5] == 0xFFu && cb[6] == 0xFFu;
+        if (!flop) { saw_other = true; continue; }
+        bool ok = true;
+        uint64_t known = 0, bset = 0;
+        uint32_t kb = 0, khole = 0, scb = 0x4444u;   // suit nibbles biased by 4: bit 3 set <=> count >= 4
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t c = cb[k];
+            ok = ok && c < 52u;
+            const uint32_t cc = c < 52u ? c : 0u;
+            known |= card_bit(cc);
+            if (k >= 2) { bset |= card_bit(cc); kb += S.cardkey[cc]; scb += 1u << (4 * card_suit(cc)); }
+            else khole += S.cardkey[cc];
+        }
+        ok = ok && __popcll(known) == 5;
+        if (!ok) {
+            if (tid < 16) out[idx * 16 + tid] = 0xFFFFFFFFu;
+            continue;
+        }
+        if (tid < 12) S.cnt[tid] = 0;
+        if (tid < 4) S.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
+        if (warp == 0) {   // unseen cards in (rank, suit) order
+            const uint32_t p0 = path_of_code(lane), p1 = path_of_code(lane + 32);
+            const bool in0 = !((known >> p0) & 1ull);
+            const bool in1 = (lane + 32 < 52) && !((known >> p1) & 1ull);
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (in0) S.code[__popc(m0 & lt)] = (uint8_t)lane;
+            if (in1) S.code[__popc(m0) + __popc(m1 & lt)] = (uint8_t)(lane + 32);
+        }
+        {   // NF[1820]: board + every multiset of four ranks (rank list from the static table)
+            uint32_t bcnt = 0;
+#pragma unroll
+            for (int k = 2; k < 5; ++k) bcnt += 1u << (2 * card_rank(cb[k]));
+            for (uint32_t e = tid; e < (uint32_t)kNf; e += kThreads) {
+                const uint32_t rr = __ldg(T.nf4_ranks + e);
+                uint32_t key = kb;
+                bool valid = true;
+                uint32_t prev = 99, run = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t r = (rr >> (4 * q)) & 15u;
+                    key += S.cardkey[r];
+                    run = (r == prev) ? run + 1 : 1;
+                    prev = r;
+                    valid = valid && (run + ((bcnt >> (2 * r)) & 3u) <= 4);
+                }
+                S.NF[e] = valid ? (uint16_t)nf_lookup(h7, key) : (uint16_t)0;
+            }
+        }
+        __syncthreads();
+        {   // per-position tables
+            if (tid < (uint32_t)kUnseen) {
+                const uint32_t cd = S.code[tid], r = cd >> 2, su = cd & 3u;
+                S.I[tid] = r | (choose2(r + 1) << 4) | (choose4(r + 3) << 11) | (su << 22);
+#pragma unroll
+                for (uint32_t s2 = 0; s2 < 4; ++s2)
+                    S.X[s2 * kXPitch + tid] = choose3(r + 2) | ((su == s2 ? (1u << r) : 0u) << 16);
+            }
+            const uint32_t ours_now = treys_rank(h5, S.flush, kb + khole, known);
+            uint32_t c0 = 0, c1 = 0, c2 = 0;
+            for (uint32_t p = tid; p < (uint32_t)kPairs; p += kThreads) {
+                const uint32_t pr = __ldg(T.pairs + p);
+                const uint32_t i = pr & 0xFFu, j = pr >> 8;
+                const uint32_t pi = path_of_code(S.code[i]), pj = path_of_code(S.code[j]);
+                const uint32_t key = S.cardkey[pi] + S.cardkey[pj];
+                const uint64_t cs = card_bit(pi) | card_bit(pj);
+                const uint32_t our7 = treys_rank(h7, S.flush, kb + khole + key, known | cs);
+                const uint32_t opp5 = treys_rank(h5, S.flush, kb + key, bset | cs);
+                const uint32_t cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
+                c0 += cls == 0; c1 += cls == 1; c2 += cls == 2;
+                S.W[i * kPitch3 + j] = (our7 << 19) | (1u << (6 * cls));
+            }
+            c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+            c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+            c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
+            if (lane == 0) { atomicAdd(&S.cnt[6], c0); atomicAdd(&S.cnt[7], c1); atomicAdd(&S.cnt[8], c2); }
+        }
+        __syncthreads();
+
+        uint32_t acc[6] = {0, 0, 0, 0, 0, 0};
+        uint32_t wide[6] = {0, 0, 0, 0, 0, 0};
+        uint32_t since = 0;
+        uint32_t next_lane = warp < n_tasks ? __ldg(T.flop_lanes + warp * 32 + lane) : 0xFFFFFFFFu;
+        uint32_t next_hdr = warp < n_tasks ? __ldg(T.flop_task_hdr + warp) : 0u;
+        for (uint32_t t = warp; t < n_tasks; t += kWarps) {
+            const uint32_t trip = next_lane, hdr = next_hdr;
+            if (t + kWarps < n_tasks) {   // prefetch the next task of this warp
+                next_lane = __ldg(T.flop_lanes + (t + kWarps) * 32 + lane);
+                next_hdr = __ldg(T.flop_task_hdr + t + kWarps);
+            }
+            const uint32_t k0 = hdr & 0xFFu, iters = hdr >> 8;
+            if (iters == 0) continue;
+            if (since + iters > 31) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    wide[0] += acc[q] & 63u; wide[1] += (acc[q] >> 6) & 63u; wide[2] += (acc[q] >> 12) & 63u;
+                    wide[3] += acc[3 + q] & 63u; wide[4] += (acc[3 + q] >> 6) & 63u; wide[5] += (acc[3 + q] >> 12) & 63u;
+                    acc[q] = 0; acc[3 + q] = 0;
+                }
+                since = 0;
+            }
+            since += iters;
+            // ---- lane invariants ---------------------------------------------------------------------------------------
+            uint32_t wab = 0, wad = 0, wbd = 0, nf = 0, mask6 = 0;
+            const uint32_t *pac = S.W + 47 * kPitch3, *pbc = pac, *pcd = pac, *px = S.X + 48;   // zero words
+            if (trip != 0xFFFFFFFFu) {
+                const uint32_t a = trip & 0xFFu, b = (trip >> 8) & 0xFFu, d = (trip >> 16) & 0xFFu;
+                const uint32_t ia = S.I[a], ib = S.I[b], id = S.I[d];
+                nf = (ia & 15u) + ((ib >> 4) & 127u) + ((id >> 11) & 2047u);
+                const uint32_t sa = ia >> 22, sb = ib >> 22, sd = id >> 22;
+                const uint32_t sc6 = scb + (1u << (4 * sa)) + (1u << (4 * sb)) + (1u << (4 * sd));
+                const uint32_t fl = sc6 & 0x8888u;
+                uint32_t sf = 0;
+                if (fl) {
+                    sf = (uint32_t)(__ffs(fl) - 1) >> 2;
+                    const uint32_t *xr = S.X + sf * kXPitch;
+                    mask6 = S.bmask[sf] | ((xr[a] | xr[b] | xr[d]) >> 16);
+                }
+                wab = S.W[a * kPitch3 + b];
+                wad = S.W[a * kPitch3 + d];
+                wbd = S.W[b * kPitch3 + d];
+                const uint32_t c0i = b + 1 + k0;
+                pac = S.W + a * kPitch3 + c0i;
+                pbc = S.W + b * kPitch3 + c0i;
+                pcd = S.W + c0i * kPitch3 + d;
+                px = S.X + sf * kXPitch + c0i;
+            }
+            // ---- the walk over c --------------------------------------------------------------------------------------------
+#pragma unroll 2
+            for (uint32_t k = 0; k < iters; ++k) {
+                const uint32_t wac = pac[k], wbc = pbc[k], wcd = pcd[k * kPitch3], x = px[k];
+                uint32_t R = S.NF[nf + (x & 0xFFFFu)];
+                const uint32_t m = mask6 | (x >> 16);
+                if (__popc(m) >= 5) R = S.flush[m];
+                const uint32_t lo = R << 19, hi = lo + (1u << 19);
+                add_if_lt(acc[0], wcd, lo, wab, one);  add_if_ge(acc[3], wcd, hi, wab, one);   // P=ab Q=cd
+                add_if_lt(acc[0], wab, lo, wcd, one);  add_if_ge(acc[3], wab, hi, wcd, one);   // P=cd Q=ab
+                add_if_lt(acc[1], wbd, lo, wac, one);  add_if_ge(acc[4], wbd, hi, wac, one);   // P=ac Q=bd
+                add_if_lt(acc[1], wac, lo, wbd, one);  add_if_ge(acc[4], wac, hi, wbd, one);   // P=bd Q=ac
+                add_if_lt(acc[2], wbc, lo, wad, one);  add_if_ge(acc[5], wbc, hi, wad, one);   // P=ad Q=bc
+                add_if_lt(acc[2], wad, lo, wbc, one);  add_if_ge(acc[5], wad, hi, wbc, one);   // P=bc Q=ad
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            wide[0] += acc[q] & 63u; wide[1] += (acc[q] >> 6) & 63u; wide[2] += (acc[q] >> 12) & 63u;
+            wide[3] += acc[3 + q] & 63u; wide[4] += (acc[3 + q] >> 6) & 63u; wide[5] += (acc[3 + q] >> 12) & 63u;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, wide[q]);
+            if (lane == 0 && v) atomicAdd(&S.cnt[q], v);
+        }
+        __syncthreads();
+        if (tid < 16) {
+            uint32_t v;
+            if (tid < 3) v = S.cnt[6 + tid];
+            else if (tid < 12) {
+                const uint32_t cls = (tid - 3) / 3, o = (tid - 3) % 3;
+                const uint32_t lt = S.cnt[cls], gt = S.cnt[3 + cls], all = 990u * S.cnt[6 + cls];
+                v = o == 0 ? lt : (o == 2 ? gt : all - lt - gt);
+            } else if (tid < 15) v = S.cnt[6 + tid - 12];
+            else v = 3u;
+            out[idx * 16 + tid] = v;
+        }
+    }
+    if (saw_other && tid == 0) atomicOr(other_rows, 1);
+}
+
 // Second pass for rows the flop kernel skipped: the plain-enumeration kernel filtered to non-flop rows.
 cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                 int *other_rows_flag, cudaStream_t st) {
+                                 int *other_rows_flag, int impl, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
+    if (impl != 2) {
+        const size_t smem3 = sizeof(Flop3Smem);
+        cudaError_t e3 = cudaFuncSetAttribute(hp_flop_treys_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+        if (e3 != cudaSuccess) return e3;
+        static int bps3 = 0;
+        if (bps3 == 0) {
+            e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps3, hp_flop_treys_v3_kernel, kThreads, smem3);
+            if (e3 != cudaSuccess) return e3;
+            if (bps3 < 1) bps3 = 1;
+        }
+        int64_t blocks3 = (int64_t)sms * bps3;
+        if (blocks3 > n) blocks3 = n;
+        e3 = cudaMemsetAsync(other_rows_flag, 0, sizeof(int), st);
+        if (e3 != cudaSuccess) return e3;
+        hp_flop_treys_v3_kernel<<<(int)blocks3, kThreads, smem3, st>>>(sit, n, out, T, other_rows_flag, 1u);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(FlopSmem);
     cudaError_t e = cudaFuncSetAttribute(hp_flop_treys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -23,7 +23,8 @@ cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, i
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                              const int *run_flag, int skip_flops, cudaStream_t st);
 // Treys-mode flop rows only; sets *other_rows_flag when it met turn/river rows (left untouched for launch_hp_direct).
+// impl: 3 = lane-per-(a,b,d) kernel (default), 2 = the earlier warp-per-(a,b) kernel (kept for A/B measurements).
 cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                 int *other_rows_flag, cudaStream_t st);
+                                 int *other_rows_flag, int impl, cudaStream_t st);
 
 }  // namespace holdem

@@ -217,6 +217,43 @@ struct Builder {
         int p = 0;
         for (int j = 1; j < 52; ++j)
             for (int i = 0; i < j; ++i) t.pairs[p++] = (uint16_t)(i | (j << 8));
+        // ---- 6. flop kernel work list ------------------------------------------------------------------------------
+        {
+            struct Task { uint32_t hdr; std::vector<uint32_t> lanes; };
+            std::vector<Task> tasks;
+            for (int L = 44; L >= 1; --L) {
+                std::vector<uint32_t> group;
+                for (int b = 45 - L; b >= 1; --b)
+                    for (int a = 0; a < b; ++a) group.push_back((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(b + 1 + L) << 16));
+                for (size_t s0 = 0; s0 < group.size(); s0 += 32) {
+                    std::vector<uint32_t> lanes(32, 0xFFFFFFFFu);
+                    for (size_t l = 0; l < 32 && s0 + l < group.size(); ++l) lanes[l] = group[s0 + l];
+                    // the kernel's packed 6-bit counters take at most 31 iterations between drains: split long walks
+                    for (int k0 = 0; k0 < L; k0 += 31) {
+                        int iters = std::min(31, L - k0);
+                        tasks.push_back({(uint32_t)k0 | ((uint32_t)iters << 8), lanes});
+                    }
+                }
+            }
+            std::stable_sort(tasks.begin(), tasks.end(),
+                             [](const Task &x, const Task &y) { return (x.hdr >> 8) > (y.hdr >> 8); });
+            for (const Task &tk : tasks) {
+                t.flop_task_hdr.push_back(tk.hdr);
+                t.flop_lanes.insert(t.flop_lanes.end(), tk.lanes.begin(), tk.lanes.end());
+            }
+            while (t.flop_task_hdr.size() % 4) t.flop_task_hdr.push_back(0);  // 16-byte multiple; iters 0 = no-op
+            t.flop_lanes.resize(t.flop_task_hdr.size() * 32, 0xFFFFFFFFu);
+        }
+        // ---- 7. the 1820 multisets of four ranks ---------------------------------------------------------------------------
+        t.nf4_ranks.assign(1824, 0);
+        for (int r0 = 0; r0 < 13; ++r0)
+            for (int r1 = r0; r1 < 13; ++r1)
+                for (int r2 = r1; r2 < 13; ++r2)
+                    for (int r3 = r2; r3 < 13; ++r3) {
+                        int e = r0 + (r1 + 1) * r1 / 2 + (r2 + 2) * (r2 + 1) * r2 / 6 +
+                                (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24;
+                        t.nf4_ranks[e] = (uint16_t)(r0 | (r1 << 4) | (r2 << 8) | (r3 << 12));
+                    }
         ok = true;
     }
 };
@@ -263,6 +300,26 @@ int selftest(char *msg, int msg_len) {
     if (t.nf[0].lookup(k_worst) != 7462) return fail("worst hand");
     if (t.nf[0].lookup(k_broadway) != 1600) return fail("broadway");
     if (t.pairs[0] != (0 | 1 << 8) || t.pairs[1] != (0 | 2 << 8) || t.pairs[2] != (1 | 2 << 8)) return fail("pairs");
+    {   // the flop work list covers every 4-set of 47 positions exactly once
+        uint64_t sets = 0;
+        for (size_t tk = 0; tk < t.flop_task_hdr.size(); ++tk) {
+            uint32_t k0 = t.flop_task_hdr[tk] & 0xFF, iters = t.flop_task_hdr[tk] >> 8;
+            if (iters > 31) return fail("task too long");
+            for (int l = 0; l < 32; ++l) {
+                uint32_t v = t.flop_lanes[tk * 32 + l];
+                if (v == 0xFFFFFFFFu) continue;
+                uint32_t a = v & 0xFF, b = (v >> 8) & 0xFF, d = (v >> 16) & 0xFF;
+                if (!(a < b && b + 1 + k0 + iters <= d && d <= 46)) return fail("bad flop lane");
+                sets += iters;
+            }
+        }
+        if (sets != 178365) return fail("flop work list does not cover C(47,4)");
+        for (int e = 0; e < 1820; ++e) {
+            uint16_t v = t.nf4_ranks[e];
+            int r0 = v & 15, r1 = (v >> 4) & 15, r2 = (v >> 8) & 15, r3 = v >> 12;
+            if (!(r0 <= r1 && r1 <= r2 && r2 <= r3 && r3 < 13)) return fail("nf4 ranks");
+        }
+    }
     if (msg && msg_len > 0) msg[0] = 0;
     return 0;
 }
@@ -277,6 +334,10 @@ TableImage make_image(const Tables &t) {
     };
     im.off_flush = append(t.flush.data(), t.flush.size() * 2);
     im.off_pairs = append(t.pairs.data(), t.pairs.size() * 2);
+    im.off_task_hdr = append(t.flop_task_hdr.data(), t.flop_task_hdr.size() * 4);
+    im.off_lanes = append(t.flop_lanes.data(), t.flop_lanes.size() * 4);
+    im.off_nf4 = append(t.nf4_ranks.data(), t.nf4_ranks.size() * 2);
+    im.n_tasks = (uint32_t)t.flop_task_hdr.size();
     for (int i = 0; i < 3; ++i) {
         im.off_disp[i] = append(t.nf[i].disp.data(), t.nf[i].disp.size() * 2);
         im.off_val[i] = append(t.nf[i].val.data(), t.nf[i].val.size() * 2);

@@ -46,6 +46,14 @@ struct Tables {
     // pairs[p] = i | j << 8 for the p-th pair in colex order (prefix-stable: the first C(m,2) entries are the
     // pairs of {0..m-1} for every m).
     std::vector<uint16_t> pairs;
+    // Static work list of the flop hand-potential kernel (kernels_hp_flop.cu): every (a,b,d), a<b<d-1, over the 47
+    // unseen-card positions, grouped into warp tasks of 32 lanes that share the loop length d-b-1 (the lane then walks
+    // c = b+1 .. d-1).  task_hdr[t] = k0 | iters << 8 (c starts at b+1+k0); flop_lanes[32 t + l] = a | b<<8 | d<<16 or
+    // 0xFFFFFFFF for a padding lane.  Tasks are sorted by iters descending.
+    std::vector<uint32_t> flop_task_hdr;
+    std::vector<uint32_t> flop_lanes;
+    // nf4_ranks[e] = the four ranks (4 bits each, ascending) of the e-th rank multiset, e = C(r0,1)+C(r1+1,2)+C(r2+2,3)+C(r3+3,4)
+    std::vector<uint16_t> nf4_ranks;
     // Statistics kept for selftest().
     int n_keys[3] = {0, 0, 0};
 };
@@ -56,7 +64,8 @@ int selftest(char *msg, int msg_len);  // 0 = ok
 // Flat device image of the tables: one allocation, 16-byte aligned sections, offsets in bytes.
 struct TableImage {
     std::vector<uint8_t> bytes;
-    uint32_t off_flush = 0, off_pairs = 0;
+    uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0;
+    uint32_t n_tasks = 0;
     uint32_t off_disp[3] = {0, 0, 0}, off_val[3] = {0, 0, 0};
 };
 TableImage make_image(const Tables &t);
