@@ -197,6 +197,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL_DEBUG=VERSION/WARN/INFO prints a banner there
+        if not os.environ.get("HOLDEM_KEEP_NCCL_DEBUG"):
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     hb._lib.init(local_rank)
 
@@ -403,7 +406,7 @@ def main():
         "verified": ok,
     }
     line.update(extras)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -445,9 +445,10 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 px = S.X + sf * kXPitch + c0i;
             }
             // ---- the walk over c --------------------------------------------------------------------------------------------
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t k = 0; k < iters; ++k) {
-                const uint32_t wac = pac[k], wbc = pbc[k], wcd = pcd[k * kPitch3], x = px[k];
+                const uint32_t wac = *pac, wbc = *pbc, wcd = *pcd, x = *px;
+                ++pac; ++pbc; ++px; pcd += kPitch3;
                 uint32_t R = S.NF[nf + (x & 0xFFFFu)];
                 const uint32_t m = mask6 | (x >> 16);
                 if (__popc(m) >= 5) R = S.flush[m];
