@@ -174,6 +174,10 @@ int holdem_init(int device) {
     S.T.flop_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_lanes);
     S.T.nf4_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf4);
     S.T.n_flop_tasks = im.n_tasks;
+    S.T.turn_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_hdr);
+    S.T.turn_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_lanes);
+    S.T.nf3_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf3);
+    S.T.n_turn_tasks = im.n_turn_tasks;
     for (int i = 0; i < 3; ++i) {
         NfHash &h = S.T.nf[i];
         h.disp = reinterpret_cast<const uint16_t *>(S.image + im.off_disp[i]);
@@ -307,14 +311,16 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
     return HOLDEM_OK;
 }
 
-// Treys mode: the deduplicating flop kernel takes every 3-card-board row; turn/river rows (if it saw any) are finished
-// by the plain-enumeration kernel.  Reference mode: plain enumeration only.
+// Treys mode: the deduplicating flop kernel takes every 3-card-board row and flags what else it saw; turn rows go to the
+// deduplicating turn kernel, river rows (HS only) to the plain-enumeration kernel.  Both exit at once when not needed.  Reference mode: plain enumeration only.
 static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out,
                                cudaStream_t st) {
     if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, nullptr, 0, st);
     int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     static const int impl = (getenv("HOLDEM_FLOP_KERNEL") && atoi(getenv("HOLDEM_FLOP_KERNEL")) == 2) ? 2 : 3;
     cudaError_t e = launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st);
+    if (e != cudaSuccess) return e;
+    e = launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
     return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
 }

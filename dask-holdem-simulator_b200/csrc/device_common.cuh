@@ -32,6 +32,10 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint32_t *flop_lanes;     // [n_flop_tasks * 32] a | b<<8 | d<<16, 0xFFFFFFFF = padding lane
     const uint16_t *nf4_ranks;      // [1820] four ascending ranks, 4 bits each
     uint32_t n_flop_tasks;
+    const uint32_t *turn_task_hdr;  // same layout for the turn kernel: lanes are a | b<<8
+    const uint32_t *turn_lanes;
+    const uint16_t *nf3_ranks;      // [455] three ascending ranks, 4 bits each
+    uint32_t n_turn_tasks;
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

@@ -59,8 +59,22 @@ eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restri
         flush = s_flush;
     }
     __syncthreads();
+    // kIlp hands per thread per step: all loads are issued before the dependent lookups so that several HBM requests
+    // and shared-memory gathers are in flight per thread (the per-hand chain is load -> 7 gathers -> 2 gathers -> store).
+    constexpr int kIlp = 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kIlp - 1) * stride < n; i += kIlp * stride) {
+        uint2 w[kIlp];
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j) w[j] = __ldg(cards + i + j * stride);
+        uint32_t r[kIlp];
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j) r[j] = eval_row<NC>(w[j], s_cardkey, flush, h);
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j) out[i + j * stride] = (uint16_t)r[j];
+    }
+    for (; i < n; i += stride) {
         uint2 w = __ldg(cards + i);
         out[i] = (uint16_t)eval_row<NC>(w, s_cardkey, flush, h);
     }

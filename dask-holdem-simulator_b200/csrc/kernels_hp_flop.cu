@@ -101,7 +101,7 @@ hp_flop_treys_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__res
         if (tid < 64) S.cardkey[tid] = tid < 52 ? c_rank_key[tid % 13] : 0u;
     }
     const NfHash h5 = T.nf[0], h7 = T.nf[2];
-    bool saw_other = false;
+    int saw_other = 0;
 
     for (int64_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
         __syncthreads();
@@ -111,7 +111,7 @@ hp_flop_treys_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__res
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cb[k] = (w.x >> (8 * k)) & 0xFFu; cb[4 + k] = (w.y >> (8 * k)) & 0xFFu; }
         const bool flop = cb[5] == 0xFFu && cb[6] == 0xFFu;
-        if (!flop) { saw_other = true; continue; }   // turn / river rows are left to the plain-enumeration kernel
+        if (!flop) { saw_other |= (cb[6] == 0xFFu) ? 1 : 2; continue; }   // turn rows: hp_turn_treys_kernel; river: plain enumeration
         bool ok = true;
         uint64_t known = 0, bset = 0;
         uint32_t kb = 0, khole = 0, scb = 0x3333u;
@@ -249,7 +249,7 @@ hp_flop_treys_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__res
             out[idx * 16 + tid] = v;
         }
     }
-    if (saw_other && tid == 0) atomicOr(other_rows, 1);
+    if (saw_other && tid == 0) atomicOr(other_rows, saw_other);
 }
 
 // =====================================================================================================================
@@ -308,7 +308,7 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     }
     const NfHash h5 = T.nf[0], h7 = T.nf[2];
     const uint32_t n_tasks = T.n_flop_tasks;
-    bool saw_other = false;
+    int saw_other = 0;
 
     for (int64_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
         __syncthreads();
@@ -317,7 +317,7 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cb[k] = (w.x >> (8 * k)) & 0xFFu; cb[4 + k] = (w.y >> (8 * k)) & 0xFFu; }
         const bool flop = cb[5] == 0xFFu && cb[6] == 0xFFu;
-        if (!flop) { saw_other = true; continue; }
+        if (!flop) { saw_other |= (cb[6] == 0xFFu) ? 1 : 2; continue; }
         bool ok = true;
         uint64_t known = 0, bset = 0;
         uint32_t kb = 0, khole = 0, scb = 0x4444u;   // suit nibbles biased by 4: bit 3 set <=> count >= 4
@@ -484,7 +484,7 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             out[idx * 16 + tid] = v;
         }
     }
-    if (saw_other && tid == 0) atomicOr(other_rows, 1);
+    if (saw_other && tid == 0) atomicOr(other_rows, saw_other);
 }
 
 // Second pass for rows the flop kernel skipped: the plain-enumeration kernel filtered to non-flop rows.

@@ -186,18 +186,18 @@ struct HpSmem {
 template <int MODE>
 __global__ void __launch_bounds__(kHpThreads)
 hp_direct_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                 const int *__restrict__ run_flag, int skip_flops) {
+                 const int *__restrict__ run_flag, int skip_boards) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     HpSmem &S = *reinterpret_cast<HpSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // second pass after the flop kernel: nothing to do unless that kernel saw turn/river rows
-    if (run_flag != nullptr && *run_flag == 0) return;
+    if (run_flag != nullptr && (*run_flag & 2) == 0) return;
     if (tid < 64) S.cardkey[tid] = tid < 52 ? c_rank_key[tid % 13] : 0u;
 
     for (int64_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
         __syncthreads();  // previous situation fully consumed (and cardkey visible on the first pass)
         Situation s = parse_situation(sit, idx);
-        if (skip_flops && s.board[3] == 0xFFu && s.board[4] == 0xFFu) continue;  // done by the flop kernel
+        if (skip_boards && s.board[4] == 0xFFu) continue;  // 3- and 4-card boards are done by the flop / turn kernels
         if (!s.ok) {
             if (tid < 16) out[idx * 16 + tid] = 0xFFFFFFFFu;
             continue;
@@ -330,7 +330,7 @@ hp_direct_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restric
 }
 
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
-                             const int *run_flag, int skip_flops, cudaStream_t st) {
+                             const int *run_flag, int skip_boards, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(HpSmem);
     cudaError_t e;
@@ -338,11 +338,11 @@ cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, 
     if (mode == kModeTreys) {
         e = cudaFuncSetAttribute(hp_direct_kernel<kModeTreys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hp_direct_kernel<kModeTreys><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_flops);
+        hp_direct_kernel<kModeTreys><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_boards);
     } else {
         e = cudaFuncSetAttribute(hp_direct_kernel<kModeReference>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hp_direct_kernel<kModeReference><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_flops);
+        hp_direct_kernel<kModeReference><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_boards);
     }
     return cudaGetLastError();
 }

@@ -19,10 +19,14 @@ cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int bloc
 
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                             cudaStream_t st);
-// run_flag: optional device int; the kernel exits at once when *run_flag == 0.  skip_flops: leave 3-card-board rows alone.
+// run_flag: optional device int; the kernel exits at once unless bit 1 is set.  skip_boards: leave 3- and 4-card-board rows
+// alone (they belong to the flop / turn kernels).
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
-                             const int *run_flag, int skip_flops, cudaStream_t st);
-// Treys-mode flop rows only; sets *other_rows_flag when it met turn/river rows (left untouched for launch_hp_direct).
+                             const int *run_flag, int skip_boards, cudaStream_t st);
+// Treys-mode turn rows only; exits at once unless bit 0 of *run_flag is set (the flop kernel saw 4-card boards).
+cudaError_t launch_hp_turn_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
+                                 const int *run_flag, cudaStream_t st);
+// Treys-mode flop rows only; sets bit 0 / bit 1 of *other_rows_flag when it met turn / river rows (left to the kernels below).
 // impl: 3 = lane-per-(a,b,d) kernel (default), 2 = the earlier warp-per-(a,b) kernel (kept for A/B measurements).
 cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                  int *other_rows_flag, int impl, cudaStream_t st);

@@ -244,6 +244,34 @@ struct Builder {
             while (t.flop_task_hdr.size() % 4) t.flop_task_hdr.push_back(0);  // 16-byte multiple; iters 0 = no-op
             t.flop_lanes.resize(t.flop_task_hdr.size() * 32, 0xFFFFFFFFu);
         }
+        // ---- 6b. turn kernel work list -----------------------------------------------------------------------------------
+        {
+            struct Task { uint32_t hdr; std::vector<uint32_t> lanes; };
+            std::vector<Task> tasks;
+            for (int b = 1; b <= 44; ++b) {           // walk length 45 - b, b lanes (a = 0..b-1)
+                const int L = 45 - b;
+                for (int s0 = 0; s0 < b; s0 += 32) {
+                    std::vector<uint32_t> lanes(32, 0xFFFFFFFFu);
+                    for (int l = 0; l < 32 && s0 + l < b; ++l) lanes[l] = (uint32_t)(s0 + l) | ((uint32_t)b << 8);
+                    for (int k0 = 0; k0 < L; k0 += 31)
+                        tasks.push_back({(uint32_t)k0 | ((uint32_t)std::min(31, L - k0) << 8), lanes});
+                }
+            }
+            std::stable_sort(tasks.begin(), tasks.end(),
+                             [](const Task &x, const Task &y) { return (x.hdr >> 8) > (y.hdr >> 8); });
+            for (const Task &tk : tasks) {
+                t.turn_task_hdr.push_back(tk.hdr);
+                t.turn_lanes.insert(t.turn_lanes.end(), tk.lanes.begin(), tk.lanes.end());
+            }
+            while (t.turn_task_hdr.size() % 4) t.turn_task_hdr.push_back(0);
+            t.turn_lanes.resize(t.turn_task_hdr.size() * 32, 0xFFFFFFFFu);
+            t.nf3_ranks.assign(456, 0);
+            for (int r0 = 0; r0 < 13; ++r0)
+                for (int r1 = r0; r1 < 13; ++r1)
+                    for (int r2 = r1; r2 < 13; ++r2)
+                        t.nf3_ranks[r0 + (r1 + 1) * r1 / 2 + (r2 + 2) * (r2 + 1) * r2 / 6] =
+                            (uint16_t)(r0 | (r1 << 4) | (r2 << 8));
+        }
         // ---- 7. the 1820 multisets of four ranks ---------------------------------------------------------------------------
         t.nf4_ranks.assign(1824, 0);
         for (int r0 = 0; r0 < 13; ++r0)
@@ -314,6 +342,18 @@ int selftest(char *msg, int msg_len) {
             }
         }
         if (sets != 178365) return fail("flop work list does not cover C(47,4)");
+        sets = 0;
+        for (size_t tk = 0; tk < t.turn_task_hdr.size(); ++tk) {
+            uint32_t k0 = t.turn_task_hdr[tk] & 0xFF, iters = t.turn_task_hdr[tk] >> 8;
+            for (int l = 0; l < 32; ++l) {
+                uint32_t v = t.turn_lanes[tk * 32 + l];
+                if (v == 0xFFFFFFFFu) continue;
+                uint32_t a = v & 0xFF, b = (v >> 8) & 0xFF;
+                if (!(a < b && b + k0 + iters <= 45 && iters <= 31)) return fail("bad turn lane");
+                sets += iters;
+            }
+        }
+        if (sets != 15180) return fail("turn work list does not cover C(46,3)");
         for (int e = 0; e < 1820; ++e) {
             uint16_t v = t.nf4_ranks[e];
             int r0 = v & 15, r1 = (v >> 4) & 15, r2 = (v >> 8) & 15, r3 = v >> 12;
@@ -338,6 +378,10 @@ TableImage make_image(const Tables &t) {
     im.off_lanes = append(t.flop_lanes.data(), t.flop_lanes.size() * 4);
     im.off_nf4 = append(t.nf4_ranks.data(), t.nf4_ranks.size() * 2);
     im.n_tasks = (uint32_t)t.flop_task_hdr.size();
+    im.off_turn_hdr = append(t.turn_task_hdr.data(), t.turn_task_hdr.size() * 4);
+    im.off_turn_lanes = append(t.turn_lanes.data(), t.turn_lanes.size() * 4);
+    im.off_nf3 = append(t.nf3_ranks.data(), t.nf3_ranks.size() * 2);
+    im.n_turn_tasks = (uint32_t)t.turn_task_hdr.size();
     for (int i = 0; i < 3; ++i) {
         im.off_disp[i] = append(t.nf[i].disp.data(), t.nf[i].disp.size() * 2);
         im.off_val[i] = append(t.nf[i].val.data(), t.nf[i].val.size() * 2);

@@ -52,6 +52,11 @@ struct Tables {
     // 0xFFFFFFFF for a padding lane.  Tasks are sorted by iters descending.
     std::vector<uint32_t> flop_task_hdr;
     std::vector<uint32_t> flop_lanes;
+    // Same for the turn kernel (kernels_hp_turn.cu): every (a,b), a<b<45, over 46 positions, the lane walks c = b+1..45.
+    // turn_lanes[32 t + l] = a | b<<8 or 0xFFFFFFFF.  nf3_ranks[e]: three ascending ranks, e = C(r0,1)+C(r1+1,2)+C(r2+2,3).
+    std::vector<uint32_t> turn_task_hdr;
+    std::vector<uint32_t> turn_lanes;
+    std::vector<uint16_t> nf3_ranks;
     // nf4_ranks[e] = the four ranks (4 bits each, ascending) of the e-th rank multiset, e = C(r0,1)+C(r1+1,2)+C(r2+2,3)+C(r3+3,4)
     std::vector<uint16_t> nf4_ranks;
     // Statistics kept for selftest().
@@ -66,6 +71,7 @@ struct TableImage {
     std::vector<uint8_t> bytes;
     uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0;
     uint32_t n_tasks = 0;
+    uint32_t off_turn_hdr = 0, off_turn_lanes = 0, off_nf3 = 0, n_turn_tasks = 0;
     uint32_t off_disp[3] = {0, 0, 0}, off_val[3] = {0, 0, 0};
 };
 TableImage make_image(const Tables &t);

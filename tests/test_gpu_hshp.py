@@ -156,3 +156,34 @@ def test_dropin_handcalculations(hb):
         HC.evaluate_best_hand([_C("Qs"), _C("Th")], [_C("Ah"), _C("Kd")])
     with pytest.raises(ValueError):
         HC.HandStrength(torch.tensor([0, 0]), torch.tensor([2, 3, 4]))
+
+
+def test_hp_mixed_streets_in_one_batch(hb, oracle):
+    """Flop, turn and river rows interleaved in one call: the three kernels each take their rows."""
+    parts = [hb.random_situations(40, seed=90 + nb, n_board=nb) for nb in (3, 4, 5)]
+    sit = np.concatenate(parts)
+    rng = np.random.default_rng(3)
+    sit = sit[rng.permutation(sit.shape[0])]
+    for mode in ("treys", "reference"):
+        got = _u32(hb.hand_potential_counts(torch.from_numpy(sit).cuda(), mode))
+        assert np.array_equal(got, oracle.hp_batch(sit, mode)), mode
+    only_turn = parts[1]
+    assert np.array_equal(_u32(hb.hand_potential_counts(torch.from_numpy(only_turn).cuda(), "treys")),
+                          oracle.hp_batch(only_turn, "treys"))
+    only_river = parts[2]
+    assert np.array_equal(_u32(hb.hand_potential_counts(torch.from_numpy(only_river).cuda(), "treys")),
+                          oracle.hp_batch(only_river, "treys"))
+
+
+def test_hp_turn_full_size_properties(hb):
+    """65,536 random turn situations: size-independent checks + equality with the plain-enumeration kernel."""
+    n = 65536
+    sit = hb.random_situations(n, seed=20251022, n_board=4)
+    d_sit = torch.from_numpy(sit).cuda()
+    rows = hb.hand_potential_counts(d_sit, "treys")
+    r = rows.cpu().numpy().astype(np.int64)
+    assert (r[:, 15] == 4).all() and (r[:, 12:15].sum(axis=1) == 1035).all()
+    assert (r[:, 3:12].reshape(n, 3, 3).sum(axis=2) == 44 * r[:, 12:15]).all()
+    assert np.array_equal(hb.hand_strength_counts(d_sit, "treys").cpu().numpy(), r[:, 0:3])
+    direct = hb.hand_potential_counts(d_sit[:8192].contiguous(), "treys", direct=True)
+    assert torch.equal(rows[:8192], direct)
