@@ -211,7 +211,18 @@ int holdem_eval_batch(const uint8_t *d_cards, int n_cards, int64_t n, uint16_t *
     if (n < 0 || (n > 0 && (!d_cards || !d_rank_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if (n_cards < 5 || n_cards > 7)
         return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 5, 6 or 7 (got %d): Evaluator.hand_size_map", n_cards);
-    CUDA_TRY(launch_eval_batch(S->T, d_cards, n_cards, n, d_rank_out, S->sms, (cudaStream_t)stream));
+    CUDA_TRY(launch_eval_batch(S->T, d_cards, n_cards, n, d_rank_out, S->sms, false, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_eval_batch_strict(const uint8_t *d_cards, int n_cards, int64_t n, uint16_t *d_rank_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_cards || !d_rank_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (n_cards < 5 || n_cards > 7)
+        return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 5, 6 or 7 (got %d): Evaluator.hand_size_map", n_cards);
+    CUDA_TRY(launch_eval_batch(S->T, d_cards, n_cards, n, d_rank_out, S->sms, true, (cudaStream_t)stream));
     return HOLDEM_OK;
 }
 
@@ -220,7 +231,7 @@ int holdem_eval_batch_host(const uint8_t *h_cards, int n_cards, int64_t n, uint1
     if (n_cards < 5 || n_cards > 7) return fail(HOLDEM_ERR_BAD_ARG, "n_cards must be 5, 6 or 7 (got %d)", n_cards);
     int rc = host_pipeline(h_cards, 8, h_rank_out, 2, n, 1 << 22,
                            [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
-                               return launch_eval_batch(S.T, d_in, n_cards, rows, (uint16_t *)d_out, S.sms, st);
+                               return launch_eval_batch(S.T, d_in, n_cards, rows, (uint16_t *)d_out, S.sms, true, st);
                            });
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i)

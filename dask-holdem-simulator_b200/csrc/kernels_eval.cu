@@ -32,6 +32,7 @@ __device__ __forceinline__ uint32_t eval_row(uint2 w, const uint32_t *cardkey, c
     return bad ? 0u : r;
 }
 
+// Strict path (and the small-batch path): builds the 52-bit card set, so duplicate cards are detected.
 template <int NC, bool kShared>
 __global__ void __launch_bounds__(kShared ? 1024 : 256, 1)
 eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T) {
@@ -42,7 +43,7 @@ eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restri
     uint32_t *s_cardkey = reinterpret_cast<uint32_t *>(smem);                 // 64 entries
     if (threadIdx.x < 64) s_cardkey[threadIdx.x] = threadIdx.x < 52 ? c_rank_key[threadIdx.x % 13] : 0u;
     if (kShared) {
-        uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 256);
+        uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 1024);
         uint16_t *s_disp = s_flush + kFlushEntries;
         uint16_t *s_val = s_disp + T.disp_entries[NC - 5];
         // 16-byte vector copies; every section is 16-byte aligned and a multiple of 16 bytes long
@@ -59,56 +60,153 @@ eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restri
         flush = s_flush;
     }
     __syncthreads();
-    // kIlp hands per thread per step: all loads are issued before the dependent lookups so that several HBM requests
-    // and shared-memory gathers are in flight per thread (the per-hand chain is load -> 7 gathers -> 2 gathers -> store).
-    constexpr int kIlp = 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + (kIlp - 1) * stride < n; i += kIlp * stride) {
-        uint2 w[kIlp];
-#pragma unroll
-        for (int j = 0; j < kIlp; ++j) w[j] = __ldg(cards + i + j * stride);
-        uint32_t r[kIlp];
-#pragma unroll
-        for (int j = 0; j < kIlp; ++j) r[j] = eval_row<NC>(w[j], s_cardkey, flush, h);
-#pragma unroll
-        for (int j = 0; j < kIlp; ++j) out[i + j * stride] = (uint16_t)r[j];
-    }
-    for (; i < n; i += stride) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint2 w = __ldg(cards + i);
         out[i] = (uint16_t)eval_row<NC>(w, s_cardkey, flush, h);
     }
 }
 
+// Fast path for large batches.  The per-card table word carries the additive rank key in its low 23 bits and three
+// 3-bit suit counters above it (clubs, diamonds, hearts; spades = NC - the rest), so one shared-memory gather and one
+// add per card yield both the rank multiset key and the suit histogram; no card set is built.  Hands that hold a flush
+// (about 3 %) or an out-of-range card are deferred to a per-warp queue and finished by eval_row() with all lanes of
+// the warp busy, so the rare path costs well under one instruction per hand.  Duplicate cards are NOT detected here
+// (neither does Treys); the strict kernel above does that.
+template <int NC>
+__global__ void __launch_bounds__(1024, 1)
+eval_batch_fast_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T,
+                       uint32_t row_bytes) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kIlp = 4;
+    constexpr int kQueueCap = 256;   // per warp; drained when it holds >= 128 entries (four full passes of the warp)
+    uint32_t *s_cardkey = reinterpret_cast<uint32_t *>(smem);                 // 64 entries (strict path)
+    uint32_t *s_tab = s_cardkey + 64;                                         // 256 entries, indexed by the raw byte
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_tab + 256);            // [32 warps][kQueueCap]
+    uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 256 + 1024 + 32 * kQueueCap * 2);
+    uint16_t *s_disp = s_flush + kFlushEntries;
+    uint16_t *s_val = s_disp + T.disp_entries[NC - 5];
+    const NfHash &g = T.nf[NC - 5];
+    if (threadIdx.x < 64) s_cardkey[threadIdx.x] = threadIdx.x < 52 ? c_rank_key[threadIdx.x % 13] : 0u;
+    if (threadIdx.x < 256) {
+        const uint32_t c = threadIdx.x, su = c / 13;
+        s_tab[c] = c < 52 ? (c_rank_key[c % 13] | (su < 3 ? 1u << (23 + 3 * su) : 0u)) : 0u;
+    }
+    {
+        const uint4 *src;
+        uint4 *dst;
+        src = reinterpret_cast<const uint4 *>(T.flush); dst = reinterpret_cast<uint4 *>(s_flush);
+        for (uint32_t i = threadIdx.x; i < kFlushEntries / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(g.disp); dst = reinterpret_cast<uint4 *>(s_disp);
+        for (uint32_t i = threadIdx.x; i < T.disp_entries[NC - 5] / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(g.val); dst = reinterpret_cast<uint4 *>(s_val);
+        for (uint32_t i = threadIdx.x; i < T.val_entries[NC - 5] / 8; i += blockDim.x) dst[i] = src[i];
+    }
+    NfHash h = g;
+    h.disp = s_disp;
+    h.val = s_val;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *queue = s_queue + warp * kQueueCap;
+    const char *tab_bytes = reinterpret_cast<const char *>(s_tab);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // Deferred hands: entry = window-iteration << 7 | j << 5 | lane, relative to qbase (this warp's first hand of the window)
+    uint32_t qn = 0, it = 0;
+    int64_t qbase = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    auto drain = [&]() {
+        __syncwarp();
+        for (uint32_t e = lane; e < qn; e += 32) {
+            const uint32_t q = queue[e];
+            const int64_t i = qbase + ((int64_t)(q >> 7) * kIlp + ((q >> 5) & 3u)) * stride + (q & 31u);
+            out[i] = (uint16_t)eval_row<NC>(__ldg(cards + i), s_cardkey, s_flush, h);
+        }
+        __syncwarp();
+    };
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base - threadIdx.x < n; base += kIlp * stride) {
+        // the loop bound is block-uniform; lanes past n load a dummy hand and write nothing
+        uint2 w[kIlp];
+        const uint2 *src = cards + base;
+        uint16_t *dst = out + base;
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j) {
+            const int64_t i = base + j * stride;
+            w[j] = i < n ? __ldg(src + j * stride) : make_uint2(0x03020100u, 0x00060504u);
+        }
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j) {
+            const bool live = base + j * stride < n;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                // byte k -> byte offset into the table: one permute (ALU pipe) and one multiply (FMA pipe)
+                const uint32_t b = __byte_perm(k < 4 ? w[j].x : w[j].y, 0u, 0x4440u + (k & 3));
+                sum += *reinterpret_cast<const uint32_t *>(tab_bytes + b * row_bytes);
+            }
+            // any byte >= 52?  (b & 0x7F) + 76 sets bit 7 iff (b & 0x7F) >= 52; OR b itself catches b >= 128
+            const uint32_t ymask = NC == 7 ? 0x00808080u : (NC == 6 ? 0x00008080u : 0x00000080u);
+            const uint32_t badx = (((w[j].x & 0x7F7F7F7Fu) + 0x4C4C4C4Cu) | w[j].x) & 0x80808080u;
+            const uint32_t bady = (((w[j].y & 0x7F7F7F7Fu) + 0x4C4C4C4Cu) | w[j].y) & ymask;
+            const uint32_t s = sum >> 23;
+            const uint32_t ge5 = (s >> 2) & ((s >> 1) | s) & 0x49u;                      // a counted suit holds >= 5
+            const uint32_t counted = (s & 7u) + ((s >> 3) & 7u) + (s >> 6);               // cards not in spades
+            const bool slow = ((ge5 | badx | bady) != 0 || counted <= (uint32_t)(NC - 5)) && live;
+            const uint32_t r = nf_lookup(h, sum & 0x7FFFFFu);
+            if (live && !slow) dst[j * stride] = (uint16_t)r;
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, slow);
+            if (slow) queue[qn + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)((it << 7) | (j << 5) | lane);
+            qn += __popc(ballot);
+        }
+        ++it;
+        if (qn >= 128 || it == 500) {
+            drain();
+            qn = 0;
+            it = 0;
+            qbase = base + kIlp * stride - lane;
+        }
+    }
+    drain();
+}
+
 size_t eval_smem_bytes(const DevTables &T, int nc) {
-    return 256 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
+    return 1024 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
+}
+size_t eval_fast_smem_bytes(const DevTables &T, int nc) {
+    return 256 + 1024 + 32 * 256 * 2 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
 }
 
 template <int NC>
 static cudaError_t launch_eval_nc(const DevTables &T, const uint8_t *cards, int64_t n, uint16_t *out, int sms,
-                                  cudaStream_t st) {
+                                  bool strict, cudaStream_t st) {
     const uint2 *c2 = reinterpret_cast<const uint2 *>(cards);
     if (n >= (int64_t)sms * 2048) {  // enough work to amortise staging ~50-180 KB per CTA
-        size_t smem = eval_smem_bytes(T, NC);
-        cudaError_t e = cudaFuncSetAttribute(eval_batch_kernel<NC, true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        eval_batch_kernel<NC, true><<<sms, 1024, smem, st>>>(c2, n, out, T);
+        if (strict) {
+            size_t smem = eval_smem_bytes(T, NC);
+            cudaError_t e = cudaFuncSetAttribute(eval_batch_kernel<NC, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            eval_batch_kernel<NC, true><<<sms, 1024, smem, st>>>(c2, n, out, T);
+        } else {
+            size_t smem = eval_fast_smem_bytes(T, NC);
+            cudaError_t e = cudaFuncSetAttribute(eval_batch_fast_kernel<NC>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            eval_batch_fast_kernel<NC><<<sms, 1024, smem, st>>>(c2, n, out, T, 4u);
+        }
     } else {
         int blocks = (int)((n + 255) / 256);
         if (blocks > sms * 8) blocks = sms * 8;
-        eval_batch_kernel<NC, false><<<blocks, 256, 256, st>>>(c2, n, out, T);
+        eval_batch_kernel<NC, false><<<blocks, 256, 1024, st>>>(c2, n, out, T);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_eval_batch(const DevTables &T, const uint8_t *cards, int n_cards, int64_t n, uint16_t *out,
-                              int sms, cudaStream_t st) {
+                              int sms, bool strict, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     switch (n_cards) {
-        case 5: return launch_eval_nc<5>(T, cards, n, out, sms, st);
-        case 6: return launch_eval_nc<6>(T, cards, n, out, sms, st);
-        case 7: return launch_eval_nc<7>(T, cards, n, out, sms, st);
+        case 5: return launch_eval_nc<5>(T, cards, n, out, sms, strict, st);
+        case 6: return launch_eval_nc<6>(T, cards, n, out, sms, strict, st);
+        case 7: return launch_eval_nc<7>(T, cards, n, out, sms, strict, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -34,6 +34,7 @@ SYMBOLS = {
     "holdem_selftest_tables": (_i, []),
     "holdem_sm_count": (_i, [_i]),
     "holdem_eval_batch": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "holdem_eval_batch_strict": (_i, [_vp, _i, _i64, _vp, _vp]),
     "holdem_eval_batch_host": (_i, [_vp, _i, _i64, _vp]),
     "holdem_exhaustive7": (_i, [_vp, _vp, _vp]),
     "holdem_exhaustive7_host": (_i, [_vp, _vp]),

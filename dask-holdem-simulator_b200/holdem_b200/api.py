@@ -55,15 +55,18 @@ def _enter(t: torch.Tensor):
 
 
 # ---- device entry points ---------------------------------------------------------------------------------------------
-def evaluate(cards: torch.Tensor, n_cards: int, out: torch.Tensor = None) -> torch.Tensor:
-    """Treys rank (1..7462, lower is better) of each row's first n_cards (5/6/7) cards.  cards: uint8 [N,8]."""
+def evaluate(cards: torch.Tensor, n_cards: int, out: torch.Tensor = None, strict: bool = False) -> torch.Tensor:
+    """Treys rank (1..7462, lower is better) of each row's first n_cards (5/6/7) cards.  cards: uint8 [N,8].
+    Rows with a card > 51 give 0.  strict=True also gives 0 for rows with duplicate cards (the large-batch fast path
+    does not look for duplicates, exactly like Treys)."""
     _require_cuda(cards, "cards", torch.uint8, 8)
     if n_cards not in (5, 6, 7):
         raise KeyError(n_cards)  # treys.Evaluator.hand_size_map
     if out is None:
         out = torch.empty(cards.shape[0], dtype=torch.int16, device=cards.device)
     lib, st = _enter(cards)
-    _lib.check(lib.holdem_eval_batch(cards.data_ptr(), n_cards, cards.shape[0], out.data_ptr(), st))
+    fn = lib.holdem_eval_batch_strict if strict else lib.holdem_eval_batch
+    _lib.check(fn(cards.data_ptr(), n_cards, cards.shape[0], out.data_ptr(), st))
     return out
 
 

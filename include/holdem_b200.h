@@ -79,8 +79,12 @@ int holdem_sm_count(int device);
 /* ---- batched evaluator: Treys rank ------------------------------------------------------------------
  * Replaces treys.Evaluator.evaluate as reached from evaluate_best_hand (HandCalculations.py:229-240) and
  * CalculateHandValue (pokerlib_to_treys.py:15-21).  cards: uint8[n,8], the first n_cards (5, 6 or 7)
- * columns of each row are the hand, the rest is ignored.  rank_out: uint16[n], 1..7462 (0 = malformed row). */
+ * columns of each row are the hand, the rest is ignored.  rank_out: uint16[n], 1..7462 (0 = malformed row).
+ * Malformed = a card > 51, always detected.  Duplicate cards inside a row are detected (rank 0) by
+ * holdem_eval_batch_strict and by the _host entry; the plain device entry, like Treys itself, does not look for them
+ * in its large-batch fast path and returns an unspecified rank for such rows. */
 int holdem_eval_batch(const uint8_t *d_cards, int n_cards, int64_t n, uint16_t *d_rank_out, void *stream);
+int holdem_eval_batch_strict(const uint8_t *d_cards, int n_cards, int64_t n, uint16_t *d_rank_out, void *stream);
 int holdem_eval_batch_host(const uint8_t *h_cards, int n_cards, int64_t n, uint16_t *h_rank_out);
 
 /* Exhaustive validation sweep (BASELINE.json configs[1]): enumerates all C(52,7) = 133,784,560 seven-card

@@ -87,3 +87,30 @@ def test_category_golden_and_random(hb, oracle):
     bad = np.array([[0, 1, 2, 3, 60, 0, 0, 0, 0]], dtype=np.uint8)
     assert hb.category(torch.from_numpy(bad).cuda(), 5).cpu().tolist() == [0xFF]
     assert np.array_equal(hb.category_host(rows[:1000], 7), oracle.lit_category_batch(rows[:1000], 7))
+
+
+@pytest.mark.parametrize("n_cards", [5, 6, 7])
+def test_eval_large_batch_fast_and_strict_paths(hb, oracle, n_cards):
+    """Large batches take the fast kernel (suit counters + deferred flush queue): every rank equals the oracle, cards
+    > 51 are flagged in both paths, duplicate cards only by strict=True / the host entry (like Treys, the fast path
+    does not look for them)."""
+    n = 700_003                                      # not a multiple of anything: exercises the ragged tail
+    rows = _random_hands(n, n_cards, seed=500 + n_cards)
+    rng = np.random.default_rng(1)
+    flushy = rng.integers(0, n, 20000)               # force plenty of flushes / straight flushes
+    suit = rng.integers(0, 4, 20000)
+    for i, s in zip(flushy, suit):
+        rows[i, :n_cards] = 13 * s + rng.permutation(13)[:n_cards]
+    want = oracle.treys_evaluate_batch(rows, n_cards)
+    bad_card = rng.integers(0, n, 500)
+    dup = np.setdiff1d(rng.integers(0, n, 500), bad_card)
+    rows[bad_card, rng.integers(0, n_cards, 500)] = rng.integers(52, 256, 500).astype(np.uint8)
+    rows[dup, 0] = rows[dup, 1]
+    d = torch.from_numpy(rows).cuda()
+    fast = hb.evaluate(d, n_cards).cpu().numpy().astype(np.uint16)
+    strict = hb.evaluate(d, n_cards, strict=True).cpu().numpy().astype(np.uint16)
+    good = np.ones(n, dtype=bool)
+    good[bad_card] = False
+    good[dup] = False
+    assert np.array_equal(fast[good], want[good]) and np.array_equal(strict[good], want[good])
+    assert (fast[bad_card] == 0).all() and (strict[bad_card] == 0).all() and (strict[dup] == 0).all()
