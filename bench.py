@@ -27,7 +27,7 @@ SITUATIONS_PER_GPU = 65536
 SEED = 20251019
 EVALS_PER_SITUATION = 1_072_353          # 1,070,190 + 1,081 + 1,082
 ISSUED_EVALS_PER_SITUATION = 178_365 + 1_081 + 1_082 + 1_820   # what the deduplicating kernel actually evaluates
-ISSUED_SMEM_GATHERS_PER_4SET = 8         # Lcd, Lw, Lk, 4 x W row words, NF (kernels_hp_flop.cu run_task)
+ISSUED_SMEM_GATHERS_PER_4SET = 5         # W[a][c], W[b][c], W[c][d], X[suit][c], NF (kernels_hp_flop.cu, v3 walk)
 METRIC = "flop_hs_hp_situations_per_sec"
 UNIT = "situations/s"
 
@@ -296,6 +296,11 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     lookup_peak_random, _ = hb.smem_gather_microbench(table_bytes=4096, iters=4096, pattern=0, blocks_per_sm=2,
                                                       threads=1024, device=local_rank)
     lookup_peak_cf, _ = hb.smem_gather_microbench(table_bytes=4096, iters=4096, pattern=1, blocks_per_sm=2,
@@ -305,10 +310,12 @@ def main():
     issued = n_local * ISSUED_EVALS_PER_SITUATION / (kernel_ms * 1e-3)
     issued_gathers = n_local * 178_365 * ISSUED_SMEM_GATHERS_PER_4SET / (kernel_ms * 1e-3)
     roofline = {
-        "kernel": "hp_flop_treys_kernel", "bound": "smem_lookup",
+        "kernel": "hp_flop_treys_v3_kernel", "bound": "smem_lookup",
         "achieved": achieved / 1e9, "peak": lookup_peak_random / 1e9, "unit": "Glookup/s",
         "frac": achieved / lookup_peak_random,
-        "traffic": None,
+        "traffic": traffic.get("hp_flop_treys_v3_kernel", {}).get("dram_bytes_read", None) if traffic else None,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
+                        "(profiles/traffic.json); algorithmic HBM bytes per launch = 65,536 x 72 B = 4.7 MB",
         "note": "algorithmic = 1,072,353 evaluations (1 table lookup each) per situation x 65,536 situations per "
                 "launch / CUDA-event launch time; peak = uniformly random uint16 shared-memory gathers measured in "
                 "this run (4 KB table, the NF footprint class); the kernel deduplicates opponent hands (178,365 "
@@ -350,10 +357,13 @@ def main():
         ev_ok = bool(np.array_equal(out16[:200000].cpu().numpy().astype(np.uint16), O.treys_evaluate_batch(sample, 7)))
         extras["eval7_stream"] = {
             "evals_per_sec_per_gpu": ev_rate, "hands": n_hands, "ms": ev_ms, "verified_vs_oracle": ev_ok,
-            "roofline": {"kernel": "eval_batch_kernel<7,smem tables>", "bound": "hbm",
+            "roofline": {"kernel": "eval_batch_fast_kernel<7>", "bound": "hbm",
                          "achieved": 10 * ev_rate / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": 10 * ev_rate / 1e9 / hbm_peak, "peak_source": hbm_peak_src,
-                         "traffic": None, "note": "inputs 256 MiB + outputs 64 MiB per launch (> 126 MB L2)"}}
+                         "traffic": (lambda t: t.get("dram_bytes_read", 0) + t.get("dram_bytes_write", 0) if t else None)(
+                             traffic.get("eval_batch_fast_kernel<7>")),
+                         "note": "inputs 256 MiB + outputs 64 MiB per launch (> 126 MB L2); traffic from the committed ncu "
+                                 "capture (profiles/traffic.json)"}}
         del hands, out16
         # exhaustive sweep, hands generated in-kernel (BASELINE.json configs[1])
         hb.exhaustive7(local_rank)
@@ -397,9 +407,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sit_np.nbytes) * world,
                 "d2h_bytes_per_step": int(host_out.nbytes) * world, "steps": e2e_steps,
                 "api": "holdem_hp_batch_host (C ABI, host buffers; pinned staging, chunked H2D/kernel/D2H)"},
-        "gpu_launches": 2 * args.steps,
-        "gpu_launches_note": "per step: hp_flop_treys_kernel + hp_direct_kernel (second pass, exits at once when "
-                             "the batch holds no turn/river rows)",
+        "gpu_launches": 3 * args.steps,
+        "gpu_launches_note": "per step: hp_flop_treys_v3_kernel + hp_turn_treys_kernel + hp_direct_kernel (the last two "
+                             "exit at once when the batch holds no turn / river rows)",
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
