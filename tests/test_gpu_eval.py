@@ -114,3 +114,20 @@ def test_eval_large_batch_fast_and_strict_paths(hb, oracle, n_cards):
     good[dup] = False
     assert np.array_equal(fast[good], want[good]) and np.array_equal(strict[good], want[good])
     assert (fast[bad_card] == 0).all() and (strict[bad_card] == 0).all() and (strict[dup] == 0).all()
+
+
+def test_showdown_whole_table(hb, oracle):
+    """all 22 seats of a hand in one evaluator launch; winners under the correct rule and under the
+    reference's max() rule (GameBoard.py:210)."""
+    from holdem_b200 import table
+    hole, board = table.deal_tables(2000, seed=20251020, seats=22)
+    ranks = table.showdown_ranks(torch.from_numpy(hole).cuda(), torch.from_numpy(board).cuda())
+    rows = np.full((2000 * 22, 8), 255, dtype=np.uint8)
+    rows[:, 0:2] = hole.reshape(-1, 2)
+    rows[:, 2:7] = np.repeat(board, 22, axis=0)
+    want = oracle.treys_evaluate_batch(rows, 7).reshape(2000, 22)
+    assert np.array_equal(ranks.cpu().numpy().astype(np.uint16), want)
+    best = table.winners(ranks, "best").cpu().numpy()
+    ref = table.winners(ranks, "reference").cpu().numpy()
+    assert np.array_equal(best, want == want.min(axis=1, keepdims=True))
+    assert np.array_equal(ref, want == want.max(axis=1, keepdims=True))

@@ -187,3 +187,27 @@ def test_hp_turn_full_size_properties(hb):
     assert np.array_equal(hb.hand_strength_counts(d_sit, "treys").cpu().numpy(), r[:, 0:3])
     direct = hb.hand_potential_counts(d_sit[:8192].contiguous(), "treys", direct=True)
     assert torch.equal(rows[:8192], direct)
+
+
+def _oracle_chunk(args):
+    from oracle import oracle as O
+    sit_bytes, n, mode = args
+    sit = np.frombuffer(sit_bytes, dtype=np.uint8).reshape(n, 8)
+    return O.hp_batch(sit, mode).tobytes()
+
+
+def test_hp_treys_1024_flops_vs_oracle(hb):
+    """SURVEY 8d config 3 parity sample: the first 1,024 situations of the 65,536-situation bench workload, every count
+    of every row against the C oracle (run on all host cores)."""
+    import multiprocessing as mp
+    import os
+    sit = hb.random_situations(65536, seed=20251019)[:1024]
+    got = _u32(hb.hand_potential_counts(torch.from_numpy(sit).cuda(), "treys"))
+    workers = max(1, min(32, len(os.sched_getaffinity(0))))
+    chunks = [np.ascontiguousarray(sit[i::workers]) for i in range(workers)]
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_oracle_chunk, [(c.tobytes(), len(c), "treys") for c in chunks])
+    want = np.zeros((1024, 16), dtype=np.uint32)
+    for i, p in enumerate(parts):
+        want[i::workers] = np.frombuffer(p, dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(got, want)

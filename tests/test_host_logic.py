@@ -142,3 +142,48 @@ def test_dropin_surface():
     HC.set_mode("treys")
     with pytest.raises(ValueError):
         HC.set_mode("bogus")
+
+
+def test_policy_matches_reference_decision_golden():
+    """Batched Decision mirror vs golden vectors from the unmodified reference Decision.py (tests/golden/)."""
+    import json
+    from holdem_b200 import policy
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "decision_golden.json")))["cases"]
+    for pos in ("SB", "BB", "NONE"):
+        sub = [c for c in g if c[3] == pos]
+        hs = torch.tensor([c[0] for c in sub], dtype=torch.float64)
+        pp = torch.tensor([c[1] for c in sub], dtype=torch.float64)
+        npot = torch.tensor([c[2] for c in sub], dtype=torch.float64)
+        codes = policy.decide_batch(hs, pp, npot, pos).tolist()
+        want = [policy.NONE_TAKEN if c[4] is None else policy.ACTIONS.index(c[4]) for c in sub]
+        assert codes == want
+    # mixed positions in one call + the scalar form with the reference's signature
+    hs = torch.tensor([c[0] for c in g], dtype=torch.float64)
+    pp = torch.tensor([c[1] for c in g], dtype=torch.float64)
+    npot = torch.tensor([c[2] for c in g], dtype=torch.float64)
+    pos = torch.tensor([policy.POSITIONS[c[3]] for c in g])
+    assert policy.decide_batch(hs, pp, npot, pos).tolist() == \
+        [policy.NONE_TAKEN if c[4] is None else policy.ACTIONS.index(c[4]) for c in g]
+    for c in g[::97]:
+        assert policy.decision_based_on_blind_position(c[0], c[1], c[2], c[3]) == c[4]
+    with pytest.raises(ValueError):
+        policy.decision_based_on_blind_position(0.5, 0.5, 0.5, "UTG")
+    rows = torch.tensor([[558, 397, 126, 334713, 148530, 172965, 70272, 265983, 130617, 27162, 16905, 104109,
+                          558, 397, 126, 3]], dtype=torch.int32)
+    assert policy.decide_from_counts(rows, "BB").tolist() == [policy.CHECK]
+
+
+def test_table_helpers_cpu():
+    from holdem_b200 import table
+    hole, board = table.deal_tables(50, seed=20251020, seats=22)
+    assert hole.shape == (50, 22, 2) and board.shape == (50, 5)
+    for h in range(50):
+        cards = hole[h].reshape(-1).tolist() + board[h].tolist()
+        assert len(set(cards)) == 49 and max(cards) < 52
+    sit = table.situations_for_street(hole, board, 4)
+    assert sit.shape == (1100, 8) and (sit[:, 6:] == 255).all() and (sit[:, 2:6] == np.repeat(board[:, :4], 22, 0)).all()
+    ranks = torch.tensor([[10, 10, 7000, 3], [5, 9, 9, 2]], dtype=torch.int16)
+    assert table.winners(ranks, "best").tolist() == [[False, False, False, True], [False, False, False, True]]
+    assert table.winners(ranks, "reference").tolist() == [[False, False, True, False], [False, True, True, False]]
+    active = torch.tensor([[True, True, True, False], [True, True, True, True]])
+    assert table.winners(ranks, "best", active).tolist() == [[True, True, False, False], [False, False, False, True]]
