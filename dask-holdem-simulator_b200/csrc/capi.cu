@@ -178,6 +178,11 @@ int holdem_init(int device) {
     S.T.turn_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_lanes);
     S.T.nf3_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf3);
     S.T.n_turn_tasks = im.n_turn_tasks;
+    for (int q = 0; q < 2; ++q) {
+        S.T.ref_task_hdr[q] = reinterpret_cast<const uint32_t *>(S.image + im.off_ref_hdr[q]);
+        S.T.ref_lanes[q] = reinterpret_cast<const uint32_t *>(S.image + im.off_ref_lanes[q]);
+        S.T.n_ref_tasks[q] = im.n_ref_tasks[q];
+    }
     for (int i = 0; i < 3; ++i) {
         NfHash &h = S.T.nf[i];
         h.disp = reinterpret_cast<const uint16_t *>(S.image + im.off_disp[i]);
@@ -326,7 +331,7 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
 // deduplicating turn kernel, river rows (HS only) to the plain-enumeration kernel.  Both exit at once when not needed.  Reference mode: plain enumeration only.
 static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out,
                                cudaStream_t st) {
-    if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, nullptr, 0, st);
+    if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_ref(S.T, d_sit, n, d_out, S.sms, st);
     int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     static const int impl = (getenv("HOLDEM_FLOP_KERNEL") && atoi(getenv("HOLDEM_FLOP_KERNEL")) == 2) ? 2 : 3;
     cudaError_t e = launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st);

@@ -36,6 +36,9 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint32_t *turn_lanes;
     const uint16_t *nf3_ranks;      // [455] three ascending ranks, 4 bits each
     uint32_t n_turn_tasks;
+    const uint32_t *ref_task_hdr[2];  // reference-mode kernel, 46 / 45 unseen positions (47 uses the flop list)
+    const uint32_t *ref_lanes[2];
+    uint32_t n_ref_tasks[2];
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

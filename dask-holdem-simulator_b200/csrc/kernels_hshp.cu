@@ -6,8 +6,9 @@
 // hp_direct_kernel: one CTA per situation; one warp per opponent holding, lanes stride over the runouts; one opponent
 //                   evaluation per (holding, runout) pair exactly like the reference's nested loop (:193-218), but
 //                   our own final rank is computed once per runout instead of once per pair (:210).  This is the
-//                   independent second implementation the deduplicating flop kernel (kernels_hp_flop.cu) is checked
-//                   against, and the production path for HOLDEM_MODE_REFERENCE and for turn/river boards.
+//                   independent second implementation the deduplicating flop / turn kernels (kernels_hp_flop.cu,
+//                   kernels_hp_turn.cu) are checked against, and the production path for HOLDEM_MODE_REFERENCE (all
+//                   streets) and for Treys-mode river rows (HS only).
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -72,9 +73,11 @@ __device__ __forceinline__ int warp_list_complement(uint64_t excluded, uint8_t *
     return __popc(m0) + __popc(m1);
 }
 
-__device__ __forceinline__ LitHand lit_from_cards(const uint32_t *c, int n) {
+__device__ __forceinline__ LitHand lit_from_cards(const uint32_t (&c)[5], int n) {
     LitHand h = {0, 0, 0, 0, 0};
-    for (int k = 0; k < n; ++k) lit_add_card(h, c[k]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < n) lit_add_card(h, c[k]);
     return h;
 }
 
@@ -115,7 +118,8 @@ hs_kernel(const uint8_t *__restrict__ sit, int64_t n, int mode, uint32_t *__rest
         if (mode == kModeTreys) {
             const NfHash &h = T.nf[s.nb - 3];
             uint32_t kb = 0;
-            for (int k = 0; k < s.nb; ++k) kb += s_cardkey[s.board[k]];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) kb += k < s.nb ? s_cardkey[s.board[k]] : 0u;
             uint32_t ours = treys_rank(h, T.flush, kb + s_cardkey[s.hole[0]] + s_cardkey[s.hole[1]], s.known);
             for (int p = lane; p < n_opp; p += 32) {
                 uint32_t pr = __ldg(T.pairs + p);
@@ -219,7 +223,8 @@ hp_direct_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restric
             const int run_cards = 5 - s.nb;
             n_run = run_cards == 2 ? n_opp : (run_cards == 1 ? m : 0);
             const NfHash &hn = T.nf[s.nb - 3];
-            for (int k = 0; k < s.nb; ++k) kb += S.cardkey[s.board[k]];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) kb += k < s.nb ? S.cardkey[s.board[k]] : 0u;
             const uint32_t khole = S.cardkey[s.hole[0]] + S.cardkey[s.hole[1]];
             const uint32_t ours_now = treys_rank(hn, T.flush, kb + khole, s.known);
             for (int p = tid; p < n_opp; p += kHpThreads) {

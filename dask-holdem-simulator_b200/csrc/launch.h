@@ -32,4 +32,7 @@ cudaError_t launch_hp_turn_treys(const DevTables &T, const uint8_t *sit, int64_t
 cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                  int *other_rows_flag, int impl, cudaStream_t st);
 
+// HOLDEM_MODE_REFERENCE, all streets: 4-set walk for the regular runouts + arithmetic ranking of the irregular ones.
+cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
+
 }  // namespace holdem

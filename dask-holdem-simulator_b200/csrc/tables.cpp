@@ -106,6 +106,31 @@ bool build_hash(const std::vector<uint32_t> &keys, const std::vector<uint16_t> &
     return false;
 }
 
+// Work list over m positions: every (a,b,d), a<b<d-1<m-1, grouped by walk length d-b-1 into 32-lane tasks (see tables.h).
+void build_walk_list(int m, std::vector<uint32_t> &hdr_out, std::vector<uint32_t> &lanes_out) {
+    struct Task { uint32_t hdr; std::vector<uint32_t> lanes; };
+    std::vector<Task> tasks;
+    for (int L = m - 3; L >= 1; --L) {
+        std::vector<uint32_t> group;
+        for (int b = m - 2 - L; b >= 1; --b)
+            for (int a = 0; a < b; ++a) group.push_back((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(b + 1 + L) << 16));
+        for (size_t s0 = 0; s0 < group.size(); s0 += 32) {
+            std::vector<uint32_t> lanes(32, 0xFFFFFFFFu);
+            for (size_t l = 0; l < 32 && s0 + l < group.size(); ++l) lanes[l] = group[s0 + l];
+            // the kernels' packed 6-bit counters take at most 31 iterations between drains: split long walks
+            for (int k0 = 0; k0 < L; k0 += 31)
+                tasks.push_back({(uint32_t)k0 | ((uint32_t)std::min(31, L - k0) << 8), lanes});
+        }
+    }
+    std::stable_sort(tasks.begin(), tasks.end(), [](const Task &x, const Task &y) { return (x.hdr >> 8) > (y.hdr >> 8); });
+    for (const Task &tk : tasks) {
+        hdr_out.push_back(tk.hdr);
+        lanes_out.insert(lanes_out.end(), tk.lanes.begin(), tk.lanes.end());
+    }
+    while (hdr_out.size() % 4) hdr_out.push_back(0);  // 16-byte multiple; iters 0 = no-op
+    lanes_out.resize(hdr_out.size() * 32, 0xFFFFFFFFu);
+}
+
 struct Builder {
     Tables t;
     bool ok = false;
@@ -217,33 +242,10 @@ struct Builder {
         int p = 0;
         for (int j = 1; j < 52; ++j)
             for (int i = 0; i < j; ++i) t.pairs[p++] = (uint16_t)(i | (j << 8));
-        // ---- 6. flop kernel work list ------------------------------------------------------------------------------
-        {
-            struct Task { uint32_t hdr; std::vector<uint32_t> lanes; };
-            std::vector<Task> tasks;
-            for (int L = 44; L >= 1; --L) {
-                std::vector<uint32_t> group;
-                for (int b = 45 - L; b >= 1; --b)
-                    for (int a = 0; a < b; ++a) group.push_back((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(b + 1 + L) << 16));
-                for (size_t s0 = 0; s0 < group.size(); s0 += 32) {
-                    std::vector<uint32_t> lanes(32, 0xFFFFFFFFu);
-                    for (size_t l = 0; l < 32 && s0 + l < group.size(); ++l) lanes[l] = group[s0 + l];
-                    // the kernel's packed 6-bit counters take at most 31 iterations between drains: split long walks
-                    for (int k0 = 0; k0 < L; k0 += 31) {
-                        int iters = std::min(31, L - k0);
-                        tasks.push_back({(uint32_t)k0 | ((uint32_t)iters << 8), lanes});
-                    }
-                }
-            }
-            std::stable_sort(tasks.begin(), tasks.end(),
-                             [](const Task &x, const Task &y) { return (x.hdr >> 8) > (y.hdr >> 8); });
-            for (const Task &tk : tasks) {
-                t.flop_task_hdr.push_back(tk.hdr);
-                t.flop_lanes.insert(t.flop_lanes.end(), tk.lanes.begin(), tk.lanes.end());
-            }
-            while (t.flop_task_hdr.size() % 4) t.flop_task_hdr.push_back(0);  // 16-byte multiple; iters 0 = no-op
-            t.flop_lanes.resize(t.flop_task_hdr.size() * 32, 0xFFFFFFFFu);
-        }
+        // ---- 6. flop kernel work list (47 positions) and the reference-mode lists for 46 / 45 positions -----------------
+        build_walk_list(47, t.flop_task_hdr, t.flop_lanes);
+        build_walk_list(46, t.ref_task_hdr[0], t.ref_lanes[0]);
+        build_walk_list(45, t.ref_task_hdr[1], t.ref_lanes[1]);
         // ---- 6b. turn kernel work list -----------------------------------------------------------------------------------
         {
             struct Task { uint32_t hdr; std::vector<uint32_t> lanes; };
@@ -342,6 +344,13 @@ int selftest(char *msg, int msg_len) {
             }
         }
         if (sets != 178365) return fail("flop work list does not cover C(47,4)");
+        for (int q = 0; q < 2; ++q) {
+            sets = 0;
+            for (size_t tk = 0; tk < t.ref_task_hdr[q].size(); ++tk)
+                for (int l = 0; l < 32; ++l)
+                    if (t.ref_lanes[q][tk * 32 + l] != 0xFFFFFFFFu) sets += t.ref_task_hdr[q][tk] >> 8;
+            if (sets != (q == 0 ? 163185u : 148995u)) return fail("reference work list does not cover C(m,4)");
+        }
         sets = 0;
         for (size_t tk = 0; tk < t.turn_task_hdr.size(); ++tk) {
             uint32_t k0 = t.turn_task_hdr[tk] & 0xFF, iters = t.turn_task_hdr[tk] >> 8;
@@ -382,6 +391,11 @@ TableImage make_image(const Tables &t) {
     im.off_turn_lanes = append(t.turn_lanes.data(), t.turn_lanes.size() * 4);
     im.off_nf3 = append(t.nf3_ranks.data(), t.nf3_ranks.size() * 2);
     im.n_turn_tasks = (uint32_t)t.turn_task_hdr.size();
+    for (int q = 0; q < 2; ++q) {
+        im.off_ref_hdr[q] = append(t.ref_task_hdr[q].data(), t.ref_task_hdr[q].size() * 4);
+        im.off_ref_lanes[q] = append(t.ref_lanes[q].data(), t.ref_lanes[q].size() * 4);
+        im.n_ref_tasks[q] = (uint32_t)t.ref_task_hdr[q].size();
+    }
     for (int i = 0; i < 3; ++i) {
         im.off_disp[i] = append(t.nf[i].disp.data(), t.nf[i].disp.size() * 2);
         im.off_val[i] = append(t.nf[i].val.data(), t.nf[i].val.size() * 2);

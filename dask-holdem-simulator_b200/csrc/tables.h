@@ -57,6 +57,10 @@ struct Tables {
     std::vector<uint32_t> turn_task_hdr;
     std::vector<uint32_t> turn_lanes;
     std::vector<uint16_t> nf3_ranks;
+    // Work lists of the reference-mode kernel (kernels_hp_ref.cu) for 46 and 45 unseen positions (turn / river boards;
+    // the flop reuses flop_task_hdr / flop_lanes): same layout as the flop list.
+    std::vector<uint32_t> ref_task_hdr[2];   // [0]: 46 positions, [1]: 45 positions
+    std::vector<uint32_t> ref_lanes[2];
     // nf4_ranks[e] = the four ranks (4 bits each, ascending) of the e-th rank multiset, e = C(r0,1)+C(r1+1,2)+C(r2+2,3)+C(r3+3,4)
     std::vector<uint16_t> nf4_ranks;
     // Statistics kept for selftest().
@@ -72,6 +76,7 @@ struct TableImage {
     uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0;
     uint32_t n_tasks = 0;
     uint32_t off_turn_hdr = 0, off_turn_lanes = 0, off_nf3 = 0, n_turn_tasks = 0;
+    uint32_t off_ref_hdr[2] = {0, 0}, off_ref_lanes[2] = {0, 0}, n_ref_tasks[2] = {0, 0};
     uint32_t off_disp[3] = {0, 0, 0}, off_val[3] = {0, 0, 0};
 };
 TableImage make_image(const Tables &t);

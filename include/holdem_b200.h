@@ -116,7 +116,8 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
 
 /* Same results as holdem_hp_batch computed by the plain (non-deduplicating) enumeration kernel: one opponent
  * evaluation per (opponent holding, runout) pair.  Kept as the independent second implementation the parity
- * tests cross-check against, and as the only path for HOLDEM_MODE_REFERENCE and turn/river boards. */
+ * tests cross-check the deduplicating flop / turn kernels against; it is also what holdem_hp_batch itself runs for
+ * HOLDEM_MODE_REFERENCE and for Treys-mode river rows. */
 int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
 
 /* ---- roofline micro-benchmarks (bench.py) ---------------------------------------------------------------
