@@ -28,6 +28,7 @@ SEED = 20251019
 EVALS_PER_SITUATION = 1_072_353          # 1,070,190 + 1,081 + 1,082
 ISSUED_EVALS_PER_SITUATION = 178_365 + 1_081 + 1_082 + 1_820   # what the deduplicating kernel actually evaluates
 ISSUED_SMEM_GATHERS_PER_4SET = 5         # W[a][c], W[b][c], W[c][d], X[suit][c], NF (kernels_hp_flop.cu, v3 walk)
+WARP_INSTR_PER_SITUATION = 24669140132 / 65536   # smsp__inst_executed.sum of one launch (profiles/r1_hp_flop_v3_*)
 METRIC = "flop_hs_hp_situations_per_sec"
 UNIT = "situations/s"
 
@@ -325,6 +326,16 @@ def main():
         "issued_gathers_frac_of_conflict_free_peak": issued_gathers / lookup_peak_cf,
         "peak_conflict_free_Glookup_s": lookup_peak_cf / 1e9,
         "kernel_ms": kernel_ms,
+        "issue_slots": {
+            "warp_instructions_per_situation": WARP_INSTR_PER_SITUATION,
+            "achieved_warp_instr_per_sec": WARP_INSTR_PER_SITUATION * n_local / (kernel_ms * 1e-3),
+            "peak_warp_instr_per_sec": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
+            "frac": WARP_INSTR_PER_SITUATION * n_local / (kernel_ms * 1e-3)
+                    / (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+            "note": "the kernel is instruction-issue bound (ncu: smsp__issue_active 86.6 %, ALU pipe 71.8 %, FMA pipe "
+                    "32.5 %, shared-memory wavefronts 47.9 % of peak); warp instructions per situation = "
+                    "smsp__inst_executed.sum / 65,536 from the committed ncu capture, peak = 148 SMs x 4 schedulers x "
+                    "the SM clock sampled during this run"},
         "hbm_algorithmic_GBs": n_local * 72 / (kernel_ms * 1e-3) / 1e9, "hbm_peak_GBs": hbm_peak,
         "hbm_peak_source": hbm_peak_src,
     }
