@@ -12,8 +12,10 @@
 //             Categories come from a per-situation table NF[1820] over rank multisets of the four added cards (two
 //             nibbles per entry: the category without and with a flush present, because the reference tests "straight"
 //             before "flush") plus a suit/straight-flush test on the rare flush path.
-//   irregular Q touches P or our hole cards: 4m-2 = 186/182/178 per P.  These are ranked arithmetically from
-//             nibble-packed multiset counts (lit_category, device_common.cuh), one warp per P, lanes over Q.
+//   irregular Q touches P or our hole cards: 4m-2 = 186/182/178 per P, Q = {e, x} with e one of u, v, h0, h1.  Lane = P, the
+//             warp walks x together; the category comes from a second per-situation table NF2[pair of ranks][pair of
+//             ranks] (91 x 91 nibble pairs) and the suit logic is done on multiplicities (a repeated card counts twice
+//             towards the flush, and forbids the straight flush, exactly as the reference's Counter / set code does).
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -35,6 +37,7 @@ struct RefSmem {
     uint32_t cnt[12];                  // behind[3], ahead[3] (by class), class totals[3]
     uint32_t bmask[4];                 // board rank mask per suit
     uint8_t NF[kRNf + 4];              // category of board + 4-rank multiset: low nibble plain, high nibble with a flush
+    uint8_t NF2[91 * 91 + 3];          // the same table indexed by two rank pairs [pid(r,r')][pid(r'',r''')], pid(a<=b) = b(b+1)/2 + a
     uint8_t ourH[2][48];               // our category with runout {hole card h, position x}
     uint8_t code[64];                  // unseen cards, rank-major code rank*4+suit, ascending
 };
@@ -131,6 +134,24 @@ hp_ref_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__
             const uint32_t nfc = lit_category(h);
             const uint32_t with_flush = (nfc == 4u || nfc >= 6u) ? nfc : 5u;
             S.NF[e] = (uint8_t)(nfc | (with_flush << 4));
+        }
+        for (uint32_t e = tid; e < 91u * 91u; e += kRThreads) {   // pair-of-pairs view for the irregular runouts
+            const uint32_t p2 = e / 91u, q2 = e - 91u * p2;
+            uint32_t r4[4];
+            {   // unrank pid = b(b+1)/2 + a
+                uint32_t b = 0;
+                while ((b + 1) * (b + 2) / 2 <= p2) ++b;
+                r4[0] = p2 - b * (b + 1) / 2; r4[1] = b;
+                b = 0;
+                while ((b + 1) * (b + 2) / 2 <= q2) ++b;
+                r4[2] = q2 - b * (b + 1) / 2; r4[3] = b;
+            }
+            LitHand h = lb;
+            h.sc = 0; h.cards = 0; h.dup = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { h.rc += 1ull << (4 * r4[q]); h.rmask |= 1u << r4[q]; }
+            const uint32_t nfc = lit_category(h);
+            S.NF2[e] = (uint8_t)(nfc | (((nfc == 4u || nfc >= 6u) ? nfc : 5u) << 4));
         }
         __syncthreads();
         {   // per-position and per-pair tables
@@ -240,50 +261,73 @@ hp_ref_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__
             wide[3] += acc[3 + q] & 63u; wide[4] += (acc[3 + q] >> 6) & 63u; wide[5] += (acc[3 + q] >> 12) & 63u;
         }
 
-        // ---- irregular runouts: Q touches the holding or our hole cards; one warp per holding, lanes over the 4m+1 slots ------
+        // ---- irregular runouts: Q = {e, x} with e in {u, v, h0, h1} and x an unseen position, plus Q = {h0, h1}.  Lane = holding
+        //      P = (u,v); the warp walks x in step, so everything about x is warp-uniform and everything about P is hoisted.
+        //      The opponent's category comes from NF2[pid(ru,rv)][pid(re,rx)]; suit counts are multiplicities (a repeated
+        //      card counts twice, :56), a straight flush needs the flush suit's cards pairwise distinct (:26-27).
         {
             const uint32_t h0 = cb[0], h1 = cb[1];
-            const LitHand lh0 = r_one_card(h0), lh1 = r_one_card(h1);
-            const uint32_t our_hh = lit_category(lit_merge(lours, lit_merge(lh0, lh1)));   // runout = our own two cards
-            const uint32_t n_slots = 4 * m + 1;
-            for (uint32_t p = warp; p < n_pairs; p += kRWarps) {
-                const uint32_t pr = __ldg(T.pairs + p);
+            const uint32_t rh0 = card_rank(h0), sh0 = card_suit(h0), rh1 = card_rank(h1), sh1 = card_suit(h1);
+            const uint64_t bh0 = card_bit(h0), bh1 = card_bit(h1);
+            const uint32_t our_hh = lit_category(lit_merge(lours, lit_merge(r_one_card(h0), r_one_card(h1))));
+            const uint32_t scb3 = scb - 0x1111u;   // bias 3: bit 3 of a nibble set <=> that suit holds >= 5 cards
+            const uint32_t half = (m + 1) / 2;
+            const uint32_t n_ptasks = (n_pairs + 31) / 32;
+            for (uint32_t t = warp; t < 2 * n_ptasks; t += kRWarps) {
+                const uint32_t p = (t >> 1) * 32 + lane;
+                const bool live = p < n_pairs;
+                const uint32_t pr = __ldg(T.pairs + (live ? p : 0u));
                 const uint32_t u = pr & 0xFFu, v = pr >> 8;
-                const uint32_t cu = r_path_of_code(S.code[u]), cv = r_path_of_code(S.code[v]);
+                const uint32_t cdu = S.code[u], cdv = S.code[v];
+                const uint32_t ru = cdu >> 2, su = cdu & 3u, rv = cdv >> 2, sv = cdv & 3u;
+                const uint64_t bu = card_bit(r_path_of_code(cdu)), bv = card_bit(r_path_of_code(cdv));
+                const uint64_t cs_bp = bset | bu | bv;
+                const uint32_t sc_bp = scb3 + (1u << (4 * su)) + (1u << (4 * sv));
+                const uint32_t p2row = (rv * (rv + 1) / 2 + ru) * 91u;
                 const uint32_t wuv = S.W[u * kRPitch + v];
                 const uint32_t cls = (wuv & 63u) ? 0u : ((wuv & (63u << 6)) ? 1u : 2u);
-                const LitHand lbp = lit_merge(lb, lit_merge(r_one_card(cu), r_one_card(cv)));
                 uint32_t behind = 0, ahead = 0;
-                for (uint32_t sidx = lane; sidx < n_slots; sidx += 32) {
-                    // slot -> runout {e, x}: kind 0: e=u, 1: e=v, 2: e=h0, 3: e=h1 (x = an unseen position); last slot: {h0,h1}
-                    const uint32_t kind = sidx >= 3 * m ? (sidx >= 4 * m ? 4u : 3u) : (sidx >= 2 * m ? 2u : (sidx >= m ? 1u : 0u));
-                    const uint32_t x = sidx - (kind < 4 ? kind : 0u) * m;
-                    bool valid = true;
-                    uint32_t ours, ecard = cu, xcard = 0;
-                    if (kind == 4) {
-                        ecard = h0; xcard = h1; ours = our_hh;
-                    } else {
-                        xcard = r_path_of_code(S.code[x]);
-                        if (kind == 0) {            // {u, x}, x != u   (x == v is the runout Q == P)
-                            valid = x != u;
-                            ours = S.W[(x < u ? x : u) * kRPitch + (x < u ? u : x)] >> 19;
-                        } else if (kind == 1) {     // {v, x}, x not in P (the pair {u,v} was counted under kind 0)
-                            ecard = cv;
-                            valid = x != u && x != v;
-                            ours = S.W[(x < v ? x : v) * kRPitch + (x < v ? v : x)] >> 19;
-                        } else {                    // {h, x}: the runout repeats one of our hole cards
-                            ecard = kind == 2 ? h0 : h1;
-                            ours = S.ourH[kind - 2][x];
-                        }
+
+                // one runout {e, x}: e has rank re / suit se / bit be and is (e_in_p) or is not one of the opponent's own cards
+                auto item = [&](uint32_t re, uint32_t se, uint64_t be, bool e_in_p, uint32_t ours, bool valid,
+                                uint32_t rx, uint32_t sx, uint64_t bx, bool x_in_p) {
+                    const uint32_t lo_r = re < rx ? re : rx, hi_r = re < rx ? rx : re;
+                    const uint32_t e8 = S.NF2[p2row + hi_r * (hi_r + 1) / 2 + lo_r];
+                    const uint32_t fl = (sc_bp + (1u << (4 * se)) + (1u << (4 * sx))) & 0x8888u;
+                    uint32_t opp = e8 & 15u;
+                    if (fl) {
+                        const uint32_t s = (uint32_t)(__ffs(fl) - 1) >> 2;
+                        opp = e8 >> 4;
+                        const bool repeated = (e_in_p && se == s) || (x_in_p && sx == s);
+                        const uint32_t fm = (uint32_t)((cs_bp | be | bx) >> (13 * s)) & 0x1FFFu;
+                        if (!repeated && cyclic_run5(fm)) opp = 8u;
                     }
-                    if (valid) {
-                        const uint32_t opp = lit_category(lit_merge(lbp, lit_merge(r_one_card(ecard), r_one_card(xcard))));   // :211
-                        behind += ours < opp;
-                        ahead += ours > opp;
-                    }
+                    if (valid) { behind += ours < opp; ahead += ours > opp; }
+                };
+
+                const uint32_t x_lo = (t & 1u) ? half : 0u, x_hi = (t & 1u) ? m : half;
+                for (uint32_t x = x_lo; x < x_hi; ++x) {
+                    const uint32_t cdx = S.code[x];
+                    const uint32_t rx = cdx >> 2, sx = cdx & 3u;
+                    const uint64_t bx = card_bit(r_path_of_code(cdx));
+                    const bool x_in_p = x == u || x == v;
+                    // {u, x}, x != u (x == v is the runout Q == P); our category is that of the plain pair runout
+                    item(ru, su, bu, true, S.W[(x < u ? x : u) * kRPitch + (x < u ? u : x)] >> 19, live && x != u,
+                         rx, sx, bx, x_in_p);
+                    // {v, x}, x outside P
+                    item(rv, sv, bv, true, S.W[(x < v ? x : v) * kRPitch + (x < v ? v : x)] >> 19, live && !x_in_p,
+                         rx, sx, bx, x_in_p);
+                    // {h0, x}, {h1, x}: the runout repeats one of OUR hole cards (never one of the opponent's)
+                    item(rh0, sh0, bh0, false, S.ourH[0][x], live, rx, sx, bx, x_in_p);
+                    item(rh1, sh1, bh1, false, S.ourH[1][x], live, rx, sx, bx, x_in_p);
                 }
-                wide[cls] += behind;
-                wide[3 + cls] += ahead;
+                if ((t & 1u) == 0)   // {h0, h1}: once per holding
+                    item(rh0, sh0, bh0, false, our_hh, live, rh1, sh1, bh1, false);
+                if (live) {
+                    if (cls == 0) { wide[0] += behind; wide[3] += ahead; }
+                    else if (cls == 1) { wide[1] += behind; wide[4] += ahead; }
+                    else { wide[2] += behind; wide[5] += ahead; }
+                }
             }
         }
 #pragma unroll
