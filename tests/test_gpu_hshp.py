@@ -211,3 +211,49 @@ def test_hp_treys_1024_flops_vs_oracle(hb):
     for i, p in enumerate(parts):
         want[i::workers] = np.frombuffer(p, dtype=np.uint32).reshape(-1, 16)
     assert np.array_equal(got, want)
+
+
+def test_host_entry_chunked_pipeline_matches_device_entry(hb):
+    """The *_host entry points stream large batches through pinned staging in chunks (32,768 rows for HP, 2^20 for HS):
+    a batch spanning several chunks with a ragged tail must equal the device entry row for row, in both modes."""
+    n = 2 * 32768 + 4097
+    sit = hb.random_situations(n, seed=404)
+    d_sit = torch.from_numpy(sit).cuda()
+    for mode in ("treys", "reference"):
+        dev = _u32(hb.hand_potential_counts(d_sit, mode))
+        host = hb.hand_potential_counts_host(sit, mode)
+        assert host.dtype == np.uint32 and np.array_equal(host, dev), mode
+    big = hb.random_situations((1 << 20) + 12345, seed=405, n_board=5)
+    assert np.array_equal(hb.hand_strength_counts_host(big, "treys"),
+                          _u32(hb.hand_strength_counts(torch.from_numpy(big).cuda(), "treys")))
+
+
+def test_concurrent_streams_and_threads(hb, oracle):
+    """Device entry points are stream-ordered and thread-safe: four host threads, each on its own CUDA stream."""
+    import threading
+    sit = hb.random_situations(256, seed=406)
+    want = oracle.hp_batch(sit[:32], "treys")
+    d_sit = torch.from_numpy(sit).cuda()
+    ref = hb.hand_potential_counts(d_sit, "treys").clone()
+    torch.cuda.synchronize()
+    results, errors = [None] * 4, []
+
+    def worker(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                outs = [hb.hand_potential_counts(d_sit, "treys") for _ in range(5)]
+                outs.append(hb.hand_potential_counts(d_sit[:64].contiguous(), "reference"))
+            st.synchronize()
+            results[i] = outs
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+    ref64 = hb.hand_potential_counts(d_sit[:64].contiguous(), "reference", direct=True)
+    for outs in results:
+        assert all(torch.equal(o, ref) for o in outs[:5]) and torch.equal(outs[5], ref64)
+    assert np.array_equal(_u32(ref[:32]), want)
