@@ -274,6 +274,9 @@ struct Flop3Smem {
     uint32_t W[kRows3 * kPitch3];      // [i][j], i<j<47: our7 << 19 | one-hot class; everything else stays zero
     uint32_t X[4 * kXPitch];           // [suit][i]: C(r_i+2,3) | (suit_i == suit ? 1 << r_i : 0) << 16; i >= 47 zero
     uint32_t I[48];                    // per position: r | C(r+1,2) << 4 | C(r+3,4) << 11 | suit << 22
+    uint32_t NF32[kNf + 4];            // non-flush rank << 19 (the compare threshold, ready to use)
+    uint16_t Xb[4 * kXPitch];          // [suit][i]: rank bit of i if it has that suit (high half of X, as its own array)
+    uint16_t C3x4[kXPitch];            // per position: 4 * C(r_i+2,3) = byte offset contribution into NF32
     uint16_t NF[kNf + 4];
     uint32_t cardkey[64];
     uint32_t cnt[12];
@@ -303,7 +306,8 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         uint4 *dst = reinterpret_cast<uint4 *>(S.flush);
         for (uint32_t i = tid; i < kFlushEntries / 8; i += kThreads) dst[i] = src[i];
         for (uint32_t i = tid; i < (uint32_t)(kRows3 * kPitch3); i += kThreads) S.W[i] = 0;   // pad rows stay zero
-        for (uint32_t i = tid; i < (uint32_t)(4 * kXPitch); i += kThreads) S.X[i] = 0;
+        for (uint32_t i = tid; i < (uint32_t)(4 * kXPitch); i += kThreads) { S.X[i] = 0; S.Xb[i] = 0; }
+        if (tid < (uint32_t)kXPitch) S.C3x4[tid] = 0;
         if (tid < 64) S.cardkey[tid] = tid < 52 ? c_rank_key[tid % 13] : 0u;
     }
     const NfHash h5 = T.nf[0], h7 = T.nf[2];
@@ -363,7 +367,7 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     prev = r;
                     valid = valid && (run + ((bcnt >> (2 * r)) & 3u) <= 4);
                 }
-                S.NF[e] = valid ? (uint16_t)nf_lookup(h7, key) : (uint16_t)0;
+                S.NF32[e] = valid ? nf_lookup(h7, key) << 19 : 0u;
             }
         }
         __syncthreads();
@@ -372,8 +376,11 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t cd = S.code[tid], r = cd >> 2, su = cd & 3u;
                 S.I[tid] = r | (choose2(r + 1) << 4) | (choose4(r + 3) << 11) | (su << 22);
 #pragma unroll
-                for (uint32_t s2 = 0; s2 < 4; ++s2)
+                for (uint32_t s2 = 0; s2 < 4; ++s2) {
                     S.X[s2 * kXPitch + tid] = choose3(r + 2) | ((su == s2 ? (1u << r) : 0u) << 16);
+                    S.Xb[s2 * kXPitch + tid] = (uint16_t)(su == s2 ? (1u << r) : 0u);
+                }
+                S.C3x4[tid] = (uint16_t)(4u * choose3(r + 2));
             }
             const uint32_t ours_now = treys_rank(h5, S.flush, kb + khole, known);
             uint32_t c0 = 0, c1 = 0, c2 = 0;
@@ -421,7 +428,8 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             since += iters;
             // ---- lane invariants ---------------------------------------------------------------------------------------
             uint32_t wab = 0, wad = 0, wbd = 0, nf = 0, mask6 = 0;
-            const uint32_t *pac = S.W + 47 * kPitch3, *pbc = pac, *pcd = pac, *px = S.X + 48;   // zero words
+            const uint32_t *pac = S.W + 47 * kPitch3, *pbc = pac, *pcd = pac;   // zero words
+            const uint16_t *pxb = S.Xb + 48, *pc3 = S.C3x4 + 48;
             if (trip != 0xFFFFFFFFu) {
                 const uint32_t a = trip & 0xFFu, b = (trip >> 8) & 0xFFu, d = (trip >> 16) & 0xFFu;
                 const uint32_t ia = S.I[a], ib = S.I[b], id = S.I[d];
@@ -442,17 +450,20 @@ hp_flop_treys_v3_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 pac = S.W + a * kPitch3 + c0i;
                 pbc = S.W + b * kPitch3 + c0i;
                 pcd = S.W + c0i * kPitch3 + d;
-                px = S.X + sf * kXPitch + c0i;
+                pxb = S.Xb + sf * kXPitch + c0i;
+                pc3 = S.C3x4 + c0i;
+                nf *= 4u;   // byte offset into NF32
             }
             // ---- the walk over c --------------------------------------------------------------------------------------------
 #pragma unroll 4
             for (uint32_t k = 0; k < iters; ++k) {
-                const uint32_t wac = *pac, wbc = *pbc, wcd = *pcd, x = *px;
-                ++pac; ++pbc; ++px; pcd += kPitch3;
-                uint32_t R = S.NF[nf + (x & 0xFFFFu)];
-                const uint32_t m = mask6 | (x >> 16);
-                if (__popc(m) >= 5) R = S.flush[m];
-                const uint32_t lo = R << 19, hi = lo + (1u << 19);
+                const uint32_t wac = *pac, wbc = *pbc, wcd = *pcd;
+                const uint32_t xb = *pxb, c3 = *pc3;
+                ++pac; ++pbc; ++pxb; ++pc3; pcd += kPitch3;
+                uint32_t lo = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(S.NF32) + nf + c3);
+                const uint32_t m = mask6 | xb;
+                if (__popc(m) >= 5) lo = (uint32_t)S.flush[m] << 19;
+                const uint32_t hi = lo + (1u << 19);
                 add_if_lt(acc[0], wcd, lo, wab, one);  add_if_ge(acc[3], wcd, hi, wab, one);   // P=ab Q=cd
                 add_if_lt(acc[0], wab, lo, wcd, one);  add_if_ge(acc[3], wab, hi, wcd, one);   // P=cd Q=ab
                 add_if_lt(acc[1], wbd, lo, wac, one);  add_if_ge(acc[4], wbd, hi, wac, one);   // P=ac Q=bd
