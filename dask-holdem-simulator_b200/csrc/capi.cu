@@ -173,6 +173,7 @@ int holdem_init(int device) {
     S.T.flop_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_task_hdr);
     S.T.flop_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_lanes);
     S.T.nf4_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf4);
+    S.T.idx4 = reinterpret_cast<const uint16_t *>(S.image + im.off_idx4);
     S.T.n_flop_tasks = im.n_tasks;
     S.T.turn_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_hdr);
     S.T.turn_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_lanes);
@@ -333,8 +334,10 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
                                cudaStream_t st) {
     if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_ref(S.T, d_sit, n, d_out, S.sms, st);
     int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    static const int impl = (getenv("HOLDEM_FLOP_KERNEL") && atoi(getenv("HOLDEM_FLOP_KERNEL")) == 2) ? 2 : 3;
-    cudaError_t e = launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st);
+    // HOLDEM_FLOP_KERNEL=3 / 2 select the earlier 4-set kernels (kept for A/B measurements and cross-checks)
+    static const int impl = getenv("HOLDEM_FLOP_KERNEL") ? atoi(getenv("HOLDEM_FLOP_KERNEL")) : 4;
+    cudaError_t e = (impl == 2 || impl == 3) ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st)
+                                             : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
     e = launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
@@ -358,6 +361,18 @@ int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if ((rc = check_mode(mode))) return rc;
     CUDA_TRY(launch_hp_direct(S->T, d_sit, n, mode, d_out, S->sms, nullptr, 0, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (variant < 2 || variant > 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
+    int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (cudaStream_t)stream));
+    else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, flag, variant, (cudaStream_t)stream));
     return HOLDEM_OK;
 }
 

@@ -39,6 +39,7 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint32_t *ref_task_hdr[2];  // reference-mode kernel, 46 / 45 unseen positions (47 uses the flop list)
     const uint32_t *ref_lanes[2];
     uint32_t n_ref_tasks[2];
+    const uint16_t *idx4;             // [91*91] two rank pairs -> index into the 1820 four-rank multisets
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

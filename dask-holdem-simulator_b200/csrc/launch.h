@@ -31,6 +31,9 @@ cudaError_t launch_hp_turn_treys(const DevTables &T, const uint8_t *sit, int64_t
 // impl: 3 = lane-per-(a,b,d) kernel (default), 2 = the earlier warp-per-(a,b) kernel (kept for A/B measurements).
 cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                  int *other_rows_flag, int impl, cudaStream_t st);
+// Rank-multiset flop kernel (kernels_hp_flop4.cu): same contract and bit-identical counts, the default.
+cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
+                                    int *other_rows_flag, cudaStream_t st);
 
 // HOLDEM_MODE_REFERENCE, all streets: 4-set walk for the regular runouts + arithmetic ranking of the irregular ones.
 cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);

@@ -284,6 +284,18 @@ struct Builder {
                                 (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24;
                         t.nf4_ranks[e] = (uint16_t)(r0 | (r1 << 4) | (r2 << 8) | (r3 << 12));
                     }
+        // ---- 8. two rank pairs -> four-rank multiset index -------------------------------------------------------------------
+        t.idx4.assign(91 * 91 + 7, 0);
+        for (int q2 = 0; q2 < 13; ++q2)
+            for (int q1 = 0; q1 <= q2; ++q1)
+                for (int y = 0; y < 13; ++y)
+                    for (int x = 0; x <= y; ++x) {
+                        int r[4] = {q1, q2, x, y};
+                        std::sort(r, r + 4);
+                        int e = r[0] + (r[1] + 1) * r[1] / 2 + (r[2] + 2) * (r[2] + 1) * r[2] / 6 +
+                                (r[3] + 3) * (r[3] + 2) * (r[3] + 1) * r[3] / 24;
+                        t.idx4[91 * (q2 * (q2 + 1) / 2 + q1) + y * (y + 1) / 2 + x] = (uint16_t)e;
+                    }
         ok = true;
     }
 };
@@ -368,6 +380,17 @@ int selftest(char *msg, int msg_len) {
             int r0 = v & 15, r1 = (v >> 4) & 15, r2 = (v >> 8) & 15, r3 = v >> 12;
             if (!(r0 <= r1 && r1 <= r2 && r2 <= r3 && r3 < 13)) return fail("nf4 ranks");
         }
+        for (int e = 0; e < 91 * 91; ++e) {   // idx4 points at the multiset made of the two pairs' ranks
+            int qp = e / 91, pp = e % 91, q2 = 0, y = 0;
+            while ((q2 + 1) * (q2 + 2) / 2 <= qp) ++q2;
+            while ((y + 1) * (y + 2) / 2 <= pp) ++y;
+            int want[4] = {qp - q2 * (q2 + 1) / 2, q2, pp - y * (y + 1) / 2, y};
+            std::sort(want, want + 4);
+            uint16_t v = t.nf4_ranks[t.idx4[e]];
+            int got[4] = {v & 15, (v >> 4) & 15, (v >> 8) & 15, v >> 12};
+            for (int k = 0; k < 4; ++k)
+                if (got[k] != want[k]) return fail("idx4");
+        }
     }
     if (msg && msg_len > 0) msg[0] = 0;
     return 0;
@@ -386,6 +409,7 @@ TableImage make_image(const Tables &t) {
     im.off_task_hdr = append(t.flop_task_hdr.data(), t.flop_task_hdr.size() * 4);
     im.off_lanes = append(t.flop_lanes.data(), t.flop_lanes.size() * 4);
     im.off_nf4 = append(t.nf4_ranks.data(), t.nf4_ranks.size() * 2);
+    im.off_idx4 = append(t.idx4.data(), t.idx4.size() * 2);
     im.n_tasks = (uint32_t)t.flop_task_hdr.size();
     im.off_turn_hdr = append(t.turn_task_hdr.data(), t.turn_task_hdr.size() * 4);
     im.off_turn_lanes = append(t.turn_lanes.data(), t.turn_lanes.size() * 4);

@@ -120,6 +120,11 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
  * HOLDEM_MODE_REFERENCE and for Treys-mode river rows. */
 int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
 
+/* Treys-mode flop rows through one named implementation of the flop kernel (A/B measurements and cross-checks; every
+ * variant returns the same counts): 4 = rank-multiset kernel (what holdem_hp_batch runs), 3 = deduplicating 4-set walk,
+ * 2 = the earlier warp-per-pair 4-set kernel.  Rows with 4- or 5-card boards are left untouched. */
+int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
+
 /* ---- roofline micro-benchmarks (bench.py) ---------------------------------------------------------------
  * Issues `iters` dependent uniformly-random uint16 gathers per thread over a shared-memory table of
  * `table_bytes` from every lane of a full grid and returns the elapsed device time (CUDA events on `stream`).

@@ -1,0 +1,176 @@
+"""CPU prototype of the rank-multiset flop HS+HP algorithm (kernels_hp_flop4.cu), checked against the oracle.
+
+Test infrastructure: validates the counting identity the CUDA kernel relies on before any GPU time is spent.
+  HP[cls(P)][cmp(our7[Q], R(P,Q))] summed over disjoint (P,Q)
+    = generic part  : sum over Q, over rank pairs pp of n_Q(pp) * [clsr(pp)] x cmp(our7[Q], NF(board+Q+pp))
+    + flush part    : for every (P,Q) where board+Q has k>=3 cards of a suit s and P holds >= 5-k cards of s:
+                      + [cls(P)] x cmp(our7[Q], flush(board+Q+P in s))  - [clsr(P)] x cmp(our7[Q], NF(board+Q+P))
+"""
+import itertools
+import sys
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O
+
+
+def evaluate_rows(rows, n):
+    a = np.full((len(rows), 8), 255, dtype=np.uint8)
+    a[:, :n] = np.array(rows, dtype=np.uint8)
+    return O.treys_evaluate_batch(a, n).astype(np.int64)
+
+
+def nonflush_cards(ranks):
+    """cards with the given rank multiset and no five of a suit (same-rank cards get different suits)."""
+    ranks = sorted(ranks)
+    return [13 * (i % 4) + r for i, r in enumerate(ranks)]
+
+
+def pp_index(x, y):
+    return y * (y + 1) // 2 + x
+
+
+def flop_counts(hole, board):
+    known = set(hole) | set(board)
+    U = sorted((c for c in range(52) if c not in known), key=lambda c: (c % 13, c // 13))
+    n = len(U)
+    assert n == 47
+    rk = [c % 13 for c in U]
+    su = [c // 13 for c in U]
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    our7 = dict(zip(pairs, evaluate_rows([list(hole) + list(board) + [U[i], U[j]] for i, j in pairs], 7)))
+    opp5 = dict(zip(pairs, evaluate_rows([list(board) + [U[i], U[j]] for i, j in pairs], 5)))
+    ours_now = int(evaluate_rows([list(hole) + list(board)], 5)[0])
+    cls = {p: (0 if ours_now < v else (1 if ours_now == v else 2)) for p, v in opp5.items()}
+    tot = [sum(1 for p in pairs if cls[p] == i) for i in range(3)]
+    brk = [c % 13 for c in board]
+    u = [rk.count(r) for r in range(13)]
+    # rank-level tables
+    rank_pairs = [(x, y) for y in range(13) for x in range(y + 1)]
+    assert all(pp_index(x, y) == k for k, (x, y) in enumerate(rank_pairs))
+    # clsr: class from ranks only (non-flush 5-card rank of board + x + y)
+    def valid(ms):
+        return all(ms.count(r) <= 4 for r in set(ms))
+    rows5, idx5 = [], []
+    for k, (x, y) in enumerate(rank_pairs):
+        ms = brk + [x, y]
+        if valid(ms):
+            rows5.append(nonflush_cards(ms)); idx5.append(k)
+    v5 = evaluate_rows(rows5, 5)
+    clsr = [None] * 91
+    for k, v in zip(idx5, v5):
+        clsr[k] = 0 if ours_now < v else (1 if ours_now == v else 2)
+    # board monotone: the 5-card class from ranks must ignore the flush; nonflush_cards does that
+    T = np.zeros((91, 91), dtype=np.int64)
+    rows7, idx7 = [], []
+    for qk, (q1, q2) in enumerate(rank_pairs):
+        for pk, (x, y) in enumerate(rank_pairs):
+            ms = brk + [q1, q2, x, y]
+            if valid(ms):
+                rows7.append(nonflush_cards(ms)); idx7.append((qk, pk))
+    v7 = evaluate_rows(rows7, 7)
+    for (qk, pk), v in zip(idx7, v7):
+        T[qk, pk] = v
+    lt = [0, 0, 0]
+    gt = [0, 0, 0]
+    # ---- generic part
+    for (i, j) in pairs:
+        q1, q2 = rk[i], rk[j]
+        qk = pp_index(q1, q2)
+        o = int(our7[(i, j)])
+        chk = 0
+        for pk, (x, y) in enumerate(rank_pairs):
+            mx = u[x] - (x == q1) - (x == q2)
+            my = u[y] - (y == q1) - (y == q2)
+            nn = mx * my if x != y else mx * (mx - 1) // 2
+            if nn <= 0:
+                continue
+            chk += nn
+            R = T[qk, pk]
+            assert R > 0
+            c = clsr[pk]
+            if o < R:
+                lt[c] += nn
+            elif o > R:
+                gt[c] += nn
+        assert chk == 990
+    # ---- flush part
+    flush_cache = {}
+    def flush_rank(mask):
+        if mask not in flush_cache:
+            rs = [r for r in range(13) if mask >> r & 1]
+            best = min(int(v) for v in evaluate_rows([list(c) for c in itertools.combinations(rs, 5)], 5))
+            flush_cache[mask] = best
+        return flush_cache[mask]
+    n_items = 0
+    for s in range(4):
+        b_s = sum(1 for c in board if c // 13 == s)
+        if b_s == 0:
+            continue
+        bmask = sum(1 << (c % 13) for c in board if c // 13 == s)
+        Ls = [i for i in range(n) if su[i] == s]
+        Lns = [i for i in range(n) if su[i] != s]
+        both = [(a, b) for a, b in itertools.combinations(Ls, 2)]
+        one = [tuple(sorted((a, z))) for a in Ls for z in Lns]
+        none = [(a, b) for a, b in itertools.combinations(Lns, 2)]
+        plist = {2: both, 1: both + one, 0: both + one + none}
+        for qtype, qlist in ((2, both), (1, one), (0, none)):
+            k = b_s + qtype
+            if k < 3:
+                continue
+            need = 5 - k
+            for (i, j) in qlist:
+                o = int(our7[(i, j)])
+                qk = pp_index(rk[i], rk[j])
+                fq = bmask | sum(1 << rk[t] for t in (i, j) if su[t] == s)
+                for (a, b) in plist[need]:
+                    if a in (i, j) or b in (i, j):
+                        continue
+                    n_items += 1
+                    m = fq | sum(1 << rk[t] for t in (a, b) if su[t] == s)
+                    Rf = flush_rank(m)
+                    pk = pp_index(rk[a], rk[b])
+                    Rn = T[qk, pk]
+                    ct, cr = cls[(a, b)], clsr[pk]
+                    if o < Rf: lt[ct] += 1
+                    elif o > Rf: gt[ct] += 1
+                    if o < Rn: lt[cr] -= 1
+                    elif o > Rn: gt[cr] -= 1
+    row = np.zeros(16, dtype=np.int64)
+    row[0:3] = tot
+    for i in range(3):
+        row[3 + 3 * i + 0] = lt[i]
+        row[3 + 3 * i + 2] = gt[i]
+        row[3 + 3 * i + 1] = 990 * tot[i] - lt[i] - gt[i]
+    row[12:15] = tot
+    row[15] = 3
+    return row, n_items
+
+
+def main():
+    import random
+    rng = random.Random(7)
+    sits = []
+    # crafted textures: monotone board (+ suited hole in / out of the suit), two-tone, rainbow, paired boards
+    sits += [([14, 1], [31, 32, 33]), ([0, 1], [2, 3, 4]), ([0, 13], [5, 7, 9]), ([12, 11], [0, 2, 4]),
+             ([26, 27], [0, 2, 17]), ([12, 25], [38, 51, 0]), ([5, 18], [31, 44, 6]), ([3, 4], [5, 6, 20]),
+             ([12, 11], [10, 9, 8]), ([13, 26], [0, 1, 15])]
+    for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 20):
+        c = rng.sample(range(52), 5)
+        sits.append((c[:2], c[2:]))
+    packed = O.pack_situations(sits)
+    want = O.hp_batch(packed, "treys").astype(np.int64)
+    bad = 0
+    for k, (h, b) in enumerate(sits):
+        got, n_items = flop_counts(h, b)
+        ok = np.array_equal(got, want[k])
+        print(k, h, b, "items", n_items, "OK" if ok else f"MISMATCH\n got {got}\n want {want[k]}")
+        bad += not ok
+    print("mismatches:", bad)
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)

@@ -257,3 +257,35 @@ def test_concurrent_streams_and_threads(hb, oracle):
     for outs in results:
         assert all(torch.equal(o, ref) for o in outs[:5]) and torch.equal(outs[5], ref64)
     assert np.array_equal(_u32(ref[:32]), want)
+
+
+def _texture_situations(hb):
+    """Flops chosen by suit texture: monotone / two-tone / rainbow boards, hole cards inside and outside the board's
+    suits, paired and tripled boards, wheel and broadway draws -- the cases where the rank-multiset kernel's flush
+    corrections differ."""
+    cases = [([14, 1], [31, 32, 33]), ([0, 1], [2, 3, 4]), ([0, 13], [5, 7, 9]), ([12, 11], [0, 2, 4]),
+             ([26, 27], [0, 2, 17]), ([12, 25], [38, 51, 0]), ([5, 18], [31, 44, 6]), ([3, 4], [5, 6, 20]),
+             ([12, 11], [10, 9, 8]), ([13, 26], [0, 1, 15]), ([0, 12], [13, 26, 39]), ([1, 14], [0, 13, 26]),
+             ([12, 3], [0, 1, 2]), ([25, 38], [0, 1, 2]), ([12, 51], [0, 13, 3]), ([8, 9], [10, 11, 25]),
+             ([21, 47], [8, 34, 9]), ([7, 20], [33, 46, 6]), ([39, 40], [41, 42, 0]), ([50, 51], [49, 48, 47])]
+    return hb.pack_situations([c[0] for c in cases], [c[1] for c in cases])
+
+
+def test_hp_flop_variants_agree_and_match_oracle(hb, oracle):
+    """The three flop kernels (rank-multiset v4 = production, 4-set walk v3, warp-per-pair v2) and the plain enumeration
+    return identical rows; texture cases and 96 random deals are also checked against the CPU oracle."""
+    sit = np.concatenate([_texture_situations(hb), hb.random_situations(96, seed=811)])
+    want = oracle.hp_batch(sit, "treys")
+    d_sit = torch.from_numpy(sit).cuda()
+    for variant in (4, 3, 2):
+        got = _u32(hb.hand_potential_counts(d_sit, "treys", flop_variant=variant))
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (variant, bad[:5], sit[bad[:5]], got[bad[:5]], want[bad[:5]])
+    assert np.array_equal(_u32(hb.hand_potential_counts(d_sit, "treys", direct=True)), want)
+    big = hb.random_situations(16384, seed=812)
+    d_big = torch.from_numpy(big).cuda()
+    v4 = hb.hand_potential_counts(d_big, "treys", flop_variant=4)
+    v3 = hb.hand_potential_counts(d_big, "treys", flop_variant=3)
+    assert torch.equal(v4, v3)
+    with pytest.raises(hb.HoldemError):
+        hb.hand_potential_counts(d_sit, "treys", flop_variant=7)
