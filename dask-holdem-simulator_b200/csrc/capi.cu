@@ -337,7 +337,7 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     // HOLDEM_FLOP_KERNEL=3 / 2 select the earlier 4-set kernels (kept for A/B measurements and cross-checks)
     static const int impl = getenv("HOLDEM_FLOP_KERNEL") ? atoi(getenv("HOLDEM_FLOP_KERNEL")) : 4;
     cudaError_t e = (impl == 2 || impl == 3) ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st)
-                                             : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, st);
+                                             : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, st);
     if (e != cudaSuccess) return e;
     e = launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
@@ -371,8 +371,20 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if (variant < 2 || variant > 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
     int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (cudaStream_t)stream));
+    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, nullptr, (cudaStream_t)stream));
     else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, flag, variant, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out, uint64_t *d_cycles, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || !d_cycles || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    CUDA_TRY(cudaMemsetAsync(d_cycles, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+    CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (unsigned long long *)d_cycles,
+                                     (cudaStream_t)stream));
     return HOLDEM_OK;
 }
 

@@ -18,7 +18,7 @@ from ._lib import MODE_REFERENCE, MODE_TREYS, HP_ROW, HS_ROW
 
 __all__ = [
     "MODE_TREYS", "MODE_REFERENCE", "mode_id", "evaluate", "category", "hand_strength_counts",
-    "hand_potential_counts", "exhaustive7", "hs_from_counts", "potentials_from_counts",
+    "hand_potential_counts", "flop_phase_cycles", "exhaustive7", "hs_from_counts", "potentials_from_counts",
     "normalised_potentials", "ehs_from_counts", "evaluate_host", "category_host", "hand_strength_counts_host",
     "hand_potential_counts_host", "smem_gather_microbench", "EVALS_PER_FLOP_SITUATION",
 ]
@@ -114,6 +114,17 @@ def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = N
     fn = lib.holdem_hp_batch_direct if direct else lib.holdem_hp_batch
     _lib.check(fn(sit.data_ptr(), sit.shape[0], mode_id(mode), out.data_ptr(), st))
     return out
+
+
+def flop_phase_cycles(sit: torch.Tensor):
+    """Production flop kernel with phase clocks on -> (rows int32 [N,16], cycles int64 [4] = tables, W+T, descriptors,
+    tasks; SM cycles summed over all situations)."""
+    _require_cuda(sit, "sit", torch.uint8, 8)
+    out = torch.empty((sit.shape[0], HP_ROW), dtype=torch.int32, device=sit.device)
+    cyc = torch.zeros(4, dtype=torch.int64, device=sit.device)
+    lib, st = _enter(sit)
+    _lib.check(lib.holdem_hp_flop_phase_cycles(sit.data_ptr(), sit.shape[0], out.data_ptr(), cyc.data_ptr(), st))
+    return out, cyc
 
 
 def exhaustive7(device=None):

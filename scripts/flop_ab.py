@@ -52,6 +52,10 @@ def main():
             ref = out.clone()
         else:
             print("   equal to first variant:", bool(torch.equal(ref, out)))
+    _, cyc = hb.flop_phase_cycles(d)
+    cyc = cyc.cpu().numpy().astype(np.float64)
+    print("v4 phase cycles per situation (tables, W+T, descriptors, tasks):", (cyc / n).round(0).tolist(),
+          "share:", (cyc / cyc.sum()).round(3).tolist(), flush=True)
     for name, k in (("monotone", 1), ("two-tone", 2), ("rainbow", 3)):
         sub = np.ascontiguousarray(sit[nsuit == k])
         reps = max(1, 16384 // len(sub))

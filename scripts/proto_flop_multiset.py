@@ -105,6 +105,9 @@ def flop_counts(hole, board):
             flush_cache[mask] = best
         return flush_cache[mask]
     n_items = 0
+    Wc = {}
+    for (i, j) in pairs:
+        Wc[(i, j)] = Wc[(j, i)] = cls[(i, j)]
     for s in range(4):
         b_s = sum(1 for c in board if c // 13 == s)
         if b_s == 0:
@@ -115,7 +118,11 @@ def flop_counts(hole, board):
         both = [(a, b) for a, b in itertools.combinations(Ls, 2)]
         one = [tuple(sorted((a, z))) for a in Ls for z in Lns]
         none = [(a, b) for a, b in itertools.combinations(Lns, 2)]
-        plist = {2: both, 1: both + one, 0: both + one + none}
+        wns = [sum(1 for i in Lns if rk[i] == y) for y in range(13)]
+        # per-suit aggregates used by the "one" and "none" blocks (kernels_hp_flop4.cu builds the same lists)
+        histA = {a: [sum(1 for c in Lns if Wc[(a, c)] == k3) for k3 in range(3)] for a in Ls}
+        wnn = [wns[x] * wns[y] if x != y else wns[x] * (wns[x] - 1) // 2 for (x, y) in rank_pairs]
+        hist_none = [sum(w for w, c in zip(wnn, clsr) if c == k3 and w) for k3 in range(3)]
         for qtype, qlist in ((2, both), (1, one), (0, none)):
             k = b_s + qtype
             if k < 3:
@@ -124,13 +131,16 @@ def flop_counts(hole, board):
             for (i, j) in qlist:
                 o = int(our7[(i, j)])
                 qk = pp_index(rk[i], rk[j])
-                fq = bmask | sum(1 << rk[t] for t in (i, j) if su[t] == s)
-                for (a, b) in plist[need]:
-                    if a in (i, j) or b in (i, j):
+                qbits = sum(1 << rk[t] for t in (i, j) if su[t] == s)
+                fq = bmask | qbits
+                zs = [t for t in (i, j) if su[t] != s]          # Q's cards outside the suit (at most one when need <= 1)
+                # -- both cards of P in s: card level, disjointness = rank bits in s
+                for (a, b) in both:
+                    pbits = (1 << rk[a]) | (1 << rk[b])
+                    if pbits & qbits:
                         continue
                     n_items += 1
-                    m = fq | sum(1 << rk[t] for t in (a, b) if su[t] == s)
-                    Rf = flush_rank(m)
+                    Rf = flush_rank(fq | pbits)
                     pk = pp_index(rk[a], rk[b])
                     Rn = T[qk, pk]
                     ct, cr = cls[(a, b)], clsr[pk]
@@ -138,6 +148,43 @@ def flop_counts(hole, board):
                     elif o > Rf: gt[ct] += 1
                     if o < Rn: lt[cr] -= 1
                     elif o > Rn: gt[cr] -= 1
+                if need <= 1:
+                    assert len(zs) <= 1
+                    for a in Ls:
+                        if (1 << rk[a]) & qbits:
+                            continue
+                        n_items += 1
+                        Rf = flush_rank(fq | (1 << rk[a]))
+                        hist = list(histA[a])
+                        for z in zs:
+                            hist[Wc[(a, z)]] -= 1
+                        for c3 in range(3):
+                            if o < Rf: lt[c3] += hist[c3]
+                            elif o > Rf: gt[c3] += hist[c3]
+                        for y in range(13):
+                            w = wns[y] - sum(1 for z in zs if rk[z] == y)
+                            if w <= 0:
+                                continue
+                            n_items += 1
+                            pk = pp_index(min(rk[a], y), max(rk[a], y))
+                            Rn = T[qk, pk]
+                            cr = clsr[pk]
+                            if o < Rn: lt[cr] -= w
+                            elif o > Rn: gt[cr] -= w
+                if need == 0:
+                    assert not zs
+                    Rf = flush_rank(fq)
+                    for c3 in range(3):
+                        if o < Rf: lt[c3] += hist_none[c3]
+                        elif o > Rf: gt[c3] += hist_none[c3]
+                    for pk in range(91):
+                        if wnn[pk] <= 0:
+                            continue
+                        n_items += 1
+                        Rn = T[qk, pk]
+                        cr = clsr[pk]
+                        if o < Rn: lt[cr] -= wnn[pk]
+                        elif o > Rn: gt[cr] -= wnn[pk]
     row = np.zeros(16, dtype=np.int64)
     row[0:3] = tot
     for i in range(3):
