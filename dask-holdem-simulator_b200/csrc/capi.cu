@@ -174,6 +174,7 @@ int holdem_init(int device) {
     S.T.flop_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_lanes);
     S.T.nf4_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf4);
     S.T.idx4 = reinterpret_cast<const uint16_t *>(S.image + im.off_idx4);
+    S.T.key4 = reinterpret_cast<const uint32_t *>(S.image + im.off_key4);
     S.T.n_flop_tasks = im.n_tasks;
     S.T.turn_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_hdr);
     S.T.turn_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_lanes);

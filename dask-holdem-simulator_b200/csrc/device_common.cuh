@@ -40,6 +40,7 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint32_t *ref_lanes[2];
     uint32_t n_ref_tasks[2];
     const uint16_t *idx4;             // [91*91] two rank pairs -> index into the 1820 four-rank multisets
+    const uint32_t *key4;             // [1820] additive key of each four-rank multiset
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

@@ -14,8 +14,9 @@
 //     sum over (P,Q)  =  GENERIC part: for every Q and every rank pair pp = (x<=y):
 //                            n_Q(pp) * [clsr(pp)] x cmp(our7[Q], NF(board + ranks(Q) + pp))
 //                        with n_Q(pp) = number of unseen pairs of those ranks disjoint from Q (a product of per-rank
-//                        counts) and clsr = the flop class from ranks alone; Q's of equal rank pair and equal our7 are
-//                        merged, so this is ~100 groups x 91 rank pairs per situation;
+//                        counts) and clsr = the flop class from ranks alone; all Q of one rank pair that give us no flush
+//                        share our7, so this is 91 merged runouts (+ one entry per runout that makes OUR flush) x 91 rank
+//                        pairs per situation;
 //                     +  FLUSH part: for every (P,Q) such that board+Q has k >= 3 cards of a suit s and P holds >= 5-k
 //                        cards of s (about 8 K pairs on a rainbow flop, 40 K two-tone, 140-210 K monotone):
 //                            + [cls(P)]  x cmp(our7[Q], flush[ranks of board+Q+P in s])
@@ -27,10 +28,11 @@
 //                        that coincides with c is taken out again by a short per-lane fix-up loop.
 //   Our own flushes need no special case: our7[Q] is evaluated per card pair Q.
 //
-// Shared memory (195 KB per CTA): static flush[8192] u16 and idx4[91*91] u16 (two rank pairs -> four-rank multiset), then per
-// group (~40 KB): T[91][91] u16 = NF rank of board + rank pair q + rank pair p (expanded from the 1820 four-rank multisets
-// NF4, the only 7-card hash lookups of a situation besides 91 for our own hands); W[47][47] u16 = our7 | cls << 13 per
-// unseen pair; PD[<=320] 16-byte step descriptors of the flush part, per suit ordered
+// Shared memory (~165 KB per CTA): static flush[8192] u16 (index bits folded, m ^ m >> 6, so that the bank depends on ten
+// rank bits) and idx4[91*91] u16 (two rank pairs -> four-rank multiset), then per group (~33 KB): T[91][91] u16 (symmetric) =
+// NF rank of board + rank pair q + rank pair p, expanded from the 1820 four-rank multisets NF4 -- the only 7-card hash
+// lookups of a situation besides 91 for our own hands; W[47][47] u16 = our7 | cls << 13 per unseen pair; the runouts that
+// give us a flush; PD[<=320] 16-byte step descriptors of the flush part, per suit ordered
 // [both cards in s | one card a in s | undo steps (a, rank of c) | undo steps (rank pair), no card in s].
 // Flush part mapping: a warp task = 32 runouts Q of one (suit, cards-of-Q-in-suit) group x a segment of <= 64 steps;
 // lanes own Q (its rank, suit mask and T row live in registers), the warp walks the steps with one broadcast 16-byte load
@@ -45,24 +47,29 @@ namespace {
 constexpr int kGroupThreads = 256;
 constexpr int kGroups = 4;
 constexpr int kThreads4 = kGroupThreads * kGroups;
+constexpr int kGWarps = kGroupThreads / 32;
 constexpr int kU = 47;
 constexpr int kPairs4 = 1081;
 constexpr int kNf4 = 1820;
 constexpr int kPP = 91;            // rank pairs x <= y, index y(y+1)/2 + x
-constexpr int kTPitch = 94;        // u16 units: 47 words per row (odd) so that lanes on different rows spread over the banks
+constexpr int kTPitch = 94;        // u16 units
 constexpr int kSeg = 64;           // longest step segment of a flush task (packed 10-bit counters hold 1023)
 constexpr int kPD = 320;           // step descriptors per situation: at most 3 x 66 (rainbow) or 45 + 14 x 11 + 91 + 66
 constexpr int kMaxGroups = 12;
 constexpr int kProfSlots = 8;
 
 struct Flop4Group {                    // one situation in flight
-    uint4 PD[kPD];                     // x = 2 * (rank bits of the step's cards in s) << 16, y = weight << 10 cls(P) (add part),
-                                       // z = weight << 10 clsr(pp) (undo part), w = 2 pp; 10-bit fields per class
+    uint4 PD[kPD];                     // x = 2 * (rank bits of the step's cards in s) << 16 | 2 * fold(those bits),
+                                       // y = weight << 10 cls(P) (add part), z = weight << 10 clsr(pp) (undo part),
+                                       // w = byte offset of row pp of T; 10-bit fields per class
     uint16_t NF4[kNf4 + 4];            // non-flush rank of board + four-rank multiset
-    uint16_t T[kPP * kTPitch];
+    uint16_t T[kPP * kTPitch];         // [pp][qp] (symmetric)
     uint16_t W[kU * kU + 3];           // [i*47+j], i<j: our7 | cls << 13
+    uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8
     uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
+    uint32_t gdesc[96];                // generic part, rank pairs sorted by class: T row offset | 3x << 16 | 3y << 22 | (x==y) << 28
+    uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
     uint32_t cnt[12];                  // lt[3], gt[3], class totals[3]
     uint32_t bmask[4];                 // board rank mask per suit
     uint32_t g_first[kMaxGroups + 1];  // first task id of each flush group; [n_groups] = total
@@ -71,7 +78,9 @@ struct Flop4Group {                    // one situation in flight
     uint32_t pd_base[4], pd_len[4];    // PD section per suit
     uint32_t smask[4];                 // rank mask of the unseen cards per suit
     uint32_t hist_none[4];             // holdings without a card of the board's suit, by flop class (monotone boards)
-    uint32_t n_groups, pd_total, next_task, ours_now;
+    uint32_t gclass_end[4];            // generic part: end of each class in gdesc[]
+    uint32_t upack[2];                 // unseen cards per rank, 3 bits each (64-bit)
+    uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
     uint32_t prof[kProfSlots];
     uint8_t code[48];                  // unseen cards, rank*4+suit, ascending
     uint8_t Ls[4][16];                 // positions of the unseen cards of suit s
@@ -83,7 +92,7 @@ struct Flop4Group {                    // one situation in flight
 };
 
 struct Flop4Smem {
-    uint16_t flush[kFlushEntries];
+    uint16_t flush[kFlushEntries];     // flush[fold(mask)]
     uint16_t idx4[kPP * kPP + 7];
     uint32_t cardkey[16];              // additive key by rank
     uint8_t ppxy[96];                  // rank pair -> x | y << 4
@@ -93,8 +102,14 @@ struct Flop4Smem {
 __device__ __forceinline__ uint32_t path_of_code4(uint32_t code) { return (code & 3u) * 13u + (code >> 2); }
 __device__ __forceinline__ uint32_t tri(uint32_t n) { return n * (n + 1) / 2; }          // C(n+1,2)
 __device__ __forceinline__ uint32_t choose2u(uint32_t n) { return n * (n - 1) / 2; }    // n >= 1 or n == 0
+__device__ __forceinline__ uint32_t fold(uint32_t m) { return m ^ (m >> 6); }           // bijection on 13-bit masks, XOR-linear
 __device__ __forceinline__ void group_sync(uint32_t gid) {
     asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kGroupThreads) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
 }
 
 // One step of the flush part for the lane's runout: valid = step and runout share no card of the suit;
@@ -113,6 +128,14 @@ __device__ __forceinline__ void flush_step(uint32_t &aL, uint32_t &aG, uint32_t 
         : "+r"(aL), "+r"(aG), "+r"(sL), "+r"(sG)
         : "r"(our), "r"(rf), "r"(rn), "r"(dx), "r"(qb2), "r"(wa), "r"(ws), "r"(one));
 }
+// if (a < b) accL += w;  if (a > b) accG += w   (same pipe split)
+__device__ __forceinline__ void cmp_add(uint32_t &accL, uint32_t &accG, uint32_t a, uint32_t b, uint32_t w, uint32_t one) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.u32 p, %2, %3;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t"
+        "setp.gt.u32 p, %2, %3;\n\t@p mad.lo.u32 %1, %4, %5, %1;\n\t}"
+        : "+r"(accL), "+r"(accG)
+        : "r"(a), "r"(b), "r"(w), "r"(one));
+}
 
 }  // namespace
 
@@ -124,11 +147,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     const uint32_t gid = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
     const uint32_t lane = tid & 31, warp = tid >> 5;
     Flop4Group &G = S.G[gid];
-    uint16_t *const NF4 = G.NF4;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(T.flush);
-        uint4 *dst = reinterpret_cast<uint4 *>(S.flush);
-        for (uint32_t i = threadIdx.x; i < kFlushEntries / 8; i += kThreads4) dst[i] = src[i];
+        for (uint32_t m = threadIdx.x; m < kFlushEntries; m += kThreads4) S.flush[fold(m)] = __ldg(T.flush + m);
         for (uint32_t i = threadIdx.x; i < (uint32_t)(kPP * kPP); i += kThreads4) S.idx4[i] = __ldg(T.idx4 + i);
         if (threadIdx.x < 16) S.cardkey[threadIdx.x] = threadIdx.x < 13 ? c_rank_key[threadIdx.x] : 0u;
         if (threadIdx.x < 96) {
@@ -140,16 +160,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     }
     __syncthreads();
     const NfHash h5 = T.nf[0], h7 = T.nf[2];
+    const uint32_t flush_s = (uint32_t)__cvta_generic_to_shared(S.flush);
+    const uint32_t t_s = (uint32_t)__cvta_generic_to_shared(G.T);
     int saw_other = 0;
     uint32_t t_prev = 0;
-    // lane-static rank pairs of the generic part: pass p handles pp = lane + 32 p
-    uint32_t gx[3], gy[3];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-        const uint32_t xy = S.ppxy[lane + 32u * p];
-        gx[p] = xy & 15u;
-        gy[p] = xy >> 4;
-    }
 #define HOLDEM_PROF(slot)                                                        \
     if (prof != nullptr && tid == 0) {                                           \
         const uint32_t t_now = (uint32_t)clock64();                              \
@@ -168,7 +182,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         if (!flop) { saw_other |= (cb[6] == 0xFFu) ? 1 : 2; continue; }
         bool ok = true;
         uint64_t known = 0, bset = 0;
-        uint32_t kb = 0, khole = 0, bsuit = 0, bcnt = 0, hcnt = 0;   // bsuit: 4 x 4-bit suit counts; bcnt/hcnt: 13 x 2-bit rank counts
+        uint32_t kb = 0, khole = 0, bsuit = 0, hsuit = 0, bcnt = 0;   // bsuit/hsuit: 4 x 4-bit suit counts (board / hole + board)
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             const uint32_t c = cb[k];
@@ -176,15 +190,13 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             const uint32_t cc = c < 52u ? c : 0u;
             known |= card_bit(cc);
             const uint32_t r = card_rank(cc);
+            hsuit += 1u << (4 * card_suit(cc));
             if (k >= 2) {
                 bset |= card_bit(cc);
                 kb += S.cardkey[r];
                 bsuit += 1u << (4 * card_suit(cc));
                 bcnt += 1u << (2 * r);
-            } else {
-                khole += S.cardkey[r];
-                hcnt += 1u << (2 * r);
-            }
+            } else khole += S.cardkey[r];
         }
         ok = ok && __popcll(known) == 5;
         if (!ok) {
@@ -193,6 +205,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         if (tid < 12) G.cnt[tid] = 0;
         if (tid < 4) G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
+        if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
         if (warp == 0) {
             // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
             const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
@@ -202,15 +215,16 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             const uint32_t ltm = (1u << lane) - 1u;
             if (in0) G.code[__popc(m0 & ltm)] = (uint8_t)lane;
             if (in1) G.code[__popc(m0) + __popc(m1 & ltm)] = (uint8_t)(lane + 32);
-            if (lane < 14) {   // rank r owns codes 4r..4r+3: start position = unseen codes below 4r
-                const uint32_t c4 = 4 * lane;
+            {   // rank r owns codes 4r..4r+3: start position = unseen codes below 4r
+                const uint32_t c4 = 4 * min(lane, 13u);
                 const uint32_t below = c4 < 32 ? __popc(m0 & ((1u << c4) - 1u))
                                                : __popc(m0) + __popc(m1 & ((1u << (c4 - 32)) - 1u));
-                G.st[lane] = (uint8_t)below;
-                if (lane < 13) {
-                    const uint32_t cnt_r = c4 < 32 ? __popc((m0 >> c4) & 15u) : __popc((m1 >> (c4 - 32)) & 15u);
-                    G.u[lane] = (uint8_t)cnt_r;
-                }
+                const uint32_t cnt_r = lane < 13 ? (c4 < 32 ? __popc((m0 >> c4) & 15u) : __popc((m1 >> (c4 - 32)) & 15u)) : 0u;
+                if (lane < 14) G.st[lane] = (uint8_t)below;
+                if (lane < 13) G.u[lane] = (uint8_t)cnt_r;
+                const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 10 ? cnt_r << (3 * lane) : 0u);
+                const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (lane >= 10 && lane < 13) ? cnt_r << (3 * lane - 30) : 0u);
+                if (lane == 0) { G.upack[0] = lo | (hi << 30); G.upack[1] = hi >> 2; }
             }
             __syncwarp();
             const uint32_t cd0 = G.code[lane], cd1 = lane + 32 < kU ? G.code[lane + 32] : 0u;
@@ -266,36 +280,23 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 G.n_groups = ng;
                 G.pd_total = pdo;
                 G.next_task = 0;
+                G.n_ext = 0;
             }
         } else {
             // ---- the 7-card hash lookups of the situation: NF4[1820] = board + four ranks, our7nf[91] = hole + board + rank
-            //      pair; four independent lookups in flight per thread ---------------------------------------------------
+            //      pair; four independent lookups in flight per thread.  Multisets that cannot exist with this board read
+            //      an arbitrary table slot: their entries are only ever used with weight 0. -------------------------------
             constexpr uint32_t kWorkers = kGroupThreads - 32, kItems = kNf4 + kPP;
             for (uint32_t e0 = tid - 32; e0 < kItems; e0 += 4 * kWorkers) {
                 uint32_t key[4], slot[4], disp[4];
-                bool valid[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t e = e0 + q * kWorkers;
                     key[q] = kb;
-                    valid[q] = e < kItems;
-                    if (e < (uint32_t)kNf4) {
-                        const uint32_t rr = __ldg(T.nf4_ranks + e);
-                        uint32_t prev = 99, run = 0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t r = (rr >> (4 * c)) & 15u;
-                            key[q] += S.cardkey[r];
-                            run = (r == prev) ? run + 1 : 1;
-                            prev = r;
-                            valid[q] = valid[q] && (run + ((bcnt >> (2 * r)) & 3u) <= 4);
-                        }
-                    } else if (e < kItems) {
-                        const uint32_t xy = S.ppxy[e - kNf4], x = xy & 15u, y = xy >> 4;
-                        key[q] += khole + S.cardkey[x] + S.cardkey[y];
-                        const uint32_t cx = ((bcnt >> (2 * x)) & 3u) + ((hcnt >> (2 * x)) & 3u) + 1 + (x == y);
-                        const uint32_t cy = ((bcnt >> (2 * y)) & 3u) + ((hcnt >> (2 * y)) & 3u) + 1;
-                        valid[q] = cx <= 4 && cy <= 4;
+                    if (e < (uint32_t)kNf4) key[q] += __ldg(T.key4 + e);
+                    else if (e < kItems) {
+                        const uint32_t xy = S.ppxy[e - kNf4];
+                        key[q] += khole + S.cardkey[xy & 15u] + S.cardkey[xy >> 4];
                     }
                 }
 #pragma unroll
@@ -307,15 +308,15 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t e = e0 + q * kWorkers;
-                    const uint16_t v = valid[q] ? (uint16_t)disp[q] : (uint16_t)0;
-                    if (e < (uint32_t)kNf4) NF4[e] = v;
-                    else if (e < kItems) G.our7nf[e - kNf4] = v;
+                    if (e < (uint32_t)kNf4) G.NF4[e] = (uint16_t)disp[q];
+                    else if (e < kItems) G.our7nf[e - kNf4] = (uint16_t)disp[q];
                 }
             }
             // ---- rank-level flop class per rank pair (5-card hash) -----------------------------------------------------------
             if (tid >= kGroupThreads - 96) {
                 const uint32_t pp = tid - (kGroupThreads - 96);
-                const uint32_t ours_now = treys_rank(h5, S.flush, kb + khole, known);
+                const uint32_t fm = flush_mask(known, 5);
+                const uint32_t ours_now = fm ? (uint32_t)S.flush[fold(fm)] : nf_lookup(h5, kb + khole);
                 if (pp == 0) G.ours_now = ours_now;
                 uint32_t word = 0, code = 3;
                 if (pp < (uint32_t)kPP) {
@@ -336,23 +337,32 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         {
             // ---- W: our final rank with the pair as runout, flop class of the pair as a holding (no global memory) ---------
             const uint32_t ours_now = G.ours_now;
-            const bool monotone = ((bsuit + 0x5555u) & 0x8888u) != 0;   // some suit holds all three board cards
+            // the suit in which we can still make a flush (>= 3 of hole + board), and the one the board is monotone in
+            const uint32_t f3 = (hsuit + 0x5555u) & 0x8888u;            // nibble >= 3
+            const uint32_t fs = f3 ? (uint32_t)(__ffs(f3) - 1) >> 2 : 4u;
+            const uint32_t fneed = f3 ? 5u - ((hsuit >> (4 * fs)) & 15u) : 9u;
+            const uint32_t hbmask = f3 ? (uint32_t)(known >> (13 * fs)) & 0x1FFFu : 0u;
+            const uint32_t m3 = (bsuit + 0x5555u) & 0x8888u;
+            const uint32_t ms = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
+            const uint32_t mbmask = m3 ? G.bmask[ms] : 0u;
             uint32_t c0 = 0, c1 = 0, c2 = 0;
             for (uint32_t p = tid; p < (uint32_t)kPairs4; p += kGroupThreads) {
                 const uint32_t pr = __ldg(T.pairs + p);
                 const uint32_t i = pr & 0xFFu, j = pr >> 8;
                 const uint32_t ci = G.code[i], cj = G.code[j];
-                const uint32_t pp = tri(cj >> 2) + (ci >> 2);
-                const uint64_t cs = card_bit(path_of_code4(ci)) | card_bit(path_of_code4(cj));
-                const uint32_t fm7 = flush_mask(known | cs, 5);
-                const uint32_t our7 = fm7 ? (uint32_t)S.flush[fm7] : (uint32_t)G.our7nf[pp];
+                const uint32_t ri = ci >> 2, rj = cj >> 2, si = ci & 3u, sj = cj & 3u;
+                const uint32_t pp = tri(rj) + ri;
+                uint32_t our7 = G.our7nf[pp];
+                const uint32_t fbits = (si == fs ? 1u << ri : 0u) | (sj == fs ? 1u << rj : 0u);
+                if ((uint32_t)__popc(fbits) >= fneed) {            // this runout gives us a flush: its own generic entry
+                    our7 = S.flush[fold(hbmask | fbits)];
+                    G.ext[atomicAdd(&G.n_ext, 1u)] = pp | (our7 << 8);
+                    atomicAdd(&G.qflush[pp], 1u);
+                }
                 uint32_t cls = G.clsr[pp];
-                if (monotone) {
-                    const uint32_t fm5 = flush_mask(bset | cs, 5);
-                    if (fm5) {
-                        const uint32_t opp5 = S.flush[fm5];
-                        cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
-                    }
+                if (si == ms && sj == ms) {                        // monotone board and a suited holding: a flopped flush
+                    const uint32_t opp5 = S.flush[fold(mbmask | (1u << ri) | (1u << rj))];
+                    cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
                 }
                 c0 += cls == 0; c1 += cls == 1; c2 += cls == 2;
                 G.W[i * kU + j] = (uint16_t)(our7 | (cls << 13));
@@ -367,14 +377,37 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (((bsuit >> (4 * s)) & 15u) >= 2 && ai < G.ns[s]) {
                     const uint32_t nsu = G.ns[s];
                     const uint32_t ra = G.code[G.Ls[s][ai]] >> 2;
-                    G.PD[G.pd_base[s] + choose2u(nsu) + ai] = make_uint4((2u << ra) << 16, 0u, 0u, 0u);
+                    G.PD[G.pd_base[s] + choose2u(nsu) + ai] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, 0u, 0u);
                 }
             }
             if (tid < 4) G.hist_none[tid] = 0;
-            // ---- T[qp][pp] = NF4[multiset(qp + pp)] --------------------------------------------------------------------------
-            for (uint32_t e = tid; e < (uint32_t)(kPP * kPP); e += kGroupThreads) {
-                const uint32_t qp = e / kPP, pp = e - qp * kPP;
-                G.T[qp * kTPitch + pp] = NF4[S.idx4[e]];
+            if (warp == kGWarps - 1) {
+                // ---- generic part: the rank pairs sorted by flop class, one descriptor each ---------------------------------
+                uint32_t base = 0;
+#pragma unroll
+                for (uint32_t c = 0; c < 3; ++c) {
+#pragma unroll
+                    for (uint32_t ps = 0; ps < 3; ++ps) {
+                        const uint32_t pp = lane + 32u * ps;
+                        const bool mine = pp < (uint32_t)kPP && G.clsr[pp] == c;
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
+                        if (mine) {
+                            const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
+                            G.gdesc[base + __popc(bal & ((1u << lane) - 1u))] =
+                                (pp * (kTPitch * 2)) | ((3u * x) << 16) | ((3u * y) << 22) | ((uint32_t)(x == y) << 28);
+                        }
+                        base += __popc(bal);
+                    }
+                    if (lane == 0) G.gclass_end[c] = base;
+                }
+            }
+            // ---- T[pp][qp] = NF4[multiset(pp + qp)], row by row ---------------------------------------------------------------------
+            for (uint32_t row = warp; row < (uint32_t)kPP; row += kGWarps) {
+#pragma unroll
+                for (uint32_t ps = 0; ps < 3; ++ps) {
+                    const uint32_t col = lane + 32u * ps;
+                    if (col < (uint32_t)kPP) G.T[row * kTPitch + col] = G.NF4[S.idx4[row * kPP + col]];
+                }
             }
         }
         group_sync(gid);                                                                            // (C)
@@ -394,8 +427,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t pa = G.Ls[s][pr & 0xFFu], pb = G.Ls[s][pr >> 8];
                     const uint32_t ra = G.code[pa] >> 2, rb = G.code[pb] >> 2;
                     const uint32_t cls = G.W[pa * kU + pb] >> 13;
-                    const uint32_t pp = tri(rb) + ra;
-                    G.PD[e] = make_uint4(((2u << ra) | (2u << rb)) << 16, 1u << (10 * cls), G.clsw[pp], 2u * pp);
+                    const uint32_t pp = tri(rb) + ra, bits = (1u << ra) | (1u << rb);
+                    G.PD[e] = make_uint4((bits << 17) | (2u * fold(bits)), 1u << (10 * cls), G.clsw[pp], pp * (kTPitch * 2));
                 } else if (t < nboth + nsu) {
                     // written in the previous phase; y accumulates below
                 } else if (t < nboth + 14u * nsu) {                // undo step for {a, any c of rank y outside s}
@@ -410,42 +443,33 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         const uint32_t i = min(pa, pc), j = max(pa, pc);
                         hist += 1u << (10 * (G.W[i * kU + j] >> 13));
                     }
-                    G.PD[e] = make_uint4((2u << ra) << 16, 0u, wgt * G.clsw[pp], 2u * pp);
+                    G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, wgt * G.clsw[pp], pp * (kTPitch * 2));
                     if (hist) atomicAdd(&G.PD[G.pd_base[s] + nboth + ai].y, hist);
                 } else {                                           // undo step for a rank pair, neither card in s
                     const uint32_t pp = t - (nboth + 14u * nsu);
                     const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
                     const uint32_t wx = G.u[x] - ((sm >> x) & 1u), wy = G.u[y] - ((sm >> y) & 1u);
                     const uint32_t wgt = x != y ? wx * wy : (wx ? choose2u(wx) : 0u);
-                    G.PD[e] = make_uint4(0u, 0u, wgt * G.clsw[pp], 2u * pp);
+                    G.PD[e] = make_uint4(0u, 0u, wgt * G.clsw[pp], pp * (kTPitch * 2));
                     if (wgt) atomicAdd(&G.hist_none[G.clsr[pp]], wgt);
                 }
             }
         }
-        // per-situation lane constants of the generic part
-        uint32_t gux[3], guy[3], gcls[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            const uint32_t pp = lane + 32u * p;
-            gux[p] = pp < (uint32_t)kPP ? G.u[gx[p]] : 0u;
-            guy[p] = pp < (uint32_t)kPP ? G.u[gy[p]] : 0u;
-            gcls[p] = G.clsr[pp];
-        }
         group_sync(gid);                                                                            // (D)
         HOLDEM_PROF(2)
 
-        uint32_t gl[3] = {0, 0, 0}, gg[3] = {0, 0, 0};     // generic part: per pass (class = gcls[p])
-        uint32_t fl[3] = {0, 0, 0}, fg[3] = {0, 0, 0};     // flush part: net per class (add - undo), wraps mod 2^32
+        uint32_t accL[3] = {0, 0, 0}, accG[3] = {0, 0, 0};   // per class: our7 < R / our7 > R (net of the undo steps, mod 2^32)
         const uint32_t n_groups = G.n_groups;
         const uint32_t n_flush_tasks = G.g_first[n_groups];
-        const uint32_t n_tasks = n_flush_tasks + kPP;
+        const uint32_t n_entries = kPP + G.n_ext;
+        const uint32_t n_tasks = n_flush_tasks + (n_entries + 31) / 32;
         for (;;) {
             uint32_t task = 0;
             if (lane == 0) task = atomicAdd(&G.next_task, 1u);
             task = __shfl_sync(0xFFFFFFFFu, task, 0);
             if (task >= n_tasks) break;
             if (task < n_flush_tasks) {
-                // ================= flush task: 32 runouts Q x a segment of holdings P ==================================
+                // ================= flush task: 32 runouts Q x a segment of steps =======================================
                 uint32_t g = 0;
                 while (g + 1 < n_groups && task >= G.g_first[g + 1]) ++g;
                 const uint32_t local = task - G.g_first[g];
@@ -455,7 +479,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t p0 = seg * seglen, p1 = min(np, p0 + seglen);
                 const uint32_t qi = chunk * 32 + lane;
                 const uint32_t nsu = G.ns[s], nns = kU - nsu;
-                uint32_t our = 0, fq2 = 0, qb2 = 0, zpos = 0xFFu, qpp2 = 0;
+                uint32_t our = 0, fqf = 0, qb2 = 0, zpos = 0xFFu, qcol = 0;
                 if (qi < nq) {
                     uint32_t i, j;
                     if (qtype == 1) {
@@ -471,36 +495,36 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t ci = G.code[i], cj = G.code[j];
                     const uint32_t ri = ci >> 2, rj = cj >> 2;
                     our = G.W[i * kU + j] & 0x1FFFu;
-                    qb2 = ((ci & 3u) == s ? 2u << ri : 0u) | ((cj & 3u) == s ? 2u << rj : 0u);
-                    fq2 = 2u * G.bmask[s] | qb2;
-                    qpp2 = (tri(rj) + ri) * (kTPitch * 2);
+                    const uint32_t qbits = ((ci & 3u) == s ? 1u << ri : 0u) | ((cj & 3u) == s ? 1u << rj : 0u);
+                    qb2 = qbits << 17;
+                    fqf = 2u * fold(G.bmask[s] | qbits);
+                    qcol = 2u * (tri(rj) + ri);
                 }
-                const char *qrow = reinterpret_cast<const char *>(G.T) + qpp2;
-                const char *flushb = reinterpret_cast<const char *>(S.flush);
+                const uint32_t tq_s = t_s + qcol;
                 const uint4 *pd = G.PD + G.g_pdbase[g] + p0;
                 uint32_t aL = 0, aG = 0, sL = 0, sG = 0;
 #pragma unroll 4
                 for (uint32_t t = p0; t < p1; ++t, ++pd) {
                     const uint4 d = *pd;
-                    // the step's cards of s are neither on the board nor (when valid) in the runout: the sum is the union
-                    const uint32_t rf = *reinterpret_cast<const uint16_t *>(flushb + ((d.x >> 16) + fq2));
-                    const uint32_t rn = *reinterpret_cast<const uint16_t *>(qrow + d.w);
-                    flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2 << 16, d.y, d.z, one);
+                    // fold() is XOR-linear and the step's cards of s are disjoint from board + runout when the step is valid
+                    const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
+                    const uint32_t rn = lds_u16(tq_s + d.w);
+                    flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
                 }
                 if (qi >= nq) { aL = 0; aG = 0; sL = 0; sG = 0; }   // lanes past the end of the runout list
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    fl[c] += ((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu);
-                    fg[c] += ((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu);
+                    accL[c] += ((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu);
+                    accG[c] += ((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu);
                 }
                 const uint32_t need = 5u - (((bsuit >> (4 * s)) & 15u) + qtype);
                 if (seg == 0 && need == 0 && qi < nq) {
                     // holdings without a card of s: the board + runout flush itself, one compare for all of them
-                    const uint32_t rf = *reinterpret_cast<const uint16_t *>(flushb + fq2);
+                    const uint32_t rf = lds_u16(flush_s + fqf);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        if (our < rf) fl[c] += G.hist_none[c];
-                        if (our > rf) fg[c] += G.hist_none[c];
+                        if (our < rf) accL[c] += G.hist_none[c];
+                        if (our > rf) accG[c] += G.hist_none[c];
                     }
                 }
                 if (seg == 0 && need == 1 && qtype == 1) {
@@ -508,77 +532,66 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t rz = zpos < (uint32_t)kU ? (uint32_t)(G.code[zpos] >> 2) : 0u;
                     for (uint32_t ai = 0; ai < nsu; ++ai) {
                         const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
-                        if (qi < nq && !((qb2 >> (ra + 1)) & 1u)) {
-                            const uint32_t rf = *reinterpret_cast<const uint16_t *>(flushb + (fq2 | (2u << ra)));
+                        if (qi < nq && !((qb2 >> (ra + 17)) & 1u)) {
+                            const uint32_t rf = lds_u16(flush_s + (fqf ^ (2u * fold(1u << ra))));
                             const uint32_t i = min(pa, zpos), j = max(pa, zpos);
                             const uint32_t cl = G.W[i * kU + j] >> 13;
                             const uint32_t pp = tri(max(ra, rz)) + min(ra, rz);
-                            const uint32_t rn = *reinterpret_cast<const uint16_t *>(qrow + 2u * pp);
+                            const uint32_t rn = lds_u16(tq_s + pp * (kTPitch * 2));
                             const uint32_t cr = G.clsr[pp];
 #pragma unroll
                             for (uint32_t c = 0; c < 3; ++c) {
-                                fl[c] += (uint32_t)(cr == c && our < rn) - (uint32_t)(cl == c && our < rf);
-                                fg[c] += (uint32_t)(cr == c && our > rn) - (uint32_t)(cl == c && our > rf);
+                                accL[c] += (uint32_t)(cr == c && our < rn) - (uint32_t)(cl == c && our < rf);
+                                accG[c] += (uint32_t)(cr == c && our > rn) - (uint32_t)(cl == c && our > rf);
                             }
                         }
                     }
                 }
             } else {
-                // ================= generic task: one rank pair of Q, lanes over the rank pairs of P ========================
-                const uint32_t qp = task - n_flush_tasks;
+                // ================= generic task: 32 merged runouts, the warp walks the rank pairs of P class by class =====
+                const uint32_t e = (task - n_flush_tasks) * 32 + lane;
+                uint32_t qp = 0, val = 0, mult = 0;
+                if (e < (uint32_t)kPP) {
+                    qp = e;
+                    val = G.our7nf[e];
+                } else if (e < n_entries) {
+                    const uint32_t en = G.ext[e - kPP];
+                    qp = en & 0xFFu;
+                    val = en >> 8;
+                    mult = 1;
+                }
                 const uint32_t qxy = S.ppxy[qp], q1 = qxy & 15u, q2 = qxy >> 4;
-                const uint32_t u1 = G.u[q1], u2 = G.u[q2];
-                const uint32_t nq = q1 != q2 ? u1 * u2 : (u1 ? choose2u(u1) : 0u);
-                if (nq == 0) continue;
-                uint32_t val = 0xFFFFFFFFu;
-                if (lane < nq) {
-                    uint32_t a, b;
-                    if (q1 != q2) {
-                        a = u2 == 1 ? lane : (u2 == 2 ? lane >> 1 : (u2 == 4 ? lane >> 2 : (lane * 11u) >> 5));
-                        b = lane - a * u2;
-                    } else {
-                        a = (0x210100u >> (4 * lane)) & 15u;     // pairs of {0..3} in colex order: 01 02 12 03 13 23
-                        b = (0x333221u >> (4 * lane)) & 15u;
-                    }
-                    const uint32_t i = G.st[q1] + a, j = G.st[q2] + b;
-                    val = G.W[i * kU + j] & 0x1FFFu;
+                if (e < (uint32_t)kPP) {
+                    const uint32_t u1 = G.u[q1], u2 = G.u[q2];
+                    mult = (q1 != q2 ? u1 * u2 : (u1 ? choose2u(u1) : 0u)) - G.qflush[qp];
                 }
-                const uint16_t *row = G.T + qp * kTPitch;
-                uint32_t R[3], nn[3];
+                // unseen cards per rank once the runout's two cards are gone, 3 bits per rank
+                const uint64_t m64 = (((uint64_t)G.upack[1] << 32) | G.upack[0]) - (1ull << (3 * q1)) - (1ull << (3 * q2));
+                const uint32_t tq_s = t_s + 2u * qp;
+                uint32_t k = 0;
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const uint32_t pp = lane + 32u * p;
-                    R[p] = pp < (uint32_t)kPP ? row[pp] : 0u;
-                    const uint32_t mx = gux[p] - (gx[p] == q1) - (gx[p] == q2);
-                    const uint32_t my = guy[p] - (gy[p] == q1) - (gy[p] == q2);
-                    nn[p] = pp < (uint32_t)kPP ? (gx[p] != gy[p] ? mx * my : (mx ? choose2u(mx) : 0u)) : 0u;
-                }
-                uint32_t remaining = __ballot_sync(0xFFFFFFFFu, lane < nq);
-                while (remaining) {
-                    const uint32_t v = __shfl_sync(0xFFFFFFFFu, val, __ffs(remaining) - 1);
-                    const uint32_t same = __ballot_sync(0xFFFFFFFFu, val == v) & remaining;
-                    const uint32_t gmul = __popc(same);
-                    remaining ^= same;
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const uint32_t wgt = nn[p] * gmul;
-                        if (v < R[p]) gl[p] += wgt;
-                        if (v > R[p]) gg[p] += wgt;
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t kend = G.gclass_end[c];
+                    uint32_t l = 0, g2 = 0;
+#pragma unroll 2
+                    for (; k < kend; ++k) {
+                        const uint32_t d = G.gdesc[k];
+                        const uint32_t R = lds_u16(tq_s + (d & 0xFFFFu));
+                        const uint32_t mx = (uint32_t)(m64 >> ((d >> 16) & 63u)) & 7u;
+                        const uint32_t my = (uint32_t)(m64 >> ((d >> 22) & 63u)) & 7u;
+                        const uint32_t nn = (d >> 28) ? (mx * (mx - 1u)) >> 1 : mx * my;
+                        cmp_add(l, g2, val, R, nn * mult, one);
                     }
+                    accL[c] += l;
+                    accG[c] += g2;
                 }
             }
         }
-        // ---- reduce: per class over the warp, then into the group's counters ------------------------------------------------------
+        // ---- reduce over the warp, then into the group's counters ------------------------------------------------------------------
 #pragma unroll
         for (uint32_t c = 0; c < 3; ++c) {
-            uint32_t l = fl[c], g2 = fg[c];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                l += gcls[p] == c ? gl[p] : 0u;
-                g2 += gcls[p] == c ? gg[p] : 0u;
-            }
-            l = __reduce_add_sync(0xFFFFFFFFu, l);
-            g2 = __reduce_add_sync(0xFFFFFFFFu, g2);
+            const uint32_t l = __reduce_add_sync(0xFFFFFFFFu, accL[c]);
+            const uint32_t g2 = __reduce_add_sync(0xFFFFFFFFu, accG[c]);
             if (lane == 0) {
                 if (l) atomicAdd(&G.cnt[c], l);
                 if (g2) atomicAdd(&G.cnt[3 + c], g2);

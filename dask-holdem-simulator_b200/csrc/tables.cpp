@@ -284,6 +284,11 @@ struct Builder {
                                 (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24;
                         t.nf4_ranks[e] = (uint16_t)(r0 | (r1 << 4) | (r2 << 8) | (r3 << 12));
                     }
+        t.key4.assign(1824, 0);
+        for (int e = 0; e < 1820; ++e) {
+            const uint16_t v = t.nf4_ranks[e];
+            t.key4[e] = kRankKey[v & 15] + kRankKey[(v >> 4) & 15] + kRankKey[(v >> 8) & 15] + kRankKey[v >> 12];
+        }
         // ---- 8. two rank pairs -> four-rank multiset index -------------------------------------------------------------------
         t.idx4.assign(91 * 91 + 7, 0);
         for (int q2 = 0; q2 < 13; ++q2)
@@ -410,6 +415,7 @@ TableImage make_image(const Tables &t) {
     im.off_lanes = append(t.flop_lanes.data(), t.flop_lanes.size() * 4);
     im.off_nf4 = append(t.nf4_ranks.data(), t.nf4_ranks.size() * 2);
     im.off_idx4 = append(t.idx4.data(), t.idx4.size() * 2);
+    im.off_key4 = append(t.key4.data(), t.key4.size() * 4);
     im.n_tasks = (uint32_t)t.flop_task_hdr.size();
     im.off_turn_hdr = append(t.turn_task_hdr.data(), t.turn_task_hdr.size() * 4);
     im.off_turn_lanes = append(t.turn_lanes.data(), t.turn_lanes.size() * 4);

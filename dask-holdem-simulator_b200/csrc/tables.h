@@ -66,6 +66,8 @@ struct Tables {
     // idx4[91 qp + pp] = index (same formula) of the multiset formed by two rank pairs, qp = (q1<=q2), pp = (x<=y), each
     // numbered y(y+1)/2 + x: the expansion table of the rank-multiset flop kernel (kernels_hp_flop4.cu).
     std::vector<uint16_t> idx4;
+    // key4[e] = sum of the additive rank keys of the e-th four-rank multiset (same numbering as nf4_ranks)
+    std::vector<uint32_t> key4;
     // Statistics kept for selftest().
     int n_keys[3] = {0, 0, 0};
 };
@@ -76,7 +78,7 @@ int selftest(char *msg, int msg_len);  // 0 = ok
 // Flat device image of the tables: one allocation, 16-byte aligned sections, offsets in bytes.
 struct TableImage {
     std::vector<uint8_t> bytes;
-    uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0, off_idx4 = 0;
+    uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0, off_idx4 = 0, off_key4 = 0;
     uint32_t n_tasks = 0;
     uint32_t off_turn_hdr = 0, off_turn_lanes = 0, off_nf3 = 0, n_turn_tasks = 0;
     uint32_t off_ref_hdr[2] = {0, 0}, off_ref_lanes[2] = {0, 0}, n_ref_tasks[2] = {0, 0};
