@@ -68,7 +68,6 @@ struct Flop4Group {                    // one situation in flight
     uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8
     uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
-    uint32_t gdesc[96];                // generic part, rank pairs sorted by class: T row offset | 3x << 16 | 3y << 22 | (x==y) << 28
     uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
     uint32_t cnt[12];                  // lt[3], gt[3], class totals[3]
     uint32_t bmask[4];                 // board rank mask per suit
@@ -78,7 +77,6 @@ struct Flop4Group {                    // one situation in flight
     uint32_t pd_base[4], pd_len[4];    // PD section per suit
     uint32_t smask[4];                 // rank mask of the unseen cards per suit
     uint32_t hist_none[4];             // holdings without a card of the board's suit, by flop class (monotone boards)
-    uint32_t gclass_end[4];            // generic part: end of each class in gdesc[]
     uint32_t upack[2];                 // unseen cards per rank, 3 bits each (64-bit)
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
     uint32_t prof[kProfSlots];
@@ -128,7 +126,7 @@ __device__ __forceinline__ void flush_step(uint32_t &aL, uint32_t &aG, uint32_t 
         : "+r"(aL), "+r"(aG), "+r"(sL), "+r"(sG)
         : "r"(our), "r"(rf), "r"(rn), "r"(dx), "r"(qb2), "r"(wa), "r"(ws), "r"(one));
 }
-// if (a < b) accL += w;  if (a > b) accG += w   (same pipe split)
+// if (a < b) accL += w * m;  if (a > b) accG += w * m   (same pipe split)
 __device__ __forceinline__ void cmp_add(uint32_t &accL, uint32_t &accG, uint32_t a, uint32_t b, uint32_t w, uint32_t one) {
     asm("{\n\t.reg .pred p;\n\t"
         "setp.lt.u32 p, %2, %3;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t"
@@ -381,26 +379,6 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             }
             if (tid < 4) G.hist_none[tid] = 0;
-            if (warp == kGWarps - 1) {
-                // ---- generic part: the rank pairs sorted by flop class, one descriptor each ---------------------------------
-                uint32_t base = 0;
-#pragma unroll
-                for (uint32_t c = 0; c < 3; ++c) {
-#pragma unroll
-                    for (uint32_t ps = 0; ps < 3; ++ps) {
-                        const uint32_t pp = lane + 32u * ps;
-                        const bool mine = pp < (uint32_t)kPP && G.clsr[pp] == c;
-                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
-                        if (mine) {
-                            const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
-                            G.gdesc[base + __popc(bal & ((1u << lane) - 1u))] =
-                                (pp * (kTPitch * 2)) | ((3u * x) << 16) | ((3u * y) << 22) | ((uint32_t)(x == y) << 28);
-                        }
-                        base += __popc(bal);
-                    }
-                    if (lane == 0) G.gclass_end[c] = base;
-                }
-            }
             // ---- T[pp][qp] = NF4[multiset(pp + qp)], row by row ---------------------------------------------------------------------
             for (uint32_t row = warp; row < (uint32_t)kPP; row += kGWarps) {
 #pragma unroll
@@ -568,22 +546,24 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // unseen cards per rank once the runout's two cards are gone, 3 bits per rank
                 const uint64_t m64 = (((uint64_t)G.upack[1] << 32) | G.upack[0]) - (1ull << (3 * q1)) - (1ull << (3 * q2));
                 const uint32_t tq_s = t_s + 2u * qp;
-                uint32_t k = 0;
+                // all 91 rank pairs of P, fully unrolled (constant shifts and offsets); unweighted counts n_Q(pp) go into packed
+                // 10-bit class fields (they sum to C(45,2) = 990 per runout), the runout multiplicity is applied afterwards
+                uint32_t lp = 0, gp = 0;
+#pragma unroll
+                for (int y = 0; y < 13; ++y) {
+                    const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;
+#pragma unroll
+                    for (int x = 0; x <= y; ++x) {
+                        const int pp = y * (y + 1) / 2 + x;
+                        const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
+                        const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
+                        cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const uint32_t kend = G.gclass_end[c];
-                    uint32_t l = 0, g2 = 0;
-#pragma unroll 2
-                    for (; k < kend; ++k) {
-                        const uint32_t d = G.gdesc[k];
-                        const uint32_t R = lds_u16(tq_s + (d & 0xFFFFu));
-                        const uint32_t mx = (uint32_t)(m64 >> ((d >> 16) & 63u)) & 7u;
-                        const uint32_t my = (uint32_t)(m64 >> ((d >> 22) & 63u)) & 7u;
-                        const uint32_t nn = (d >> 28) ? (mx * (mx - 1u)) >> 1 : mx * my;
-                        cmp_add(l, g2, val, R, nn * mult, one);
-                    }
-                    accL[c] += l;
-                    accG[c] += g2;
+                    accL[c] += ((lp >> (10 * c)) & 0x3FFu) * mult;
+                    accG[c] += ((gp >> (10 * c)) & 0x3FFu) * mult;
                 }
             }
         }
