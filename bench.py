@@ -26,16 +26,15 @@ for _p in (PKG, ROOT):
 SITUATIONS_PER_GPU = 65536
 SEED = 20251019
 EVALS_PER_SITUATION = 1_072_353          # 1,070,190 + 1,081 + 1,082
-ISSUED_EVALS_PER_SITUATION = 178_365 + 1_081 + 1_082 + 1_820   # what the deduplicating kernel actually evaluates
-ISSUED_SMEM_GATHERS_PER_4SET = 5         # W[a][c], W[b][c], W[c][d], X[suit][c], NF (kernels_hp_flop.cu, v3 walk)
-WARP_INSTR_PER_SITUATION = 24669140132 / 65536   # smsp__inst_executed.sum of one launch (profiles/r1_hp_flop_v3_*)
+HASH_LOOKUPS_PER_SITUATION = 1_820 + 91 + 92   # what the rank-multiset kernel looks up in the 7-/5-card hash tables
+HOT_KERNEL = "hp_flop_treys_v4_kernel"
 METRIC = "flop_hs_hp_situations_per_sec"
 UNIT = "situations/s"
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -49,7 +48,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -145,7 +144,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    per_step = max(64, 8 * cores)   # bounded sample of the 65,536-situation workload per step
+    per_step = max(32, 4 * cores)   # bounded sample of the 65,536-situation workload per step (~1 s of CPU work)
     for _ in range(args.warmup):
         cpu_port_throughput(min(per_step, cores), cores)
     t_total = 0.0
@@ -176,7 +175,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the evaluator / micro-benchmark side measurements")
@@ -306,40 +305,88 @@ def main():
                                                       threads=1024, device=local_rank)
     lookup_peak_cf, _ = hb.smem_gather_microbench(table_bytes=4096, iters=4096, pattern=1, blocks_per_sm=2,
                                                   threads=1024, device=local_rank)
+    counters = {}
+    try:
+        counters = json.load(open(os.path.join(ROOT, "profiles", "hot_kernel_counters.json")))[HOT_KERNEL]
+    except Exception:
+        pass
     evals_per_launch = n_local * EVALS_PER_SITUATION
     achieved = evals_per_launch / (kernel_ms * 1e-3)
-    issued = n_local * ISSUED_EVALS_PER_SITUATION / (kernel_ms * 1e-3)
-    issued_gathers = n_local * 178_365 * ISSUED_SMEM_GATHERS_PER_4SET / (kernel_ms * 1e-3)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6
+    smem_peak = 148 * sm_mhz * 1e6
+    wi = counters.get("warp_instructions_per_situation")
+    wf = counters.get("shared_wavefronts_per_situation")
     roofline = {
-        "kernel": "hp_flop_treys_v3_kernel", "bound": "smem_lookup",
+        "kernel": HOT_KERNEL, "bound": "smem_lookup",
         "achieved": achieved / 1e9, "peak": lookup_peak_random / 1e9, "unit": "Glookup/s",
         "frac": achieved / lookup_peak_random,
-        "traffic": traffic.get("hp_flop_treys_v3_kernel", {}).get("dram_bytes_read", None) if traffic else None,
+        "traffic": (lambda t: t.get("dram_bytes_read", 0) + t.get("dram_bytes_write", 0) if t else None)(
+            traffic.get(HOT_KERNEL)),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
                         "(profiles/traffic.json); algorithmic HBM bytes per launch = 65,536 x 72 B = 4.7 MB",
-        "note": "algorithmic = 1,072,353 evaluations (1 table lookup each) per situation x 65,536 situations per "
-                "launch / CUDA-event launch time; peak = uniformly random uint16 shared-memory gathers measured in "
-                "this run (4 KB table, the NF footprint class); the kernel deduplicates opponent hands (178,365 "
-                "4-sets x 6 splits), so issued_* report what the hardware did",
-        "issued_evals_per_sec": issued, "issued_frac": issued / lookup_peak_random,
-        "issued_smem_gathers_per_sec": issued_gathers,
-        "issued_gathers_frac_of_conflict_free_peak": issued_gathers / lookup_peak_cf,
+        "note": "algorithmic = 1,072,353 evaluations (1 table lookup each) per situation x 65,536 situations per launch / "
+                "CUDA-event launch time; peak = uniformly random uint16 shared-memory gathers measured in this run (4 KB "
+                "table).  The production kernel does NOT visit every (holding, runout) pair: it sums over rank multisets and "
+                "corrects the flush cases card by card (DESIGN.md section 4), so frac > 1 is expected; the hardware-side "
+                "utilisation is under issue_slots / shared_memory, and plain_enumeration below is the same count obtained "
+                "with one real evaluation per pair",
+        "hash_lookups_per_situation": HASH_LOOKUPS_PER_SITUATION,
         "peak_conflict_free_Glookup_s": lookup_peak_cf / 1e9,
         "kernel_ms": kernel_ms,
-        "issue_slots": {
-            "warp_instructions_per_situation": WARP_INSTR_PER_SITUATION,
-            "achieved_warp_instr_per_sec": WARP_INSTR_PER_SITUATION * n_local / (kernel_ms * 1e-3),
-            "peak_warp_instr_per_sec": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
-            "frac": WARP_INSTR_PER_SITUATION * n_local / (kernel_ms * 1e-3)
-                    / (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
-            "note": "the kernel is instruction-issue bound (ncu: smsp__issue_active 86.6 %, ALU pipe 71.8 %, FMA pipe "
-                    "32.5 %, shared-memory wavefronts 47.9 % of peak); warp instructions per situation = "
-                    "smsp__inst_executed.sum / 65,536 from the committed ncu capture, peak = 148 SMs x 4 schedulers x "
-                    "the SM clock sampled during this run"},
+        "issue_slots": None if wi is None else {
+            "warp_instructions_per_situation": wi,
+            "achieved_warp_instr_per_sec": wi * n_local / (kernel_ms * 1e-3),
+            "peak_warp_instr_per_sec": issue_peak,
+            "frac": wi * n_local / (kernel_ms * 1e-3) / issue_peak,
+            "note": "warp instructions per situation = smsp__inst_executed.sum / 65,536 from the committed ncu capture "
+                    "(profiles/hot_kernel_counters.json), rate from this run's CUDA-event time; peak = 148 SMs x 4 schedulers "
+                    "x the SM clock sampled during this run"},
+        "shared_memory": None if wf is None else {
+            "wavefronts_per_situation": wf,
+            "achieved_wavefronts_per_sec": wf * n_local / (kernel_ms * 1e-3),
+            "peak_wavefronts_per_sec": smem_peak,
+            "frac": wf * n_local / (kernel_ms * 1e-3) / smem_peak,
+            "note": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum / 65,536 from the same capture; peak = one wavefront per "
+                    "SM per clock"},
+        "ncu": {k: counters.get(k) for k in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "lsu_pipe_pct",
+                                              "shared_wavefront_pct", "capture")} if counters else None,
         "hbm_algorithmic_GBs": n_local * 72 / (kernel_ms * 1e-3) / 1e9, "hbm_peak_GBs": hbm_peak,
         "hbm_peak_source": hbm_peak_src,
     }
 
+    # ---- the other implementations of the same counts, for scale (kernel-only, CUDA events) ---------------------------------
+    def _time(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    alt = {}
+    if not args.no_extras:
+        scratch = torch.empty_like(mine)
+        ms3 = _time(lambda: hb.hand_potential_counts(d_sit, "treys", out=scratch, flop_variant=3), 3)
+        same3 = bool(torch.equal(scratch, mine))
+        n_plain = 2048
+        d_plain = d_sit[:n_plain].contiguous()
+        plain_out = torch.empty((n_plain, hb.HP_ROW), dtype=torch.int32, device=dev)
+        msp = _time(lambda: hb.hand_potential_counts(d_plain, "treys", out=plain_out, direct=True), 3)
+        samep = bool(torch.equal(plain_out, mine[:n_plain]))
+        ok = ok and same3 and samep
+        alt = {
+            "four_set_walk_v3": {"situations_per_sec": n_local / (ms3 * 1e-3), "equal_rows": same3,
+                                 "what": "deduplicating 4-set kernel (178,365 evaluations + 1.07 M compare steps per situation)"},
+            "plain_enumeration": {"situations_per_sec": n_plain / (msp * 1e-3), "situations": n_plain, "equal_rows": samep,
+                                  "evals_per_sec": n_plain * EVALS_PER_SITUATION / (msp * 1e-3),
+                                  "frac_of_lookup_peak": n_plain * EVALS_PER_SITUATION / (msp * 1e-3) / lookup_peak_random,
+                                  "what": "hp_direct_kernel: one real evaluation (shared-memory table gathers) per (holding, "
+                                          "runout) pair -- the literal shape of the reference loop"},
+        }
     extras = {}
     if not args.no_extras:
         # batched 7-card evaluator fed from HBM: 10 algorithmic bytes per evaluation
@@ -389,7 +436,8 @@ def main():
     cpu = None
     if world == 1:
         cores = host_cores()
-        n_cpu = max(32, 4 * cores)
+        v0, dt0, _ = cpu_port_throughput(2 * cores, cores)            # probe, then size the sample for ~15 s of CPU work
+        n_cpu = int(min(8192, max(64, 15.0 * v0)))
         v, dt, cpu_rows = cpu_port_throughput(n_cpu, cores)
         ok = ok and bool(np.array_equal(cpu_rows.astype(np.int64), rows[:n_cpu]))   # GPU == oracle on the CPU sample
         py_rate = python_path_evals_per_sec()
@@ -419,8 +467,9 @@ def main():
                 "d2h_bytes_per_step": int(host_out.nbytes) * world, "steps": e2e_steps,
                 "api": "holdem_hp_batch_host (C ABI, host buffers; pinned staging, chunked H2D/kernel/D2H)"},
         "gpu_launches": 3 * args.steps,
-        "gpu_launches_note": "per step: hp_flop_treys_v3_kernel + hp_turn_treys_kernel + hp_direct_kernel (the last two "
+        "gpu_launches_note": "per step: hp_flop_treys_v4_kernel + hp_turn_treys_kernel + hp_direct_kernel (the last two "
                              "exit at once when the batch holds no turn / river rows)",
+        "other_implementations": alt,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,

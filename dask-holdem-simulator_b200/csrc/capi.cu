@@ -175,6 +175,10 @@ int holdem_init(int device) {
     S.T.nf4_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf4);
     S.T.idx4 = reinterpret_cast<const uint16_t *>(S.image + im.off_idx4);
     S.T.key4 = reinterpret_cast<const uint32_t *>(S.image + im.off_key4);
+    S.T.board_t = reinterpret_cast<const uint16_t *>(S.image + im.off_board_t);
+    S.T.board_opp5 = reinterpret_cast<const uint16_t *>(S.image + im.off_board_opp5);
+    S.T.own_our7 = reinterpret_cast<const uint16_t *>(S.image + im.off_own_our7);
+    S.T.own_rank5 = reinterpret_cast<const uint16_t *>(S.image + im.off_own_rank5);
     S.T.n_flop_tasks = im.n_tasks;
     S.T.turn_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_hdr);
     S.T.turn_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_lanes);

@@ -28,11 +28,13 @@
 //                        that coincides with c is taken out again by a short per-lane fix-up loop.
 //   Our own flushes need no special case: our7[Q] is evaluated per card pair Q.
 //
-// Shared memory (~165 KB per CTA): static flush[8192] u16 (index bits folded, m ^ m >> 6, so that the bank depends on ten
-// rank bits) and idx4[91*91] u16 (two rank pairs -> four-rank multiset), then per group (~33 KB): T[91][91] u16 (symmetric) =
-// NF rank of board + rank pair q + rank pair p, expanded from the 1820 four-rank multisets NF4 -- the only 7-card hash
-// lookups of a situation besides 91 for our own hands; W[47][47] u16 = our7 | cls << 13 per unseen pair; the runouts that
-// give us a flush; PD[<=320] 16-byte step descriptors of the flush part, per suit ordered
+// Shared memory (~150 KB per CTA): static flush[8192] u16 (index bits folded, m ^ m >> 6, so that the bank depends on ten
+// rank bits) and the colex pair list, then per group (~33 KB): T[91][91] u16 (symmetric) = non-flush rank of board + rank
+// pair q + rank pair p, our7nf[91] and opp5nf[91] -- three rows of direct-indexed tables (tables.h: board_t, own_our7,
+// board_opp5; indexed by the board's / the five known cards' rank multiset) that one thread fetches with cp.async.bulk
+// onto mbarriers at the start of the situation, so the kernel performs no hash lookups at all; W[47][47] u16 = our7 |
+// cls << 13 per unseen pair; the runouts that give us a flush; PD[<=320] 16-byte step descriptors of the flush part, per
+// suit ordered
 // [both cards in s | one card a in s | undo steps (a, rank of c) | undo steps (rank pair), no card in s].
 // Flush part mapping: a warp task = 32 runouts Q of one (suit, cards-of-Q-in-suit) group x a segment of <= 64 steps;
 // lanes own Q (its rank, suit mask and T row live in registers), the warp walks the steps with one broadcast 16-byte load
@@ -47,12 +49,11 @@ namespace {
 constexpr int kGroupThreads = 256;
 constexpr int kGroups = 4;
 constexpr int kThreads4 = kGroupThreads * kGroups;
-constexpr int kGWarps = kGroupThreads / 32;
 constexpr int kU = 47;
 constexpr int kPairs4 = 1081;
-constexpr int kNf4 = 1820;
 constexpr int kPP = 91;            // rank pairs x <= y, index y(y+1)/2 + x
-constexpr int kTPitch = 94;        // u16 units
+constexpr int kTPitch = 94;        // u16 units (tables.h kBoardTPitch)
+constexpr int kBoardTRow4 = kPP * kTPitch + 6;   // u16 per board (tables.h kBoardTRow): 17,120 bytes
 constexpr int kSeg = 64;           // longest step segment of a flush task (packed 10-bit counters hold 1023)
 constexpr int kPD = 320;           // step descriptors per situation: at most 3 x 66 (rainbow) or 45 + 14 x 11 + 91 + 66
 constexpr int kMaxGroups = 12;
@@ -62,11 +63,13 @@ struct Flop4Group {                    // one situation in flight
     uint4 PD[kPD];                     // x = 2 * (rank bits of the step's cards in s) << 16 | 2 * fold(those bits),
                                        // y = weight << 10 cls(P) (add part), z = weight << 10 clsr(pp) (undo part),
                                        // w = byte offset of row pp of T; 10-bit fields per class
-    uint16_t NF4[kNf4 + 4];            // non-flush rank of board + four-rank multiset
-    uint16_t T[kPP * kTPitch];         // [pp][qp] (symmetric)
+    uint16_t T[kBoardTRow4];           // [pp][qp] (symmetric): non-flush rank of board + rank pair + rank pair, bulk-copied row
+                                       // of DevTables::board_t
+    uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair (row of DevTables::own_our7)
+    uint16_t opp5nf[96];               // non-flush rank of board + rank pair (row of DevTables::board_opp5)
+    unsigned long long bar[2];         // mbarriers: [0] the two small rows, [1] T
     uint16_t W[kU * kU + 3];           // [i*47+j], i<j: our7 | cls << 13
     uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8
-    uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
     uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
     uint32_t cnt[12];                  // lt[3], gt[3], class totals[3]
@@ -91,8 +94,7 @@ struct Flop4Group {                    // one situation in flight
 
 struct Flop4Smem {
     uint16_t flush[kFlushEntries];     // flush[fold(mask)]
-    uint16_t idx4[kPP * kPP + 7];
-    uint32_t cardkey[16];              // additive key by rank
+    uint16_t pairs[kPairs4 + 3];       // colex pairs i | j << 8 of 47 positions
     uint8_t ppxy[96];                  // rank pair -> x | y << 4
     Flop4Group G[kGroups];
 };
@@ -104,6 +106,23 @@ __device__ __forceinline__ uint32_t fold(uint32_t m) { return m ^ (m >> 6); }   
 __device__ __forceinline__ void group_sync(uint32_t gid) {
     asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kGroupThreads) : "memory");
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the async proxy (TMA engine); completion is counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cswap(uint32_t &a, uint32_t &b) { const uint32_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -147,17 +166,23 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     Flop4Group &G = S.G[gid];
     {
         for (uint32_t m = threadIdx.x; m < kFlushEntries; m += kThreads4) S.flush[fold(m)] = __ldg(T.flush + m);
-        for (uint32_t i = threadIdx.x; i < (uint32_t)(kPP * kPP); i += kThreads4) S.idx4[i] = __ldg(T.idx4 + i);
-        if (threadIdx.x < 16) S.cardkey[threadIdx.x] = threadIdx.x < 13 ? c_rank_key[threadIdx.x] : 0u;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)kPairs4; i += kThreads4) S.pairs[i] = __ldg(T.pairs + i);
         if (threadIdx.x < 96) {
             uint32_t y = 0;
             while (tri(y + 1) <= threadIdx.x) ++y;
             S.ppxy[threadIdx.x] = threadIdx.x < kPP ? (uint8_t)((threadIdx.x - tri(y)) | (y << 4)) : (uint8_t)0xFF;
         }
         if (tid < kProfSlots) G.prof[tid] = 0;
+        if (tid == 0) {
+            mbar_init((uint32_t)__cvta_generic_to_shared(&G.bar[0]), 1);
+            mbar_init((uint32_t)__cvta_generic_to_shared(&G.bar[1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
-    const NfHash h5 = T.nf[0], h7 = T.nf[2];
+    const uint32_t bar0_s = (uint32_t)__cvta_generic_to_shared(&G.bar[0]);
+    const uint32_t bar1_s = (uint32_t)__cvta_generic_to_shared(&G.bar[1]);
+    uint32_t parity = 0;
     const uint32_t flush_s = (uint32_t)__cvta_generic_to_shared(S.flush);
     const uint32_t t_s = (uint32_t)__cvta_generic_to_shared(G.T);
     int saw_other = 0;
@@ -180,21 +205,20 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         if (!flop) { saw_other |= (cb[6] == 0xFFu) ? 1 : 2; continue; }
         bool ok = true;
         uint64_t known = 0, bset = 0;
-        uint32_t kb = 0, khole = 0, bsuit = 0, hsuit = 0, bcnt = 0;   // bsuit/hsuit: 4 x 4-bit suit counts (board / hole + board)
+        uint32_t bsuit = 0, hsuit = 0;   // 4 x 4-bit suit counts (board / hole + board)
+        uint32_t rk[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             const uint32_t c = cb[k];
             ok = ok && c < 52u;
             const uint32_t cc = c < 52u ? c : 0u;
             known |= card_bit(cc);
-            const uint32_t r = card_rank(cc);
+            rk[k] = card_rank(cc);
             hsuit += 1u << (4 * card_suit(cc));
             if (k >= 2) {
                 bset |= card_bit(cc);
-                kb += S.cardkey[r];
                 bsuit += 1u << (4 * card_suit(cc));
-                bcnt += 1u << (2 * r);
-            } else khole += S.cardkey[r];
+            }
         }
         ok = ok && __popcll(known) == 5;
         if (!ok) {
@@ -203,7 +227,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         if (tid < 12) G.cnt[tid] = 0;
         if (tid < 4) G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
-        if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
+        if (tid >= 64 && tid < 160) G.qflush[tid - 64] = 0;
         if (warp == 0) {
             // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
             const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
@@ -242,91 +266,84 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (lane == 0) { G.ns[s] = (uint8_t)nsu; G.smask[s] = rm; }
             }
             __syncwarp();
+            {
+                // ---- flush task groups and PD sections: lane = 3 * suit + (2 - qtype), scans over the warp -------------------------
+                const uint32_t s = min(lane / 3u, 3u), qtype = 2u - (lane - 3u * (lane / 3u));
+                const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = G.ns[s], nns = kU - nsu;
+                const uint32_t nboth = choose2u(nsu), none = nsu * nns;
+                // step list of the suit: [both cards in s | a | (a, rank of c) | rank pairs without a card of s]
+                const uint32_t len2 = nboth, len1 = nboth + 14u * nsu, len0 = len1 + kPP;
+                const uint32_t len = bs == 1 ? len2 : (bs == 2 ? len1 : (bs == 3 ? len0 : 0u));
+                // PD offset of the suit = lengths of the suits before it (every lane of a suit holds the same len)
+                uint32_t pdo = 0;
+#pragma unroll
+                for (uint32_t q = 0; q < 3; ++q) {
+                    const uint32_t lq = __shfl_sync(0xFFFFFFFFu, len, 3 * q);
+                    if (q < s) pdo += lq;
+                }
+                const uint32_t k = bs + qtype;                       // cards of s in board + runout
+                const uint32_t need = 5u - k;                        // 2, 1 or 0 cards of s in P
+                const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? none : choose2u(nns));
+                const uint32_t np = need == 2 ? len2 : (need == 1 ? len1 : len0);
+                const bool live = lane < 12 && bs != 0 && k >= 3 && nq != 0 && np != 0;
+                const uint32_t nseg = (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
+                const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
+                const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
+                const uint32_t gi = __popc(livem & ltm);
+                uint32_t first = ntask;                              // inclusive scan of the task counts
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, first, d);
+                    if ((int)lane >= d) first += v;
+                }
+                if (live) {
+                    G.g_first[gi] = first - ntask;
+                    G.g_nq[gi] = nq; G.g_np[gi] = np; G.g_nseg[gi] = nseg; G.g_seglen[gi] = seglen;
+                    G.g_pdbase[gi] = pdo;
+                    G.g_sq[gi] = s | (qtype << 2);
+                }
+                if (lane < 12 && qtype == 2) { G.pd_base[s] = pdo; G.pd_len[s] = len; }
+                if (lane == 11) {
+                    G.g_first[__popc(livem)] = first;
+                    G.n_groups = __popc(livem);
+                    G.pd_total = pdo + len;
+                    G.next_task = 0;
+                    G.n_ext = 0;
+                }
+            }
+        } else if (warp == 1) {
+            // ---- the situation's table rows, fetched by the TMA engine: T = row b3 of board_t (17 KB, needed by the tasks),
+            //      our7nf = row m5 of own_our7, opp5nf = row b3 of board_opp5 (needed at once).  No hash lookups. -----------
+            uint32_t ours_now = 0;
             if (lane == 0) {
-                // ---- flush task groups and PD sections --------------------------------------------------------------
-                uint32_t ng = 0, first = 0, pdo = 0;
-                for (uint32_t s = 0; s < 4; ++s) {
-                    const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = G.ns[s], nns = kU - nsu;
-                    const uint32_t nboth = nsu ? choose2u(nsu) : 0u, none = nsu * nns;
-                    // step list of the suit: [both cards in s | a | (a, rank of c) | rank pairs without a card of s]
-                    const uint32_t len2 = nboth, len1 = nboth + 14u * nsu, len0 = len1 + kPP;
-                    uint32_t len = 0;
-                    if (bs == 1) len = len2;
-                    else if (bs == 2) len = len1;
-                    else if (bs == 3) len = len0;
-                    G.pd_base[s] = pdo;
-                    G.pd_len[s] = len;
-                    if (bs == 0) continue;
-                    for (int qtype = 2; qtype >= 0; --qtype) {
-                        const uint32_t k = bs + (uint32_t)qtype;
-                        if (k < 3) continue;
-                        const uint32_t need = 5 - k;   // 2, 1 or 0 cards of s in P
-                        const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? none : (nns ? choose2u(nns) : 0u));
-                        const uint32_t np = need == 2 ? len2 : (need == 1 ? len1 : len0);
-                        if (nq == 0 || np == 0) continue;
-                        const uint32_t nseg = (np + kSeg - 1) / kSeg, seglen = (np + nseg - 1) / nseg;
-                        G.g_first[ng] = first;
-                        G.g_nq[ng] = nq; G.g_np[ng] = np; G.g_nseg[ng] = nseg; G.g_seglen[ng] = seglen;
-                        G.g_pdbase[ng] = pdo;
-                        G.g_sq[ng] = s | ((uint32_t)qtype << 2);
-                        first += ((nq + 31) / 32) * nseg;
-                        ++ng;
-                    }
-                    pdo += len;
-                }
-                G.g_first[ng] = first;
-                G.n_groups = ng;
-                G.pd_total = pdo;
-                G.next_task = 0;
-                G.n_ext = 0;
-            }
-        } else {
-            // ---- the 7-card hash lookups of the situation: NF4[1820] = board + four ranks, our7nf[91] = hole + board + rank
-            //      pair; four independent lookups in flight per thread.  Multisets that cannot exist with this board read
-            //      an arbitrary table slot: their entries are only ever used with weight 0. -------------------------------
-            constexpr uint32_t kWorkers = kGroupThreads - 32, kItems = kNf4 + kPP;
-            for (uint32_t e0 = tid - 32; e0 < kItems; e0 += 4 * kWorkers) {
-                uint32_t key[4], slot[4], disp[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t e = e0 + q * kWorkers;
-                    key[q] = kb;
-                    if (e < (uint32_t)kNf4) key[q] += __ldg(T.key4 + e);
-                    else if (e < kItems) {
-                        const uint32_t xy = S.ppxy[e - kNf4];
-                        key[q] += khole + S.cardkey[xy & 15u] + S.cardkey[xy >> 4];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) disp[q] = __ldg(h7.disp + ((key[q] * h7.mul_b) >> h7.bshift));
-#pragma unroll
-                for (int q = 0; q < 4; ++q) slot[q] = (((key[q] * h7.mul_s) >> h7.sshift) + disp[q]) & h7.smask;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) disp[q] = __ldg(h7.val + slot[q]);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t e = e0 + q * kWorkers;
-                    if (e < (uint32_t)kNf4) G.NF4[e] = (uint16_t)disp[q];
-                    else if (e < kItems) G.our7nf[e - kNf4] = (uint16_t)disp[q];
-                }
-            }
-            // ---- rank-level flop class per rank pair (5-card hash) -----------------------------------------------------------
-            if (tid >= kGroupThreads - 96) {
-                const uint32_t pp = tid - (kGroupThreads - 96);
+                uint32_t b0 = rk[2], b1 = rk[3], b2 = rk[4];
+                cswap(b0, b1); cswap(b1, b2); cswap(b0, b1);
+                const uint32_t b3 = b0 + tri(b1) + (b2 + 2) * (b2 + 1) * b2 / 6;
+                uint32_t a0 = rk[0], a1 = rk[1], a2 = b0, a3 = b1, a4 = b2;      // five ranks: insert the hole cards
+                cswap(a0, a1);
+                cswap(a1, a2); cswap(a2, a3); cswap(a3, a4);                    // the larger hole rank sinks into place
+                cswap(a0, a1); cswap(a1, a2); cswap(a2, a3);                    // then the smaller one
+                const uint32_t m5 = a0 + tri(a1) + (a2 + 2) * (a2 + 1) * a2 / 6 + (a3 + 3) * (a3 + 2) * (a3 + 1) * a3 / 24 +
+                                    (a4 + 4) * (a4 + 3) * (a4 + 2) * (a4 + 1) * a4 / 120;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of the buffers precede the refill
+                mbar_expect_tx(bar0_s, 2 * 192);
+                bulk_g2s((uint32_t)__cvta_generic_to_shared(G.our7nf), T.own_our7 + (size_t)m5 * 96, 192, bar0_s);
+                bulk_g2s((uint32_t)__cvta_generic_to_shared(G.opp5nf), T.board_opp5 + (size_t)b3 * 96, 192, bar0_s);
+                mbar_expect_tx(bar1_s, kBoardTRow4 * 2);
+                bulk_g2s(t_s, T.board_t + (size_t)b3 * kBoardTRow4, kBoardTRow4 * 2, bar1_s);
                 const uint32_t fm = flush_mask(known, 5);
-                const uint32_t ours_now = fm ? (uint32_t)S.flush[fold(fm)] : nf_lookup(h5, kb + khole);
-                if (pp == 0) G.ours_now = ours_now;
-                uint32_t word = 0, code = 3;
-                if (pp < (uint32_t)kPP) {
-                    const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
-                    const uint32_t cx = ((bcnt >> (2 * x)) & 3u) + 1 + (x == y), cy = ((bcnt >> (2 * y)) & 3u) + 1;
-                    if (cx <= 4 && cy <= 4) {
-                        const uint32_t v = nf_lookup(h5, kb + S.cardkey[x] + S.cardkey[y]);
-                        code = ours_now < v ? 0u : (ours_now == v ? 1u : 2u);
-                        word = 1u << (10 * code);
-                    }
-                }
-                G.clsw[pp] = word;
+                ours_now = fm ? (uint32_t)S.flush[fold(fm)] : (uint32_t)__ldg(T.own_rank5 + m5);
+                G.ours_now = ours_now;
+            }
+            ours_now = __shfl_sync(0xFFFFFFFFu, ours_now, 0);
+            mbar_wait(bar0_s, parity);
+            // ---- rank-level flop class per rank pair ------------------------------------------------------------------------
+#pragma unroll
+            for (uint32_t ps = 0; ps < 3; ++ps) {
+                const uint32_t pp = lane + 32u * ps;
+                const uint32_t v = G.opp5nf[pp];                     // 0 = the pair cannot exist with this board
+                const uint32_t code = v == 0 ? 3u : (ours_now < v ? 0u : (ours_now == v ? 1u : 2u));
+                G.clsw[pp] = v == 0 ? 0u : 1u << (10 * code);
                 G.clsr[pp] = (uint8_t)code;
             }
         }
@@ -334,6 +351,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         HOLDEM_PROF(0)
         {
             // ---- W: our final rank with the pair as runout, flop class of the pair as a holding (no global memory) ---------
+            mbar_wait(bar0_s, parity);                                 // (already complete: warp 1 waited before the barrier)
             const uint32_t ours_now = G.ours_now;
             // the suit in which we can still make a flush (>= 3 of hole + board), and the one the board is monotone in
             const uint32_t f3 = (hsuit + 0x5555u) & 0x8888u;            // nibble >= 3
@@ -344,8 +362,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             const uint32_t ms = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
             const uint32_t mbmask = m3 ? G.bmask[ms] : 0u;
             uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
             for (uint32_t p = tid; p < (uint32_t)kPairs4; p += kGroupThreads) {
-                const uint32_t pr = __ldg(T.pairs + p);
+                const uint32_t pr = S.pairs[p];
                 const uint32_t i = pr & 0xFFu, j = pr >> 8;
                 const uint32_t ci = G.code[i], cj = G.code[j];
                 const uint32_t ri = ci >> 2, rj = cj >> 2, si = ci & 3u, sj = cj & 3u;
@@ -379,14 +398,6 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             }
             if (tid < 4) G.hist_none[tid] = 0;
-            // ---- T[pp][qp] = NF4[multiset(pp + qp)], row by row ---------------------------------------------------------------------
-            for (uint32_t row = warp; row < (uint32_t)kPP; row += kGWarps) {
-#pragma unroll
-                for (uint32_t ps = 0; ps < 3; ++ps) {
-                    const uint32_t col = lane + 32u * ps;
-                    if (col < (uint32_t)kPP) G.T[row * kTPitch + col] = G.NF4[S.idx4[row * kPP + col]];
-                }
-            }
         }
         group_sync(gid);                                                                            // (C)
         HOLDEM_PROF(1)
@@ -401,7 +412,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 uint32_t t = e - G.pd_base[s];
                 const uint32_t nsu = G.ns[s], nboth = choose2u(nsu), sm = G.smask[s];
                 if (t < nboth) {                                   // both cards of the holding in s
-                    const uint32_t pr = __ldg(T.pairs + t);
+                    const uint32_t pr = S.pairs[t];
                     const uint32_t pa = G.Ls[s][pr & 0xFFu], pb = G.Ls[s][pr >> 8];
                     const uint32_t ra = G.code[pa] >> 2, rb = G.code[pb] >> 2;
                     const uint32_t cls = G.W[pa * kU + pb] >> 13;
@@ -434,19 +445,24 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             }
         }
         group_sync(gid);                                                                            // (D)
+        mbar_wait(bar1_s, parity);                                     // T has landed
+        parity ^= 1u;
         HOLDEM_PROF(2)
 
         uint32_t accL[3] = {0, 0, 0}, accG[3] = {0, 0, 0};   // per class: our7 < R / our7 > R (net of the undo steps, mod 2^32)
         const uint32_t n_groups = G.n_groups;
         const uint32_t n_flush_tasks = G.g_first[n_groups];
         const uint32_t n_entries = kPP + G.n_ext;
-        const uint32_t n_tasks = n_flush_tasks + (n_entries + 31) / 32;
+        // generic tasks first (they are the longest): task = 2 * chunk + half, half 0 = rank pairs with y <= 8, half 1 = y >= 9
+        const uint32_t n_gen_tasks = 2u * ((n_entries + 31) / 32);
+        const uint32_t n_tasks = n_gen_tasks + n_flush_tasks;
         for (;;) {
             uint32_t task = 0;
             if (lane == 0) task = atomicAdd(&G.next_task, 1u);
             task = __shfl_sync(0xFFFFFFFFu, task, 0);
             if (task >= n_tasks) break;
-            if (task < n_flush_tasks) {
+            if (task >= n_gen_tasks) {
+                task -= n_gen_tasks;
                 // ================= flush task: 32 runouts Q x a segment of steps =======================================
                 uint32_t g = 0;
                 while (g + 1 < n_groups && task >= G.g_first[g + 1]) ++g;
@@ -466,7 +482,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         i = min(x, y); j = max(x, y);
                         zpos = y;
                     } else {
-                        const uint32_t pr = __ldg(T.pairs + qi);
+                        const uint32_t pr = S.pairs[qi];
                         const uint8_t *L = qtype == 2 ? G.Ls[s] : G.Lns[s];
                         i = L[pr & 0xFFu]; j = L[pr >> 8];
                     }
@@ -527,7 +543,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             } else {
                 // ================= generic task: 32 merged runouts, the warp walks the rank pairs of P class by class =====
-                const uint32_t e = (task - n_flush_tasks) * 32 + lane;
+                const uint32_t e = (task >> 1) * 32 + lane;
+                const bool upper = (task & 1u) != 0;
                 uint32_t qp = 0, val = 0, mult = 0;
                 if (e < (uint32_t)kPP) {
                     qp = e;
@@ -549,15 +566,29 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // all 91 rank pairs of P, fully unrolled (constant shifts and offsets); unweighted counts n_Q(pp) go into packed
                 // 10-bit class fields (they sum to C(45,2) = 990 per runout), the runout multiplicity is applied afterwards
                 uint32_t lp = 0, gp = 0;
+                if (!upper) {
 #pragma unroll
-                for (int y = 0; y < 13; ++y) {
-                    const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;
+                    for (int y = 0; y < 9; ++y) {
+                        const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;
 #pragma unroll
-                    for (int x = 0; x <= y; ++x) {
-                        const int pp = y * (y + 1) / 2 + x;
-                        const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
-                        const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
-                        cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
+                        for (int x = 0; x <= y; ++x) {
+                            const int pp = y * (y + 1) / 2 + x;
+                            const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
+                            const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
+                            cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int y = 9; y < 13; ++y) {
+                        const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;
+#pragma unroll
+                        for (int x = 0; x <= y; ++x) {
+                            const int pp = y * (y + 1) / 2 + x;
+                            const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
+                            const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
+                            cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
+                        }
                     }
                 }
 #pragma unroll

@@ -301,6 +301,56 @@ struct Builder {
                                 (r[3] + 3) * (r[3] + 2) * (r[3] + 1) * r[3] / 24;
                         t.idx4[91 * (q2 * (q2 + 1) / 2 + q1) + y * (y + 1) / 2 + x] = (uint16_t)e;
                     }
+        // ---- 9. direct-indexed board / own-hand tables of the rank-multiset flop kernel ------------------------------------------
+        {
+            auto rank_of = [&](const int *ranks, int n, int hash) -> uint16_t {   // 0 when a rank would be needed five times
+                int cnt[13] = {0};
+                uint32_t key = 0;
+                for (int i = 0; i < n; ++i) {
+                    if (++cnt[ranks[i]] > 4) return 0;
+                    key += kRankKey[ranks[i]];
+                }
+                return (uint16_t)t.nf[hash].lookup(key);
+            };
+            int px[91], py[91];
+            for (int y = 0; y < 13; ++y)
+                for (int x = 0; x <= y; ++x) { px[y * (y + 1) / 2 + x] = x; py[y * (y + 1) / 2 + x] = y; }
+            t.board_t.assign((size_t)kBoardMultisets * kBoardTRow, 0);
+            t.board_opp5.assign((size_t)kBoardMultisets * 96, 0);
+            for (int r2 = 0; r2 < 13; ++r2)
+                for (int r1 = 0; r1 <= r2; ++r1)
+                    for (int r0 = 0; r0 <= r1; ++r0) {
+                        const int b3 = r0 + (r1 + 1) * r1 / 2 + (r2 + 2) * (r2 + 1) * r2 / 6;
+                        uint16_t *row = t.board_t.data() + (size_t)b3 * kBoardTRow;
+                        for (int q = 0; q < 91; ++q) {
+                            for (int p = q; p < 91; ++p) {
+                                const int r[7] = {r0, r1, r2, px[q], py[q], px[p], py[p]};
+                                const uint16_t v = rank_of(r, 7, 2);
+                                row[q * kBoardTPitch + p] = v;
+                                row[p * kBoardTPitch + q] = v;
+                            }
+                            const int r5[5] = {r0, r1, r2, px[q], py[q]};
+                            t.board_opp5[(size_t)b3 * 96 + q] = rank_of(r5, 5, 0);
+                        }
+                    }
+            t.own_our7.assign((size_t)kOwnMultisets * 96, 0);
+            t.own_rank5.assign(kOwnMultisets + 4, 0);
+            for (int r4 = 0; r4 < 13; ++r4)
+                for (int r3 = 0; r3 <= r4; ++r3)
+                    for (int r2 = 0; r2 <= r3; ++r2)
+                        for (int r1 = 0; r1 <= r2; ++r1)
+                            for (int r0 = 0; r0 <= r1; ++r0) {
+                                const int m5 = r0 + (r1 + 1) * r1 / 2 + (r2 + 2) * (r2 + 1) * r2 / 6 +
+                                               (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24 +
+                                               (r4 + 4) * (r4 + 3) * (r4 + 2) * (r4 + 1) * r4 / 120;
+                                const int r5[5] = {r0, r1, r2, r3, r4};
+                                t.own_rank5[m5] = rank_of(r5, 5, 0);
+                                for (int q = 0; q < 91; ++q) {
+                                    const int r[7] = {r0, r1, r2, r3, r4, px[q], py[q]};
+                                    t.own_our7[(size_t)m5 * 96 + q] = rank_of(r, 7, 2);
+                                }
+                            }
+        }
         ok = true;
     }
 };
@@ -397,6 +447,28 @@ int selftest(char *msg, int msg_len) {
                 if (got[k] != want[k]) return fail("idx4");
         }
     }
+    {   // direct-indexed tables: spot values against the hashes they were built from
+        if (t.board_t.size() != (size_t)kBoardMultisets * kBoardTRow || t.own_our7.size() != (size_t)kOwnMultisets * 96)
+            return fail("board table sizes");
+        // board 2 3 4 (ranks 0,1,2 -> b3 = 0 + 1 + 4), q = pair (5,6) = ranks (3,4), p = (A,A): straight 2-6, rank 1608
+        const int b3 = 0 + (1 + 1) * 1 / 2 + (2 + 2) * (2 + 1) * 2 / 6;
+        const int q = 4 * 5 / 2 + 3, p = 12 * 13 / 2 + 12;
+        const uint32_t key = kRankKey[0] + kRankKey[1] + kRankKey[2] + kRankKey[3] + kRankKey[4] + 2 * kRankKey[12];
+        if (t.board_t[(size_t)b3 * kBoardTRow + q * kBoardTPitch + p] != t.nf[2].lookup(key) ||
+            t.board_t[(size_t)b3 * kBoardTRow + p * kBoardTPitch + q] != t.nf[2].lookup(key))
+            return fail("board_t entry");
+        if (t.nf[2].lookup(key) != 1608) return fail("six-high straight");
+        // four deuces on the board side are impossible with a pair of deuces added twice
+        if (t.board_t[0 * kBoardTRow + 0 * kBoardTPitch + 0] != 0) return fail("impossible multiset must be 0");
+        // own hand A A K K Q: m5 of ranks (10,11,11,12,12); plus pair (Q,Q) = full house aces over... kings full? AAKKQ+QQ -> AAA? no: AA KK QQQ -> QQQAA
+        const int r[5] = {10, 11, 11, 12, 12};
+        const int m5 = r[0] + (r[1] + 1) * r[1] / 2 + (r[2] + 2) * (r[2] + 1) * r[2] / 6 +
+                       (r[3] + 3) * (r[3] + 2) * (r[3] + 1) * r[3] / 24 + (r[4] + 4) * (r[4] + 3) * (r[4] + 2) * (r[4] + 1) * r[4] / 120;
+        const uint32_t k5 = kRankKey[10] + 2 * kRankKey[11] + 2 * kRankKey[12];
+        if (t.own_rank5[m5] != t.nf[0].lookup(k5)) return fail("own_rank5 entry");
+        const int qq = 10 * 11 / 2 + 10;
+        if (t.own_our7[(size_t)m5 * 96 + qq] != t.nf[2].lookup(k5 + 2 * kRankKey[10])) return fail("own_our7 entry");
+    }
     if (msg && msg_len > 0) msg[0] = 0;
     return 0;
 }
@@ -416,6 +488,10 @@ TableImage make_image(const Tables &t) {
     im.off_nf4 = append(t.nf4_ranks.data(), t.nf4_ranks.size() * 2);
     im.off_idx4 = append(t.idx4.data(), t.idx4.size() * 2);
     im.off_key4 = append(t.key4.data(), t.key4.size() * 4);
+    im.off_board_t = append(t.board_t.data(), t.board_t.size() * 2);
+    im.off_board_opp5 = append(t.board_opp5.data(), t.board_opp5.size() * 2);
+    im.off_own_our7 = append(t.own_our7.data(), t.own_our7.size() * 2);
+    im.off_own_rank5 = append(t.own_rank5.data(), t.own_rank5.size() * 2);
     im.n_tasks = (uint32_t)t.flop_task_hdr.size();
     im.off_turn_hdr = append(t.turn_task_hdr.data(), t.turn_task_hdr.size() * 4);
     im.off_turn_lanes = append(t.turn_lanes.data(), t.turn_lanes.size() * 4);

@@ -19,6 +19,10 @@ constexpr uint32_t kRankKey[13] = {0,    1,     5,     22,     98,     453,    2
 
 constexpr int kNumClasses = 7462;
 constexpr int kFlushTableSize = 8192;
+constexpr int kBoardMultisets = 455;     // C(15,3)
+constexpr int kOwnMultisets = 6188;       // C(17,5)
+constexpr int kBoardTPitch = 94;          // u16 per row of board_t
+constexpr int kBoardTRow = 91 * kBoardTPitch + 6;   // u16 per board (17,120 bytes: a multiple of 16)
 constexpr int kMaxPairs = 1326;  // C(52,2), colex order: pair p of (i<j) has p = j(j-1)/2 + i
 
 // Hash-displace perfect hash over the additive keys of one hand size:
@@ -68,6 +72,13 @@ struct Tables {
     std::vector<uint16_t> idx4;
     // key4[e] = sum of the additive rank keys of the e-th four-rank multiset (same numbering as nf4_ranks)
     std::vector<uint32_t> key4;
+    // Direct-indexed tables of the rank-multiset flop kernel, one contiguous row per situation (fetched with one bulk copy):
+    //   board_t[b3][91][kBoardTPitch]  non-flush 7-card rank of board + rank pair q + rank pair p (symmetric in q, p),
+    //                                  b3 = r0 + C(r1+1,2) + C(r2+2,3) over the sorted board ranks; 0 = impossible multiset
+    //   board_opp5[b3][96]             non-flush 5-card rank of board + rank pair (the opponent on the flop)
+    //   own_our7[m5][96]               non-flush 7-card rank of hole + board + rank pair, m5 = five-rank multiset index
+    //   own_rank5[m5]                  non-flush 5-card rank of hole + board
+    std::vector<uint16_t> board_t, board_opp5, own_our7, own_rank5;
     // Statistics kept for selftest().
     int n_keys[3] = {0, 0, 0};
 };
@@ -79,6 +90,7 @@ int selftest(char *msg, int msg_len);  // 0 = ok
 struct TableImage {
     std::vector<uint8_t> bytes;
     uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0, off_idx4 = 0, off_key4 = 0;
+    uint32_t off_board_t = 0, off_board_opp5 = 0, off_own_our7 = 0, off_own_rank5 = 0;
     uint32_t n_tasks = 0;
     uint32_t off_turn_hdr = 0, off_turn_lanes = 0, off_nf3 = 0, n_turn_tasks = 0;
     uint32_t off_ref_hdr[2] = {0, 0}, off_ref_lanes[2] = {0, 0}, n_ref_tasks[2] = {0, 0};

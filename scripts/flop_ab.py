@@ -61,6 +61,8 @@ def main():
         reps = max(1, 16384 // len(sub))
         sub = np.concatenate([sub] * reps)[:16384] if len(sub) < 16384 else sub[:16384]
         ds = torch.from_numpy(np.ascontiguousarray(sub)).cuda()
+        _, cyc = hb.flop_phase_cycles(ds)
+        print(f"  {name:9s} phase cycles per situation:", (cyc.cpu().numpy() / len(sub)).round(0).tolist())
         for v in variants:
             ms = timed(lambda: hb.hand_potential_counts(ds, "treys", flop_variant=v))
             print(f"  {name:9s} ({(nsuit == k).mean() * 100:.1f}% of deals) variant {v}: {len(sub) / ms / 1e3:.3f} M situations/s")

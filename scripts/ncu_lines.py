@@ -29,6 +29,32 @@ want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
 for h, u, v in zip(hdr, unit, r):
     if h in want or ("issue_stalled" in h and "per_issue_active" in h and f(v) > 0.3):
         print(f"{h} [{u}] = {v}")
+vals = dict(zip(hdr, r))
+if len(sys.argv) > 5:
+    # python scripts/ncu_lines.py report units top counters.json kernel_key  -> merge the headline counters into the JSON file
+    import json
+    import os
+    path, key = sys.argv[4], sys.argv[5]
+    doc = json.load(open(path)) if os.path.exists(path) else {}
+    doc[key] = {
+        "warp_instructions_per_situation": f(vals["smsp__inst_executed.sum"]) / units,
+        "shared_wavefronts_per_situation": f(vals["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]) / units,
+        "shared_bank_conflict_wavefronts_per_situation": f(vals["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]) / units,
+        "issue_active_pct": f(vals["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+        "alu_pipe_pct": f(vals["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]),
+        "fma_pipe_pct": f(vals["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
+        "lsu_pipe_pct": f(vals["sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]),
+        "shared_wavefront_pct": f(vals["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]),
+        "gpu_time_ms_under_ncu": f(vals["gpu__time_duration.sum"]),
+        "dram_bytes_read": f(vals["dram__bytes_read.sum"]) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1}.get(
+            dict(zip(hdr, unit))["dram__bytes_read.sum"], 1),
+        "dram_bytes_write": f(vals["dram__bytes_write.sum"]) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1}.get(
+            dict(zip(hdr, unit))["dram__bytes_write.sum"], 1),
+        "units_per_launch": units,
+        "capture": os.path.basename(rep) + " (ncu --set full --clock-control none)",
+    }
+    json.dump(doc, open(path, "w"), indent=1)
+    print("wrote", path, key)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
                      text=True).stdout
 rows = list(csv.reader(src.splitlines()))
