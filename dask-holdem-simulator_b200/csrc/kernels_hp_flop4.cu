@@ -46,8 +46,8 @@ namespace holdem {
 
 namespace {
 
-constexpr int kGroupThreads = 256;
-constexpr int kGroups = 4;
+constexpr int kGroupThreads = 160;
+constexpr int kGroups = 6;
 constexpr int kThreads4 = kGroupThreads * kGroups;
 constexpr int kU = 47;
 constexpr int kPairs4 = 1081;
@@ -76,10 +76,11 @@ struct Flop4Group {                    // one situation in flight
     uint32_t bmask[4];                 // board rank mask per suit
     uint32_t g_first[kMaxGroups + 1];  // first task id of each flush group; [n_groups] = total
     uint32_t g_nq[kMaxGroups], g_np[kMaxGroups], g_nseg[kMaxGroups], g_seglen[kMaxGroups], g_pdbase[kMaxGroups];
-    uint32_t g_sq[kMaxGroups];         // suit | qtype << 2
+    uint32_t g_sq[kMaxGroups];         // suit | qtype << 2 | rank-level lanes << 4
     uint32_t pd_base[4], pd_len[4];    // PD section per suit
     uint32_t smask[4];                 // rank mask of the unseen cards per suit
     uint32_t hist_none[4];             // holdings without a card of the board's suit, by flop class (monotone boards)
+    uint32_t HA[16 * 13];              // monotone boards: class histogram (10-bit fields) of {a, c} over the c of one rank outside s
     uint32_t upack[2];                 // unseen cards per rank, 3 bits each (64-bit)
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
     uint32_t prof[kProfSlots];
@@ -283,7 +284,12 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
                 const uint32_t k = bs + qtype;                       // cards of s in board + runout
                 const uint32_t need = 5u - k;                        // 2, 1 or 0 cards of s in P
-                const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? none : choose2u(nns));
+                // Runouts with a card outside s are merged by the RANK of that card (weight = number of such cards) unless they
+                // give us a flush, which happens for all of them or none: we need hs_s + (cards of the runout in s) >= 5
+                const uint32_t hs_s = (hsuit >> (4 * s)) & 15u;
+                const bool rank_lanes = qtype != 2 && hs_s + qtype < 5;
+                const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? (rank_lanes ? 13u * nsu : none)
+                                                                     : (rank_lanes ? (uint32_t)kPP : choose2u(nns)));
                 const uint32_t np = need == 2 ? len2 : (need == 1 ? len1 : len0);
                 const bool live = lane < 12 && bs != 0 && k >= 3 && nq != 0 && np != 0;
                 const uint32_t nseg = (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
@@ -300,7 +306,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     G.g_first[gi] = first - ntask;
                     G.g_nq[gi] = nq; G.g_np[gi] = np; G.g_nseg[gi] = nseg; G.g_seglen[gi] = seglen;
                     G.g_pdbase[gi] = pdo;
-                    G.g_sq[gi] = s | (qtype << 2);
+                    G.g_sq[gi] = s | (qtype << 2) | ((uint32_t)rank_lanes << 4);
                 }
                 if (lane < 12 && qtype == 2) { G.pd_base[s] = pdo; G.pd_len[s] = len; }
                 if (lane == 11) {
@@ -434,6 +440,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     }
                     G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, wgt * G.clsw[pp], pp * (kTPitch * 2));
                     if (hist) atomicAdd(&G.PD[G.pd_base[s] + nboth + ai].y, hist);
+                    if (((bsuit >> (4 * s)) & 15u) == 3) G.HA[ai * 13 + y] = hist;
                 } else {                                           // undo step for a rank pair, neither card in s
                     const uint32_t pp = t - (nboth + 14u * nsu);
                     const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
@@ -469,30 +476,53 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t local = task - G.g_first[g];
                 const uint32_t nseg = G.g_nseg[g], seglen = G.g_seglen[g], np = G.g_np[g], nq = G.g_nq[g];
                 const uint32_t chunk = local / nseg, seg = local - chunk * nseg;
-                const uint32_t s = G.g_sq[g] & 3u, qtype = G.g_sq[g] >> 2;
+                const uint32_t s = G.g_sq[g] & 3u, qtype = (G.g_sq[g] >> 2) & 3u;
+                const bool rank_lanes = (G.g_sq[g] >> 4) != 0;
                 const uint32_t p0 = seg * seglen, p1 = min(np, p0 + seglen);
                 const uint32_t qi = chunk * 32 + lane;
-                const uint32_t nsu = G.ns[s], nns = kU - nsu;
-                uint32_t our = 0, fqf = 0, qb2 = 0, zpos = 0xFFu, qcol = 0;
+                const uint32_t nsu = G.ns[s], nns = kU - nsu, sm = G.smask[s];
+                // the lane's runout: our rank, its cards of s (rank bits), folded flush index of board + runout in s, its column
+                // of T, its multiplicity; zpos / rz describe its card outside s for the fix-up below
+                uint32_t our = 0, fqf = 0, qb2 = 0, zpos = 0xFFu, rz = 0, qcol = 0, wl = 0, rq = 99;
                 if (qi < nq) {
-                    uint32_t i, j;
-                    if (qtype == 1) {
-                        const uint32_t a = qi / nns, z = qi - a * nns;
-                        const uint32_t x = G.Ls[s][a], y = G.Lns[s][z];
-                        i = min(x, y); j = max(x, y);
-                        zpos = y;
+                    uint32_t qbits, ppq;
+                    if (rank_lanes && qtype == 1) {            // (card q of s, rank of the other card)
+                        const uint32_t a = qi / 13u;
+                        rz = qi - 13u * a;
+                        rq = G.code[G.Ls[s][a]] >> 2;
+                        qbits = 1u << rq;
+                        ppq = tri(max(rq, rz)) + min(rq, rz);
+                        wl = G.u[rz] - ((sm >> rz) & 1u);
+                        our = G.our7nf[ppq];
+                    } else if (rank_lanes) {                   // rank pair, neither card in s
+                        const uint32_t xy = S.ppxy[qi], x = xy & 15u, y = xy >> 4;
+                        const uint32_t wx = G.u[x] - ((sm >> x) & 1u), wy = G.u[y] - ((sm >> y) & 1u);
+                        qbits = 0;
+                        ppq = qi;
+                        wl = x != y ? wx * wy : (wx ? choose2u(wx) : 0u);
+                        our = G.our7nf[ppq];
                     } else {
-                        const uint32_t pr = S.pairs[qi];
-                        const uint8_t *L = qtype == 2 ? G.Ls[s] : G.Lns[s];
-                        i = L[pr & 0xFFu]; j = L[pr >> 8];
+                        uint32_t i, j;
+                        if (qtype == 1) {
+                            const uint32_t a = qi / nns, z = qi - a * nns;
+                            const uint32_t x = G.Ls[s][a], y = G.Lns[s][z];
+                            i = min(x, y); j = max(x, y);
+                            zpos = y;
+                        } else {
+                            const uint32_t pr = S.pairs[qi];
+                            const uint8_t *L = qtype == 2 ? G.Ls[s] : G.Lns[s];
+                            i = L[pr & 0xFFu]; j = L[pr >> 8];
+                        }
+                        const uint32_t ci = G.code[i], cj = G.code[j];
+                        const uint32_t ri = ci >> 2, rj = cj >> 2;
+                        our = G.W[i * kU + j] & 0x1FFFu;
+                        qbits = ((ci & 3u) == s ? 1u << ri : 0u) | ((cj & 3u) == s ? 1u << rj : 0u);
+                        ppq = tri(rj) + ri;
+                        wl = 1;
                     }
-                    const uint32_t ci = G.code[i], cj = G.code[j];
-                    const uint32_t ri = ci >> 2, rj = cj >> 2;
-                    our = G.W[i * kU + j] & 0x1FFFu;
-                    const uint32_t qbits = ((ci & 3u) == s ? 1u << ri : 0u) | ((cj & 3u) == s ? 1u << rj : 0u);
                     qb2 = qbits << 17;
                     fqf = 2u * fold(G.bmask[s] | qbits);
-                    qcol = 2u * (tri(rj) + ri);
+                    qcol = 2u * ppq;
                 }
                 const uint32_t tq_s = t_s + qcol;
                 const uint4 *pd = G.PD + G.g_pdbase[g] + p0;
@@ -505,11 +535,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t rn = lds_u16(tq_s + d.w);
                     flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
                 }
-                if (qi >= nq) { aL = 0; aG = 0; sL = 0; sG = 0; }   // lanes past the end of the runout list
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    accL[c] += ((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu);
-                    accG[c] += ((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu);
+                for (int c = 0; c < 3; ++c) {   // wl = 0 on lanes past the end of the runout list
+                    accL[c] += (((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu)) * wl;
+                    accG[c] += (((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu)) * wl;
                 }
                 const uint32_t need = 5u - (((bsuit >> (4 * s)) & 15u) + qtype);
                 if (seg == 0 && need == 0 && qi < nq) {
@@ -521,9 +550,26 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         if (our > rf) accG[c] += G.hist_none[c];
                     }
                 }
-                if (seg == 0 && need == 1 && qtype == 1) {
+                if (seg == 0 && need == 1 && qtype == 1 && rank_lanes) {
+                    // every card z of rank rz outside s was counted among the c of {a, c} in its own runout: take the pairs
+                    // {a, z} out again -- summed over z they are the class histogram HA[a][rz] and wl undo steps of (ra, rz)
+                    for (uint32_t ai = 0; ai < nsu; ++ai) {
+                        const uint32_t ra = G.code[G.Ls[s][ai]] >> 2;
+                        if (wl != 0 && ra != rq) {
+                            const uint32_t rf = lds_u16(flush_s + (fqf ^ (2u * fold(1u << ra))));
+                            const uint32_t pp = tri(max(ra, rz)) + min(ra, rz);
+                            const uint32_t rn = lds_u16(tq_s + pp * (kTPitch * 2));
+                            const uint32_t ha = G.HA[ai * 13 + rz], cw = wl * G.clsw[pp];
+#pragma unroll
+                            for (uint32_t c = 0; c < 3; ++c) {
+                                accL[c] += (our < rn ? (cw >> (10 * c)) & 0x3FFu : 0u) - (our < rf ? (ha >> (10 * c)) & 0x3FFu : 0u);
+                                accG[c] += (our > rn ? (cw >> (10 * c)) & 0x3FFu : 0u) - (our > rf ? (ha >> (10 * c)) & 0x3FFu : 0u);
+                            }
+                        }
+                    }
+                } else if (seg == 0 && need == 1 && qtype == 1) {
                     // the runout's card z outside s was counted among the c of every {a, c}: take {a, z} out again
-                    const uint32_t rz = zpos < (uint32_t)kU ? (uint32_t)(G.code[zpos] >> 2) : 0u;
+                    rz = zpos < (uint32_t)kU ? (uint32_t)(G.code[zpos] >> 2) : 0u;
                     for (uint32_t ai = 0; ai < nsu; ++ai) {
                         const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
                         if (qi < nq && !((qb2 >> (ra + 17)) & 1u)) {
