@@ -96,8 +96,34 @@ int host_pipeline(const void *h_in, size_t in_row, void *h_out, size_t out_row, 
     if (chunk_rows > n) chunk_rows = n;
     const size_t in_chunk = (size_t)chunk_rows * in_row, out_chunk = (size_t)chunk_rows * out_row;
     const size_t slot = ((in_chunk + out_chunk + 255) / 256) * 256;
-    rc = ensure_host_buffers(*S, 2 * slot, 2 * slot);
+    // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used directly:
+    // no staging copies on the host side.
+    auto is_pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct = is_pinned(h_in) && is_pinned(h_out);
+    rc = ensure_host_buffers(*S, direct ? 0 : 2 * slot, 2 * slot);
     if (rc) return rc;
+    if (direct) {
+        int64_t done = 0;
+        for (int k = 0; done < n; ++k) {
+            const int b = k & 1;
+            const int64_t rows = n - done < chunk_rows ? n - done : chunk_rows;
+            uint8_t *d_in = S->d_buf + b * slot, *d_out = d_in + in_chunk;
+            if (k >= 2) CUDA_TRY(cudaStreamSynchronize(S->streams[b]));   // the device slot is free again
+            CUDA_TRY(cudaMemcpyAsync(d_in, (const uint8_t *)h_in + (size_t)done * in_row, (size_t)rows * in_row,
+                                     cudaMemcpyHostToDevice, S->streams[b]));
+            CUDA_TRY(launch(*S, d_in, rows, d_out, S->streams[b]));
+            CUDA_TRY(cudaMemcpyAsync((uint8_t *)h_out + (size_t)done * out_row, d_out, (size_t)rows * out_row,
+                                     cudaMemcpyDeviceToHost, S->streams[b]));
+            done += rows;
+        }
+        CUDA_TRY(cudaStreamSynchronize(S->streams[0]));
+        CUDA_TRY(cudaStreamSynchronize(S->streams[1]));
+        return HOLDEM_OK;
+    }
     int64_t done = 0;
     int64_t pending_rows[2] = {0, 0};
     int64_t pending_off[2] = {0, 0};
@@ -397,7 +423,7 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
     if (n < 0 || (n > 0 && (!h_sit || !h_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     int rc = check_mode(mode);
     if (rc) return rc;
-    rc = host_pipeline(h_sit, 8, h_out, 64, n, 1 << 15,
+    rc = host_pipeline(h_sit, 8, h_out, 64, n, 1 << 14,
                        [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
                            return hp_dispatch(S, d_in, rows, mode, (uint32_t *)d_out, st);
                        });

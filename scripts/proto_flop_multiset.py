@@ -123,17 +123,41 @@ def flop_counts(hole, board):
         histA = {a: [sum(1 for c in Lns if Wc[(a, c)] == k3) for k3 in range(3)] for a in Ls}
         wnn = [wns[x] * wns[y] if x != y else wns[x] * (wns[x] - 1) // 2 for (x, y) in rank_pairs]
         hist_none = [sum(w for w, c in zip(wnn, clsr) if c == k3 and w) for k3 in range(3)]
+        hs_s = sum(1 for c in list(hole) + list(board) if c // 13 == s)
+        histA_rank = {a: {y: [sum(1 for c in Lns if rk[c] == y and Wc[(a, c)] == k3) for k3 in range(3)]
+                          for y in range(13)} for a in Ls}
+        our7nf = {}
+        for (i, j) in pairs:                      # our rank from ranks alone (no flush of ours): any suit assignment of
+            cards = list(hole) + list(board) + [U[i], U[j]]                       # those ranks without five of a suit
+            if max(sum(1 for c in cards if c // 13 == t) for t in range(4)) < 5:
+                our7nf.setdefault(pp_index(rk[i], rk[j]), int(our7[(i, j)]))
         for qtype, qlist in ((2, both), (1, one), (0, none)):
             k = b_s + qtype
             if k < 3:
                 continue
             need = 5 - k
-            for (i, j) in qlist:
-                o = int(our7[(i, j)])
-                qk = pp_index(rk[i], rk[j])
-                qbits = sum(1 << rk[t] for t in (i, j) if su[t] == s)
+            # lanes: (our, rank bits in s, rank pair index, weight, cards outside s, rank of the card outside s)
+            rank_lanes = qtype != 2 and hs_s + qtype < 5      # none of these runouts gives us a flush: merge them by rank
+            lanes = []
+            if rank_lanes and qtype == 1:
+                for a in Ls:
+                    for rz in range(13):
+                        if wns[rz]:
+                            qk = pp_index(min(rk[a], rz), max(rk[a], rz))
+                            lanes.append((our7nf[qk], 1 << rk[a], qk, wns[rz], [], rz))
+            elif rank_lanes:
+                for qk, (x, y) in enumerate(rank_pairs):
+                    if wnn[qk]:
+                        lanes.append((our7nf[qk], 0, qk, wnn[qk], [], None))
+            else:
+                for (i, j) in qlist:
+                    qbits = sum(1 << rk[t] for t in (i, j) if su[t] == s)
+                    lanes.append((int(our7[(i, j)]), qbits, pp_index(rk[i], rk[j]), 1,
+                                  [t for t in (i, j) if su[t] != s], None))
+            for (o, qbits, qk, wl, zs, rz) in lanes:
                 fq = bmask | qbits
-                zs = [t for t in (i, j) if su[t] != s]          # Q's cards outside the suit (at most one when need <= 1)
+                dl = [0, 0, 0]
+                dg = [0, 0, 0]
                 # -- both cards of P in s: card level, disjointness = rank bits in s
                 for (a, b) in both:
                     pbits = (1 << rk[a]) | (1 << rk[b])
@@ -144,10 +168,10 @@ def flop_counts(hole, board):
                     pk = pp_index(rk[a], rk[b])
                     Rn = T[qk, pk]
                     ct, cr = cls[(a, b)], clsr[pk]
-                    if o < Rf: lt[ct] += 1
-                    elif o > Rf: gt[ct] += 1
-                    if o < Rn: lt[cr] -= 1
-                    elif o > Rn: gt[cr] -= 1
+                    if o < Rf: dl[ct] += 1
+                    elif o > Rf: dg[ct] += 1
+                    if o < Rn: dl[cr] -= 1
+                    elif o > Rn: dg[cr] -= 1
                 if need <= 1:
                     assert len(zs) <= 1
                     for a in Ls:
@@ -155,36 +179,60 @@ def flop_counts(hole, board):
                             continue
                         n_items += 1
                         Rf = flush_rank(fq | (1 << rk[a]))
-                        hist = list(histA[a])
-                        for z in zs:
-                            hist[Wc[(a, z)]] -= 1
                         for c3 in range(3):
-                            if o < Rf: lt[c3] += hist[c3]
-                            elif o > Rf: gt[c3] += hist[c3]
+                            if o < Rf: dl[c3] += histA[a][c3]
+                            elif o > Rf: dg[c3] += histA[a][c3]
                         for y in range(13):
-                            w = wns[y] - sum(1 for z in zs if rk[z] == y)
-                            if w <= 0:
+                            if wns[y] <= 0:
                                 continue
                             n_items += 1
                             pk = pp_index(min(rk[a], y), max(rk[a], y))
                             Rn = T[qk, pk]
                             cr = clsr[pk]
-                            if o < Rn: lt[cr] -= w
-                            elif o > Rn: gt[cr] -= w
+                            if o < Rn: dl[cr] -= wns[y]
+                            elif o > Rn: dg[cr] -= wns[y]
                 if need == 0:
                     assert not zs
                     Rf = flush_rank(fq)
                     for c3 in range(3):
-                        if o < Rf: lt[c3] += hist_none[c3]
-                        elif o > Rf: gt[c3] += hist_none[c3]
+                        if o < Rf: dl[c3] += hist_none[c3]
+                        elif o > Rf: dg[c3] += hist_none[c3]
                     for pk in range(91):
                         if wnn[pk] <= 0:
                             continue
                         n_items += 1
                         Rn = T[qk, pk]
                         cr = clsr[pk]
-                        if o < Rn: lt[cr] -= wnn[pk]
-                        elif o > Rn: gt[cr] -= wnn[pk]
+                        if o < Rn: dl[cr] -= wnn[pk]
+                        elif o > Rn: dg[cr] -= wnn[pk]
+                for c3 in range(3):
+                    lt[c3] += wl * dl[c3]
+                    gt[c3] += wl * dg[c3]
+                # fix-up: the runout's own card(s) outside s were counted among the c of {a, c}
+                if need <= 1:
+                    for a in Ls:
+                        if (1 << rk[a]) & qbits:
+                            continue
+                        Rf = flush_rank(fq | (1 << rk[a]))
+                        if rz is not None:            # merged lane: all wl cards z of rank rz at once
+                            hz = histA_rank[a][rz]
+                            pk = pp_index(min(rk[a], rz), max(rk[a], rz))
+                            Rn = T[qk, pk]
+                            cr = clsr[pk]
+                            for c3 in range(3):
+                                if o < Rf: lt[c3] -= hz[c3]
+                                elif o > Rf: gt[c3] -= hz[c3]
+                            if o < Rn: lt[cr] += wl
+                            elif o > Rn: gt[cr] += wl
+                        for z in zs:
+                            ct = Wc[(a, z)]
+                            pk = pp_index(min(rk[a], rk[z]), max(rk[a], rk[z]))
+                            Rn = T[qk, pk]
+                            cr = clsr[pk]
+                            if o < Rf: lt[ct] -= 1
+                            elif o > Rf: gt[ct] -= 1
+                            if o < Rn: lt[cr] += 1
+                            elif o > Rn: gt[cr] += 1
     row = np.zeros(16, dtype=np.int64)
     row[0:3] = tot
     for i in range(3):

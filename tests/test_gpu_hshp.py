@@ -214,8 +214,9 @@ def test_hp_treys_1024_flops_vs_oracle(hb):
 
 
 def test_host_entry_chunked_pipeline_matches_device_entry(hb):
-    """The *_host entry points stream large batches through pinned staging in chunks (32,768 rows for HP, 2^20 for HS):
-    a batch spanning several chunks with a ragged tail must equal the device entry row for row, in both modes."""
+    """The *_host entry points stream large batches in chunks (16,384 rows for HP, 2^20 for HS), through the library's pinned
+    staging for pageable caller buffers and directly for page-locked ones: a batch spanning several chunks with a ragged
+    tail must equal the device entry row for row, in both modes and on both paths."""
     n = 2 * 32768 + 4097
     sit = hb.random_situations(n, seed=404)
     d_sit = torch.from_numpy(sit).cuda()
@@ -223,6 +224,11 @@ def test_host_entry_chunked_pipeline_matches_device_entry(hb):
         dev = _u32(hb.hand_potential_counts(d_sit, mode))
         host = hb.hand_potential_counts_host(sit, mode)
         assert host.dtype == np.uint32 and np.array_equal(host, dev), mode
+        pin_in = torch.empty((n, 8), dtype=torch.uint8, pin_memory=True)
+        pin_in.numpy()[:] = sit
+        pin_out = torch.zeros((n, 16), dtype=torch.int32, pin_memory=True)
+        got = hb.hand_potential_counts_host(pin_in.numpy(), mode, out=pin_out.numpy().view(np.uint32))
+        assert np.array_equal(got, dev), mode
     big = hb.random_situations((1 << 20) + 12345, seed=405, n_board=5)
     assert np.array_equal(hb.hand_strength_counts_host(big, "treys"),
                           _u32(hb.hand_strength_counts(torch.from_numpy(big).cuda(), "treys")))
