@@ -325,6 +325,8 @@ def main():
     achieved = evals_per_launch / (kernel_ms * 1e-3)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     issue_peak = 148 * 4 * sm_mhz * 1e6
+    issue_measured = {name: hb.int_issue_microbench(mix=mix, device=local_rank)[0]
+                      for mix, name in ((0, "compare_plus_predicated_mad"), (1, "fma_pipe_only"), (2, "alu_pipe_only"))}
     smem_peak = 148 * sm_mhz * 1e6
     wi = counters.get("warp_instructions_per_situation")
     wf = counters.get("shared_wavefronts_per_situation")
@@ -350,6 +352,8 @@ def main():
             "achieved_warp_instr_per_sec": wi * n_local / (kernel_ms * 1e-3),
             "peak_warp_instr_per_sec": issue_peak,
             "frac": wi * n_local / (kernel_ms * 1e-3) / issue_peak,
+            "measured_issue_rates_warp_instr_per_sec": issue_measured,
+            "frac_of_measured_mixed_issue_rate": wi * n_local / (kernel_ms * 1e-3) / issue_measured["compare_plus_predicated_mad"],
             "note": "warp instructions per situation = smsp__inst_executed.sum / 65,536 from the committed ncu capture "
                     "(profiles/hot_kernel_counters.json), rate from this run's CUDA-event time; peak = 148 SMs x 4 schedulers "
                     "x the SM clock sampled during this run"},

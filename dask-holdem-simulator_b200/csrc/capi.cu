@@ -459,4 +459,29 @@ int holdem_microbench_smem_gather(int table_bytes, int iters, int pattern, int b
     return HOLDEM_OK;
 }
 
+int holdem_microbench_int_issue(int iters, int mix, int blocks_per_sm, int threads, float *elapsed_ms,
+                                double *warp_instructions, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (iters < 1 || mix < 0 || mix > 2 || threads < 32 || threads > 1024 || (threads & 31) || blocks_per_sm < 1 ||
+        !elapsed_ms || !warp_instructions)
+        return fail(HOLDEM_ERR_BAD_ARG, "bad micro-benchmark arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = S->sms * blocks_per_sm;
+    CUDA_TRY(launch_int_issue(iters, mix, blocks, threads, st));  // warm-up
+    CUDA_TRY(cudaEventRecord(e0, st));
+    CUDA_TRY(launch_int_issue(iters, mix, blocks, threads, st));
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+    *warp_instructions = 16.0 * (double)iters * (double)blocks * (double)(threads / 32);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HOLDEM_OK;
+}
+
 }  // extern "C"

@@ -406,4 +406,54 @@ cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int bloc
     return cudaGetLastError();
 }
 
+// =====================================================================================================================
+// Integer issue micro-benchmark: eight independent chains per thread, each step one compare (ALU pipe) and one predicated
+// multiply-add (FMA pipe) -- the instruction pair the HP kernels are made of.  mix 0: compare + multiply-add pairs;
+// mix 1: multiply-adds only (FMA pipe); mix 2: logic ops only (ALU pipe).  Returns nothing; timed by the caller.
+// =====================================================================================================================
+__global__ void __launch_bounds__(1024, 1)
+int_issue_kernel(int iters, int mix, uint32_t one, uint32_t *__restrict__ sink) {
+    uint32_t a[8], t = threadIdx.x * 2654435761u + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = t + k * 977u;
+    if (mix == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p mad.lo.u32 %0, %1, %2, %0;\n\t}"
+                             : "+r"(a[k]) : "r"(a[(k + 1) & 7]), "r"(one));
+        }
+    } else if (mix == 1) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(one), "r"(t));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(one), "r"(t));
+            }
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[k]) : "r"(t));
+                asm volatile("and.b32 %0, %0, %1;" : "+r"(a[k]) : "r"(~one));
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= a[k];
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
+cudaError_t launch_int_issue(int iters, int mix, int blocks, int threads, cudaStream_t st) {
+    static uint32_t *sink = nullptr;
+    if (!sink) {
+        cudaError_t e = cudaMalloc(&sink, 4);
+        if (e != cudaSuccess) return e;
+    }
+    int_issue_kernel<<<blocks, threads, 0, st>>>(iters, mix, 1u, sink);
+    return cudaGetLastError();
+}
+
 }  // namespace holdem

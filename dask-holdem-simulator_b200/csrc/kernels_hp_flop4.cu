@@ -1,6 +1,6 @@
 // kernels_hp_flop4.cu -- flop hand strength + hand potential in Treys mode, rank-multiset formulation ("v4").
-// One persistent CTA of 1024 threads per SM = four independent groups of 256 threads, each working on its own situation
-// (named barriers per group): the groups share the static tables and hide each other's table-build latencies.  sm_100a only.
+// One persistent CTA of 960 threads per SM = six independent groups of 160 threads, each working on its own situation
+// (named barriers per group): the groups share the static tables and hide each other's latencies.  sm_100a only.
 //
 // What is counted (HandCalculations.py:178-226 with rank = Treys evaluate, SURVEY.md section 8a "canonical" loop):
 //     HP[cls(P)][cmp(our7[Q], R(P,Q))] += 1     for every opponent holding P and runout Q, P and Q disjoint pairs of the
@@ -18,14 +18,18 @@
 //                        share our7, so this is 91 merged runouts (+ one entry per runout that makes OUR flush) x 91 rank
 //                        pairs per situation;
 //                     +  FLUSH part: for every (P,Q) such that board+Q has k >= 3 cards of a suit s and P holds >= 5-k
-//                        cards of s (about 8 K pairs on a rainbow flop, 40 K two-tone, 140-210 K monotone):
+//                        cards of s (about 8 K pairs on a rainbow flop, 40 K two-tone, 140-210 K monotone; 7 K / 17 K /
+//                        65 K items after the mergers below):
 //                            + [cls(P)]  x cmp(our7[Q], flush[ranks of board+Q+P in s])
 //                            - [clsr(P)] x cmp(our7[Q], NF(board + ranks(Q) + ranks(P)))        (undo the generic term)
 //                        Holdings with BOTH cards in s are visited one by one.  Holdings {a in s, c not in s} share the
 //                        flush rank of a, so per a they cost one compare against the class histogram of {a,c} over all c
 //                        plus one rank-level undo step per rank of c; holdings without a card of s (only when board+Q is
-//                        already a flush) cost one compare plus one undo step per rank pair.  A runout card outside s
-//                        that coincides with c is taken out again by a short per-lane fix-up loop.
+//                        already a flush) cost one compare plus one undo step per rank pair.  Runouts get the same
+//                        treatment from their side: a runout card outside s matters through its rank only, so those
+//                        runouts are merged into weighted lanes (unless they complete OUR flush, which is true for all of
+//                        them or none); a runout card outside s that coincides with c is taken out again by a short
+//                        per-lane fix-up loop.
 //   Our own flushes need no special case: our7[Q] is evaluated per card pair Q.
 //
 // Shared memory (~150 KB per CTA): static flush[8192] u16 (index bits folded, m ^ m >> 6, so that the bank depends on ten

@@ -17,6 +17,8 @@ cudaError_t launch_category_batch(const uint8_t *cards, int n_cards, int row_str
                                   int sms, cudaStream_t st);
 cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st);
 cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int blocks, int threads, cudaStream_t st);
+// 16 warp instructions per thread per iteration; mix 0 = compare + predicated multiply-add, 1 = FMA pipe only, 2 = ALU pipe only
+cudaError_t launch_int_issue(int iters, int mix, int blocks, int threads, cudaStream_t st);
 
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                             cudaStream_t st);

@@ -10,4 +10,5 @@ from .encoding import (pack_situations, random_situations, path_from_str, str_fr
                        treys_from_path, path_from_treys, treys_from_str, path_from_poker_card,
                        path_from_rank_major, rank_major_from_path)
 from .sharded import shard_bounds, hand_potential_counts_sharded  # noqa: F401
-from . import policy, table  # noqa: F401,E402
+from .extensions import hand_strength_vs_n, preflop_hand_strength, monte_carlo_equity  # noqa: F401
+from . import policy, table, extensions  # noqa: F401,E402

@@ -20,7 +20,7 @@ __all__ = [
     "MODE_TREYS", "MODE_REFERENCE", "mode_id", "evaluate", "category", "hand_strength_counts",
     "hand_potential_counts", "flop_phase_cycles", "exhaustive7", "hs_from_counts", "potentials_from_counts",
     "normalised_potentials", "ehs_from_counts", "evaluate_host", "category_host", "hand_strength_counts_host",
-    "hand_potential_counts_host", "smem_gather_microbench", "EVALS_PER_FLOP_SITUATION",
+    "hand_potential_counts_host", "smem_gather_microbench", "int_issue_microbench", "EVALS_PER_FLOP_SITUATION",
 ]
 
 # algorithmic evaluations per situation
@@ -242,3 +242,13 @@ def smem_gather_microbench(table_bytes=131072, iters=2048, pattern=0, blocks_per
     _lib.check(lib.holdem_microbench_smem_gather(table_bytes, iters, pattern, blocks_per_sm, threads,
                                                  ctypes.byref(ms), ctypes.byref(lookups), None))
     return lookups.value / (ms.value * 1e-3), ms.value
+
+
+def int_issue_microbench(mix=0, iters=4096, blocks_per_sm=1, threads=1024, device=None):
+    """Measured integer instruction issue rate (warp instructions/s) -- the issue roofline denominator.
+    mix 0: compare + predicated multiply-add pairs (ALU + FMA pipes), 1: FMA pipe only, 2: ALU pipe only."""
+    lib = _host_enter(device)
+    ms = ctypes.c_float(0)
+    n = ctypes.c_double(0)
+    _lib.check(lib.holdem_microbench_int_issue(iters, mix, blocks_per_sm, threads, ctypes.byref(ms), ctypes.byref(n), None))
+    return n.value / (ms.value * 1e-3), ms.value

@@ -137,6 +137,12 @@ int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out
 int holdem_microbench_smem_gather(int table_bytes, int iters, int pattern, int blocks_per_sm, int threads,
                                   float *elapsed_ms, double *lookups, void *stream);
 
+/* Integer issue-rate micro-benchmark: every thread runs eight independent chains of 16 instructions per iteration.
+ * mix 0: compare (ALU pipe) + predicated multiply-add (FMA pipe) pairs, the instruction pair of the HP kernels;
+ * mix 1: multiply-adds only; mix 2: logic ops only.  Returns elapsed device time and the warp instructions issued. */
+int holdem_microbench_int_issue(int iters, int mix, int blocks_per_sm, int threads, float *elapsed_ms,
+                                double *warp_instructions, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
