@@ -205,6 +205,10 @@ int holdem_init(int device) {
     S.T.board_opp5 = reinterpret_cast<const uint16_t *>(S.image + im.off_board_opp5);
     S.T.own_our7 = reinterpret_cast<const uint16_t *>(S.image + im.off_own_our7);
     S.T.own_rank5 = reinterpret_cast<const uint16_t *>(S.image + im.off_own_rank5);
+    S.T.board4_t = reinterpret_cast<const uint16_t *>(S.image + im.off_board4_t);
+    S.T.board4_opp6 = reinterpret_cast<const uint16_t *>(S.image + im.off_board4_opp6);
+    S.T.own6_our7 = reinterpret_cast<const uint16_t *>(S.image + im.off_own6_our7);
+    S.T.own6_rank6 = reinterpret_cast<const uint16_t *>(S.image + im.off_own6_rank6);
     S.T.n_flop_tasks = im.n_tasks;
     S.T.turn_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_hdr);
     S.T.turn_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_turn_lanes);
@@ -370,7 +374,9 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     cudaError_t e = (impl == 2 || impl == 3) ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st)
                                              : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, st);
     if (e != cudaSuccess) return e;
-    e = launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st);
+    static const int timpl = getenv("HOLDEM_TURN_KERNEL") ? atoi(getenv("HOLDEM_TURN_KERNEL")) : 4;
+    e = timpl == 3 ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
+                   : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
     return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
 }
@@ -404,6 +410,17 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, nullptr, (cudaStream_t)stream));
     else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, flag, variant, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (variant != 3 && variant != 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown turn kernel variant %d", variant);
+    if (variant == 4) CUDA_TRY(launch_hp_turn_treys_v4(S->T, d_sit, n, d_out, S->sms, nullptr, (cudaStream_t)stream));
+    else CUDA_TRY(launch_hp_turn_treys(S->T, d_sit, n, d_out, S->sms, nullptr, (cudaStream_t)stream));
     return HOLDEM_OK;
 }
 

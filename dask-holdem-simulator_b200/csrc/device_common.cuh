@@ -45,6 +45,10 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint16_t *board_opp5;       // [455][96]
     const uint16_t *own_our7;         // [6188][96]
     const uint16_t *own_rank5;        // [6188]
+    const uint16_t *board4_t;         // [1820][91][16] four-card boards (turn kernel)
+    const uint16_t *board4_opp6;      // [1820][96]
+    const uint16_t *own6_our7;        // [18564][16]
+    const uint16_t *own6_rank6;       // [18564]
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

@@ -55,7 +55,7 @@ hp_turn_treys_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__res
                      const int *__restrict__ run_flag, uint32_t one) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     TurnSmem &S = *reinterpret_cast<TurnSmem *>(smem_raw);
-    if ((*run_flag & 1) == 0) return;   // the flop kernel saw no 4-card boards
+    if (run_flag != nullptr && (*run_flag & 1) == 0) return;   // the flop kernel saw no 4-card boards
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(T.flush);

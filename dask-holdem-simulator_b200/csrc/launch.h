@@ -39,6 +39,10 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, cudaStream_t st);
 
+// Rank-multiset turn kernel (kernels_hp_turn4.cu): same contract as launch_hp_turn_treys, bit-identical counts, the default.
+cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
+                                    const int *run_flag, cudaStream_t st);
+
 // HOLDEM_MODE_REFERENCE, all streets: 4-set walk for the regular runouts + arithmetic ranking of the irregular ones.
 cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
 

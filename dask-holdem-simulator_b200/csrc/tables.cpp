@@ -350,6 +350,43 @@ struct Builder {
                                     t.own_our7[(size_t)m5 * 96 + q] = rank_of(r, 7, 2);
                                 }
                             }
+            // ---- four-card boards (turn) ---------------------------------------------------------------------------------
+            t.board4_t.assign((size_t)kBoard4Multisets * kBoard4TRow, 0);
+            t.board4_opp6.assign((size_t)kBoard4Multisets * 96, 0);
+            for (int r3 = 0; r3 < 13; ++r3)
+                for (int r2 = 0; r2 <= r3; ++r2)
+                    for (int r1 = 0; r1 <= r2; ++r1)
+                        for (int r0 = 0; r0 <= r1; ++r0) {
+                            const int b4 = r0 + (r1 + 1) * r1 / 2 + (r2 + 2) * (r2 + 1) * r2 / 6 +
+                                           (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24;
+                            for (int p = 0; p < 91; ++p) {
+                                for (int rq = 0; rq < 13; ++rq) {
+                                    const int r[7] = {r0, r1, r2, r3, rq, px[p], py[p]};
+                                    t.board4_t[(size_t)b4 * kBoard4TRow + p * 16 + rq] = rank_of(r, 7, 2);
+                                }
+                                const int r6[6] = {r0, r1, r2, r3, px[p], py[p]};
+                                t.board4_opp6[(size_t)b4 * 96 + p] = rank_of(r6, 6, 1);
+                            }
+                        }
+            t.own6_our7.assign((size_t)kOwn6Multisets * 16, 0);
+            t.own6_rank6.assign(kOwn6Multisets + 4, 0);
+            for (int r5 = 0; r5 < 13; ++r5)
+                for (int r4 = 0; r4 <= r5; ++r4)
+                    for (int r3 = 0; r3 <= r4; ++r3)
+                        for (int r2 = 0; r2 <= r3; ++r2)
+                            for (int r1 = 0; r1 <= r2; ++r1)
+                                for (int r0 = 0; r0 <= r1; ++r0) {
+                                    const int m6 = r0 + (r1 + 1) * r1 / 2 + (r2 + 2) * (r2 + 1) * r2 / 6 +
+                                                   (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24 +
+                                                   (r4 + 4) * (r4 + 3) * (r4 + 2) * (r4 + 1) * r4 / 120 +
+                                                   (r5 + 5) * (r5 + 4) * (r5 + 3) * (r5 + 2) * (r5 + 1) * r5 / 720;
+                                    const int r6[6] = {r0, r1, r2, r3, r4, r5};
+                                    t.own6_rank6[m6] = rank_of(r6, 6, 1);
+                                    for (int rq = 0; rq < 13; ++rq) {
+                                        const int r[7] = {r0, r1, r2, r3, r4, r5, rq};
+                                        t.own6_our7[(size_t)m6 * 16 + rq] = rank_of(r, 7, 2);
+                                    }
+                                }
         }
         ok = true;
     }
@@ -468,6 +505,13 @@ int selftest(char *msg, int msg_len) {
         if (t.own_rank5[m5] != t.nf[0].lookup(k5)) return fail("own_rank5 entry");
         const int qq = 10 * 11 / 2 + 10;
         if (t.own_our7[(size_t)m5 * 96 + qq] != t.nf[2].lookup(k5 + 2 * kRankKey[10])) return fail("own_our7 entry");
+        // turn tables: board 2 3 4 5 (b4 = 0 + 1 + 4 + 15), river 6 (rank 4), holding (A,A): the six-high straight again
+        const int b4 = 0 + (1 + 1) * 1 / 2 + (2 + 2) * (2 + 1) * 2 / 6 + (3 + 3) * (3 + 2) * (3 + 1) * 3 / 24;
+        if (t.board4_t.size() != (size_t)kBoard4Multisets * kBoard4TRow || t.own6_our7.size() != (size_t)kOwn6Multisets * 16)
+            return fail("board4 table sizes");
+        if (t.board4_t[(size_t)b4 * kBoard4TRow + p * 16 + 4] != 1608) return fail("board4_t entry");
+        if (t.board4_opp6[(size_t)b4 * 96 + p] != t.nf[1].lookup(kRankKey[0] + kRankKey[1] + kRankKey[2] + kRankKey[3] + 2 * kRankKey[12]))
+            return fail("board4_opp6 entry");
     }
     if (msg && msg_len > 0) msg[0] = 0;
     return 0;
@@ -492,6 +536,10 @@ TableImage make_image(const Tables &t) {
     im.off_board_opp5 = append(t.board_opp5.data(), t.board_opp5.size() * 2);
     im.off_own_our7 = append(t.own_our7.data(), t.own_our7.size() * 2);
     im.off_own_rank5 = append(t.own_rank5.data(), t.own_rank5.size() * 2);
+    im.off_board4_t = append(t.board4_t.data(), t.board4_t.size() * 2);
+    im.off_board4_opp6 = append(t.board4_opp6.data(), t.board4_opp6.size() * 2);
+    im.off_own6_our7 = append(t.own6_our7.data(), t.own6_our7.size() * 2);
+    im.off_own6_rank6 = append(t.own6_rank6.data(), t.own6_rank6.size() * 2);
     im.n_tasks = (uint32_t)t.flop_task_hdr.size();
     im.off_turn_hdr = append(t.turn_task_hdr.data(), t.turn_task_hdr.size() * 4);
     im.off_turn_lanes = append(t.turn_lanes.data(), t.turn_lanes.size() * 4);

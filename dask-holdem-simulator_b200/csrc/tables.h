@@ -23,6 +23,9 @@ constexpr int kBoardMultisets = 455;     // C(15,3)
 constexpr int kOwnMultisets = 6188;       // C(17,5)
 constexpr int kBoardTPitch = 94;          // u16 per row of board_t
 constexpr int kBoardTRow = 91 * kBoardTPitch + 6;   // u16 per board (17,120 bytes: a multiple of 16)
+constexpr int kBoard4Multisets = 1820;    // C(16,4)
+constexpr int kOwn6Multisets = 18564;     // C(18,6)
+constexpr int kBoard4TRow = 91 * 16;      // u16 per four-card board (2,912 bytes)
 constexpr int kMaxPairs = 1326;  // C(52,2), colex order: pair p of (i<j) has p = j(j-1)/2 + i
 
 // Hash-displace perfect hash over the additive keys of one hand size:
@@ -79,6 +82,12 @@ struct Tables {
     //   own_our7[m5][96]               non-flush 7-card rank of hole + board + rank pair, m5 = five-rank multiset index
     //   own_rank5[m5]                  non-flush 5-card rank of hole + board
     std::vector<uint16_t> board_t, board_opp5, own_our7, own_rank5;
+    // The same for four-card boards (turn kernel, kernels_hp_turn4.cu), b4 = four-rank multiset index (nf4 numbering), m6 =
+    // six-rank multiset index:
+    //   board4_t[b4][91][16]   non-flush 7-card rank of board + river rank (column) + rank pair (row)
+    //   board4_opp6[b4][96]    non-flush 6-card rank of board + rank pair
+    //   own6_our7[m6][16]      non-flush 7-card rank of hole + board + river rank;  own6_rank6[m6]: of hole + board
+    std::vector<uint16_t> board4_t, board4_opp6, own6_our7, own6_rank6;
     // Statistics kept for selftest().
     int n_keys[3] = {0, 0, 0};
 };
@@ -91,6 +100,7 @@ struct TableImage {
     std::vector<uint8_t> bytes;
     uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0, off_idx4 = 0, off_key4 = 0;
     uint32_t off_board_t = 0, off_board_opp5 = 0, off_own_our7 = 0, off_own_rank5 = 0;
+    uint32_t off_board4_t = 0, off_board4_opp6 = 0, off_own6_our7 = 0, off_own6_rank6 = 0;
     uint32_t n_tasks = 0;
     uint32_t off_turn_hdr = 0, off_turn_lanes = 0, off_nf3 = 0, n_turn_tasks = 0;
     uint32_t off_ref_hdr[2] = {0, 0}, off_ref_lanes[2] = {0, 0}, n_ref_tasks[2] = {0, 0};

@@ -47,6 +47,7 @@ SYMBOLS = {
     "holdem_hp_batch_direct": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_flop_variant": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_flop_phase_cycles": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "holdem_hp_turn_variant": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_microbench_smem_gather": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float),
                                            ctypes.POINTER(ctypes.c_double), _vp]),
     "holdem_microbench_int_issue": (_i, [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_float),

@@ -92,12 +92,13 @@ def hand_strength_counts(sit: torch.Tensor, mode="treys") -> torch.Tensor:
 
 
 def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = None,
-                          direct: bool = False, flop_variant: int = None) -> torch.Tensor:
+                          direct: bool = False, flop_variant: int = None, turn_variant: int = None) -> torch.Tensor:
     """HS + HP counts per situation: int32 [N,16] = ahead tied behind | HP[3][3] | HPTotal[3] | n_board.
     `out` may be a [N,16] int32 view into a larger buffer (e.g. this rank's slice of an all-gather buffer).
     direct=True forces the plain-enumeration kernel (the independent second implementation).  flop_variant (treys mode,
     flop rows only; 4 = rank-multiset kernel, 3 / 2 = the 4-set kernels) runs one named implementation of the flop kernel
-    for A/B measurements; rows of other streets are then left as they are in `out`."""
+    for A/B measurements; rows of other streets are then left as they are in `out`.  turn_variant (4 = rank-multiset
+    kernel, 3 = 3-set walk) does the same for turn rows."""
     _require_cuda(sit, "sit", torch.uint8, 8)
     if out is None:
         out = torch.empty((sit.shape[0], HP_ROW), dtype=torch.int32, device=sit.device)
@@ -106,6 +107,11 @@ def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = N
         if out.shape[0] != sit.shape[0] or out.device != sit.device:
             raise ValueError("out must be [N,16] on the same device as sit")
     lib, st = _enter(sit)
+    if turn_variant is not None:
+        if mode_id(mode) != MODE_TREYS or direct or flop_variant is not None:
+            raise ValueError("turn_variant applies to mode='treys' alone")
+        _lib.check(lib.holdem_hp_turn_variant(sit.data_ptr(), sit.shape[0], int(turn_variant), out.data_ptr(), st))
+        return out
     if flop_variant is not None:
         if mode_id(mode) != MODE_TREYS or direct:
             raise ValueError("flop_variant applies to mode='treys' without direct=True")

@@ -125,6 +125,10 @@ int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *
  * 2 = the earlier warp-per-pair 4-set kernel.  Rows with 4- or 5-card boards are left untouched. */
 int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
+/* The same for Treys-mode turn rows (four board cards): 4 = rank-multiset kernel (production), 3 = deduplicating 3-set walk.
+ * Rows of other streets are left untouched. */
+int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
+
 /* The production flop kernel with its phase clocks switched on: d_cycles uint64[4] receives the SM cycles each situation
  * group spent in (0) list + hash-table phase, (1) pair table + T expansion, (2) holding descriptors, (3) generic + flush
  * tasks, summed over all situations.  Profiling aid for bench.py / DESIGN.md; results in d_out are the normal rows. */

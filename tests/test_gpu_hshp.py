@@ -295,3 +295,26 @@ def test_hp_flop_variants_agree_and_match_oracle(hb, oracle):
     assert torch.equal(v4, v3)
     with pytest.raises(hb.HoldemError):
         hb.hand_potential_counts(d_sit, "treys", flop_variant=7)
+
+
+def test_hp_turn_variants_agree_and_match_oracle(hb, oracle):
+    """Turn rows: the rank-multiset kernel (production), the 3-set walk and the plain enumeration return identical rows;
+    suit-texture cases (four / three to a flush on board, two suits twice, hole cards in and out of the suit, paired and
+    tripled boards) and random deals are checked against the CPU oracle."""
+    cases = [([0, 1], [2, 3, 4, 5]), ([13, 26], [2, 3, 4, 5]), ([12, 11], [2, 3, 4, 18]), ([25, 38], [2, 3, 4, 18]),
+             ([0, 13], [2, 3, 15, 16]), ([12, 25], [38, 51, 0, 13]), ([5, 18], [31, 44, 6, 19]), ([7, 8], [9, 10, 24, 37]),
+             ([39, 40], [41, 42, 43, 0]), ([39, 1], [41, 42, 43, 44]), ([50, 51], [49, 48, 47, 46]), ([14, 1], [31, 32, 33, 20]),
+             ([0, 12], [13, 26, 39, 1]), ([21, 47], [8, 34, 9, 35])]
+    sit = np.concatenate([hb.pack_situations([c[0] for c in cases], [c[1] for c in cases]),
+                          hb.random_situations(400, seed=821, n_board=4)])
+    want = oracle.hp_batch(sit, "treys")
+    d_sit = torch.from_numpy(sit).cuda()
+    for variant in (4, 3):
+        got = _u32(hb.hand_potential_counts(d_sit, "treys", turn_variant=variant))
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (variant, bad[:5], sit[bad[:5]], got[bad[:5]], want[bad[:5]])
+    assert np.array_equal(_u32(hb.hand_potential_counts(d_sit, "treys")), want)
+    big = hb.random_situations(65536, seed=822, n_board=4)
+    d_big = torch.from_numpy(big).cuda()
+    assert torch.equal(hb.hand_potential_counts(d_big, "treys", turn_variant=4),
+                       hb.hand_potential_counts(d_big, "treys", turn_variant=3))
