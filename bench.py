@@ -209,14 +209,20 @@ def main():
     sit_all = hb.random_situations(n_global, SEED)           # same on every rank (seeded)
     sit_np = np.ascontiguousarray(sit_all[rank * n_local:(rank + 1) * n_local])
     d_sit = torch.from_numpy(sit_np).to(dev)
+    d_sit_all = torch.from_numpy(sit_all).to(dev) if world > 1 else d_sit
     full = torch.zeros((n_global, hb.HP_ROW), dtype=torch.int32, device=dev)
     mine = full[rank * n_local:(rank + 1) * n_local]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    from holdem_b200 import sharded
 
-    def step():
-        hb.hand_potential_counts(d_sit, "treys", out=mine)
-        if world > 1:
-            dist.all_gather_into_tensor(full, mine)
+    def step(fused=None):
+        """One pass of the hot path over the global batch; every rank ends up with all rows.  N > 1: each rank computes its
+        contiguous block and the kernels store the rows into every rank's symmetric-memory buffer over NVLink (compute and
+        all-gather fused in one launch); falls back to an in-place NCCL all-gather where symmetric memory is unavailable."""
+        if world == 1:
+            hb.hand_potential_counts(d_sit, "treys", out=mine)
+            return full
+        return hb.hand_potential_counts_sharded(d_sit_all, "treys", fused=fused)
 
     def barrier():
         if world > 1:
@@ -226,6 +232,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    fused_used = world > 1 and sharded._SYMM_ERROR is None
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -236,7 +243,7 @@ def main():
     for e0, e1 in evs:
         flush_buf.fill_(1)          # L2 flush between timed iterations (not timed)
         e0.record()
-        step()
+        result = step()
         e1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -247,6 +254,22 @@ def main():
         dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
     value = n_global / (ms_per_step * 1e-3)
+    if result is not full:
+        full.copy_(result)
+    allgather_value = None
+    if fused_used:      # the same step with the NCCL all-gather instead of the kernels' own peer stores, for comparison
+        for _ in range(3):
+            step(fused=False)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            step(fused=False)
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allgather_value = n_global / (float(t.item()) / args.steps * 1e-3)
 
     # ---- kernel-only time of the dominant kernel (same launches, no collective) for the roofline ----------------------------
     k_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -474,7 +497,10 @@ def main():
         "config": {"workload": "configs[2]: 65,536 random flop situations per GPU, HS + full HP enumeration, mode=treys "
                                "(numpy default_rng(20251019) deals)",
                    "global_situations": n_global, "parallelism": f"situation-sharded x{world}"
-                   + (", in-place NCCL all-gather of the [N,16] u32 result" if world > 1 else ""),
+                   + ("" if world == 1 else (", result rows stored by the kernels into every rank's symmetric-memory buffer "
+                                             "over NVLink (fused compute + all-gather, two symmetric-memory barriers)"
+                                             if fused_used else ", in-place NCCL all-gather of the [N,16] u32 result")),
+                   "nccl_allgather_path_value": allgather_value,
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); inputs 0.5 MiB/GPU"},
         "hand_evals_per_sec_per_gpu": value * EVALS_PER_SITUATION / world,
         "wall_s_timed_region": t_wall,

@@ -199,8 +199,6 @@ int holdem_init(int device) {
     S.T.flop_task_hdr = reinterpret_cast<const uint32_t *>(S.image + im.off_task_hdr);
     S.T.flop_lanes = reinterpret_cast<const uint32_t *>(S.image + im.off_lanes);
     S.T.nf4_ranks = reinterpret_cast<const uint16_t *>(S.image + im.off_nf4);
-    S.T.idx4 = reinterpret_cast<const uint16_t *>(S.image + im.off_idx4);
-    S.T.key4 = reinterpret_cast<const uint32_t *>(S.image + im.off_key4);
     S.T.board_t = reinterpret_cast<const uint16_t *>(S.image + im.off_board_t);
     S.T.board_opp5 = reinterpret_cast<const uint16_t *>(S.image + im.off_board_opp5);
     S.T.own_our7 = reinterpret_cast<const uint16_t *>(S.image + im.off_own_our7);
@@ -366,19 +364,29 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
 // Treys mode: the deduplicating flop kernel takes every 3-card-board row and flags what else it saw; turn rows go to the
 // deduplicating turn kernel, river rows (HS only) to the plain-enumeration kernel.  Both exit at once when not needed.  Reference mode: plain enumeration only.
 static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out,
-                               cudaStream_t st) {
-    if (mode == HOLDEM_MODE_REFERENCE) return launch_hp_ref(S.T, d_sit, n, d_out, S.sms, st);
+                               cudaStream_t st, const PeerOut &peers = PeerOut{}) {
+    if (mode == HOLDEM_MODE_REFERENCE) {
+        cudaError_t e = launch_hp_ref(S.T, d_sit, n, d_out, S.sms, st);
+        if (e != cudaSuccess) return e;
+        return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, nullptr, st);
+    }
     int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    // HOLDEM_FLOP_KERNEL=3 / 2 select the earlier 4-set kernels (kept for A/B measurements and cross-checks)
+    // HOLDEM_FLOP_KERNEL=3 / 2 and HOLDEM_TURN_KERNEL=3 select the earlier kernels (kept for A/B measurements and cross-checks)
     static const int impl = getenv("HOLDEM_FLOP_KERNEL") ? atoi(getenv("HOLDEM_FLOP_KERNEL")) : 4;
-    cudaError_t e = (impl == 2 || impl == 3) ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st)
-                                             : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, st);
-    if (e != cudaSuccess) return e;
     static const int timpl = getenv("HOLDEM_TURN_KERNEL") ? atoi(getenv("HOLDEM_TURN_KERNEL")) : 4;
-    e = timpl == 3 ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
-                   : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, st);
+    const bool old_flop = impl == 2 || impl == 3, old_turn = timpl == 3;
+    const bool fused = !old_flop && !old_turn;          // the production kernels store their rows into the peers themselves
+    const PeerOut none{};
+    cudaError_t e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st)
+                             : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st);
     if (e != cudaSuccess) return e;
-    return launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
+    e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
+                 : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st);
+    if (e != cudaSuccess) return e;
+    e = launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
+    if (e != cudaSuccess) return e;
+    // river rows only (exits at once when there are none); every row when an earlier kernel was selected
+    return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, fused ? flag : nullptr, st);
 }
 
 int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream) {
@@ -388,6 +396,24 @@ int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, 
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if ((rc = check_mode(mode))) return rc;
     CUDA_TRY(hp_dispatch(*S, d_sit, n, mode, d_out, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_batch_peers(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *const *peer_out, int n_peers,
+                          void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !peer_out)) return fail(HOLDEM_ERR_BAD_ARG, "0..8 peer buffers");
+    if ((rc = check_mode(mode))) return rc;
+    PeerOut peers{};
+    peers.n = n_peers;
+    for (int k = 0; k < n_peers; ++k) {
+        if (!peer_out[k]) return fail(HOLDEM_ERR_BAD_ARG, "null peer buffer %d", k);
+        peers.p[k] = (uint32_t *)peer_out[k];
+    }
+    CUDA_TRY(hp_dispatch(*S, d_sit, n, mode, d_out, (cudaStream_t)stream, peers));
     return HOLDEM_OK;
 }
 
@@ -408,7 +434,7 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if (variant < 2 || variant > 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
     int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, nullptr, (cudaStream_t)stream));
+    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, nullptr, PeerOut{}, (cudaStream_t)stream));
     else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, flag, variant, (cudaStream_t)stream));
     return HOLDEM_OK;
 }
@@ -419,7 +445,7 @@ int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if (variant != 3 && variant != 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown turn kernel variant %d", variant);
-    if (variant == 4) CUDA_TRY(launch_hp_turn_treys_v4(S->T, d_sit, n, d_out, S->sms, nullptr, (cudaStream_t)stream));
+    if (variant == 4) CUDA_TRY(launch_hp_turn_treys_v4(S->T, d_sit, n, d_out, S->sms, nullptr, PeerOut{}, (cudaStream_t)stream));
     else CUDA_TRY(launch_hp_turn_treys(S->T, d_sit, n, d_out, S->sms, nullptr, (cudaStream_t)stream));
     return HOLDEM_OK;
 }
@@ -431,7 +457,7 @@ int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out
     if (n < 0 || !d_cycles || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     CUDA_TRY(cudaMemsetAsync(d_cycles, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
-    CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (unsigned long long *)d_cycles,
+    CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (unsigned long long *)d_cycles, PeerOut{},
                                      (cudaStream_t)stream));
     return HOLDEM_OK;
 }

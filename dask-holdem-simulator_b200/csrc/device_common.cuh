@@ -39,8 +39,6 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint32_t *ref_task_hdr[2];  // reference-mode kernel, 46 / 45 unseen positions (47 uses the flop list)
     const uint32_t *ref_lanes[2];
     uint32_t n_ref_tasks[2];
-    const uint16_t *idx4;             // [91*91] two rank pairs -> index into the 1820 four-rank multisets
-    const uint32_t *key4;             // [1820] additive key of each four-rank multiset
     const uint16_t *board_t;          // [455][8560] non-flush rank of board + rank pair + rank pair (tables.h)
     const uint16_t *board_opp5;       // [455][96]
     const uint16_t *own_our7;         // [6188][96]

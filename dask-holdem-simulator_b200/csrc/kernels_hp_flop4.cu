@@ -112,7 +112,7 @@ __device__ __forceinline__ void group_sync(uint32_t gid) { group_sync_n<kGroupTh
 
 __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                        int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one) {
+                        int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Flop4Smem &S = *reinterpret_cast<Flop4Smem *>(smem_raw);
     const uint32_t gid = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
@@ -176,7 +176,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         ok = ok && __popcll(known) == 5;
         if (!ok) {
-            if (tid < 16) out[idx * 16 + tid] = 0xFFFFFFFFu;
+            if (tid < 16) {
+                out[idx * 16 + tid] = 0xFFFFFFFFu;
+                for (int k = 0; k < peers.n; ++k) peers.p[k][idx * 16 + tid] = 0xFFFFFFFFu;
+            }
             continue;
         }
         if (tid < 12) G.cnt[tid] = 0;
@@ -619,6 +622,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             } else if (tid < 15) v = G.cnt[6 + tid - 12];
             else v = 3u;
             out[idx * 16 + tid] = v;
+            for (int k = 0; k < peers.n; ++k) peers.p[k][idx * 16 + tid] = v;   // other GPUs' result buffers (NVLink stores)
         }
     }
 #undef HOLDEM_PROF
@@ -628,7 +632,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 }
 
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    int *other_rows_flag, unsigned long long *prof, cudaStream_t st) {
+                                    int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Flop4Smem);
     cudaError_t e = cudaFuncSetAttribute(hp_flop_treys_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -637,7 +641,7 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (blocks * kGroups > n) blocks = (n + kGroups - 1) / kGroups;
     e = cudaMemsetAsync(other_rows_flag, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    hp_flop_treys_v4_kernel<<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u);
+    hp_flop_treys_v4_kernel<<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers);
     return cudaGetLastError();
 }
 

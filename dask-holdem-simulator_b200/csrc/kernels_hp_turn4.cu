@@ -80,7 +80,7 @@ __device__ __forceinline__ void tsync(uint32_t gid) { group_sync_n<kGT>(gid); }
 
 __global__ void __launch_bounds__(kThreadsT, 1)
 hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                        const int *__restrict__ run_flag, uint32_t one) {
+                        const int *__restrict__ run_flag, uint32_t one, PeerOut peers) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     if (run_flag != nullptr && !(*run_flag & 1)) return;   // the flop kernel saw no turn rows
     Turn4Smem &S = *reinterpret_cast<Turn4Smem *>(smem_raw);
@@ -134,7 +134,10 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         ok = ok && __popcll(known) == 6;
         if (!ok) {
-            if (tid < 16) out[idx * 16 + tid] = 0xFFFFFFFFu;
+            if (tid < 16) {
+                out[idx * 16 + tid] = 0xFFFFFFFFu;
+                for (int k = 0; k < peers.n; ++k) peers.p[k][idx * 16 + tid] = 0xFFFFFFFFu;
+            }
             continue;
         }
         if (tid < 12) G.cnt[tid] = 0;
@@ -525,12 +528,13 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             } else if (tid < 15) v = G.cnt[6 + tid - 12];
             else v = 4u;
             out[idx * 16 + tid] = v;
+            for (int k = 0; k < peers.n; ++k) peers.p[k][idx * 16 + tid] = v;
         }
     }
 }
 
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    const int *run_flag, cudaStream_t st) {
+                                    const int *run_flag, const PeerOut &peers, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Turn4Smem);
     static_assert(sizeof(Turn4Smem) <= 227 * 1024, "fifteen situation groups must fit the 227 KB of one CTA");
@@ -538,7 +542,29 @@ cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (e != cudaSuccess) return e;
     int64_t blocks = sms;
     if (blocks * kNG > n) blocks = (n + kNG - 1) / kNG;
-    hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u);
+    hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u, peers);
+    return cudaGetLastError();
+}
+
+// Result rows -> peer buffers, for the rows that were not written there by the kernel that produced them.
+__global__ void __launch_bounds__(256)
+rows_to_peers_kernel(const uint8_t *__restrict__ sit, int64_t n, const uint32_t *__restrict__ out, PeerOut peers,
+                     const int *__restrict__ run_flag) {
+    if (run_flag != nullptr && !(*run_flag & 2)) return;
+    const int64_t total = n * 16, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        if (run_flag != nullptr && sit[(i >> 4) * 8 + 6] == 0xFFu) continue;   // only five-card boards
+        const uint32_t v = out[i];
+        for (int k = 0; k < peers.n; ++k) peers.p[k][i] = v;
+    }
+}
+
+cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *out, const PeerOut &peers, int sms,
+                                 const int *run_flag, cudaStream_t st) {
+    if (n == 0 || peers.n == 0) return cudaSuccess;
+    int64_t blocks = (n * 16 + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    rows_to_peers_kernel<<<(int)blocks, 256, 0, st>>>(sit, n, out, peers, run_flag);
     return cudaGetLastError();
 }
 

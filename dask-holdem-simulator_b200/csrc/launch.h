@@ -8,6 +8,13 @@ namespace holdem {
 
 struct DevTables;
 
+// Result rows can be stored into other GPUs' buffers as well (peer memory over NVLink): p[k] points at the row that
+// corresponds to the kernel's row 0 inside peer k's [N,16] buffer.  n = 0: local output only.
+struct PeerOut {
+    uint32_t *p[8];
+    int n;
+};
+
 constexpr uint32_t kFlushEntries = 8192;
 
 // strict: also detect duplicate cards inside a row (builds the card set; ~1.5x the instructions of the fast path).
@@ -37,11 +44,15 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
 // prof: optional device uint64[4], cycles spent per phase summed over the situation groups (tables / W+T / descriptors /
 // tasks); nullptr in production.
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    int *other_rows_flag, unsigned long long *prof, cudaStream_t st);
+                                    int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st);
 
 // Rank-multiset turn kernel (kernels_hp_turn4.cu): same contract as launch_hp_turn_treys, bit-identical counts, the default.
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    const int *run_flag, cudaStream_t st);
+                                    const int *run_flag, const PeerOut &peers, cudaStream_t st);
+// Copies result rows of `out` to the peers: all rows (run_flag == nullptr) or, when run_flag is given, the five-card-board rows
+// and only if bit 1 of *run_flag is set (the rows the plain-enumeration kernel produced).
+cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *out, const PeerOut &peers, int sms,
+                                 const int *run_flag, cudaStream_t st);
 
 // HOLDEM_MODE_REFERENCE, all streets: 4-set walk for the regular runouts + arithmetic ranking of the irregular ones.
 cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);

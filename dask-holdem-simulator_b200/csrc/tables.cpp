@@ -284,23 +284,6 @@ struct Builder {
                                 (r3 + 3) * (r3 + 2) * (r3 + 1) * r3 / 24;
                         t.nf4_ranks[e] = (uint16_t)(r0 | (r1 << 4) | (r2 << 8) | (r3 << 12));
                     }
-        t.key4.assign(1824, 0);
-        for (int e = 0; e < 1820; ++e) {
-            const uint16_t v = t.nf4_ranks[e];
-            t.key4[e] = kRankKey[v & 15] + kRankKey[(v >> 4) & 15] + kRankKey[(v >> 8) & 15] + kRankKey[v >> 12];
-        }
-        // ---- 8. two rank pairs -> four-rank multiset index -------------------------------------------------------------------
-        t.idx4.assign(91 * 91 + 7, 0);
-        for (int q2 = 0; q2 < 13; ++q2)
-            for (int q1 = 0; q1 <= q2; ++q1)
-                for (int y = 0; y < 13; ++y)
-                    for (int x = 0; x <= y; ++x) {
-                        int r[4] = {q1, q2, x, y};
-                        std::sort(r, r + 4);
-                        int e = r[0] + (r[1] + 1) * r[1] / 2 + (r[2] + 2) * (r[2] + 1) * r[2] / 6 +
-                                (r[3] + 3) * (r[3] + 2) * (r[3] + 1) * r[3] / 24;
-                        t.idx4[91 * (q2 * (q2 + 1) / 2 + q1) + y * (y + 1) / 2 + x] = (uint16_t)e;
-                    }
         // ---- 9. direct-indexed board / own-hand tables of the rank-multiset flop kernel ------------------------------------------
         {
             auto rank_of = [&](const int *ranks, int n, int hash) -> uint16_t {   // 0 when a rank would be needed five times
@@ -472,17 +455,6 @@ int selftest(char *msg, int msg_len) {
             int r0 = v & 15, r1 = (v >> 4) & 15, r2 = (v >> 8) & 15, r3 = v >> 12;
             if (!(r0 <= r1 && r1 <= r2 && r2 <= r3 && r3 < 13)) return fail("nf4 ranks");
         }
-        for (int e = 0; e < 91 * 91; ++e) {   // idx4 points at the multiset made of the two pairs' ranks
-            int qp = e / 91, pp = e % 91, q2 = 0, y = 0;
-            while ((q2 + 1) * (q2 + 2) / 2 <= qp) ++q2;
-            while ((y + 1) * (y + 2) / 2 <= pp) ++y;
-            int want[4] = {qp - q2 * (q2 + 1) / 2, q2, pp - y * (y + 1) / 2, y};
-            std::sort(want, want + 4);
-            uint16_t v = t.nf4_ranks[t.idx4[e]];
-            int got[4] = {v & 15, (v >> 4) & 15, (v >> 8) & 15, v >> 12};
-            for (int k = 0; k < 4; ++k)
-                if (got[k] != want[k]) return fail("idx4");
-        }
     }
     {   // direct-indexed tables: spot values against the hashes they were built from
         if (t.board_t.size() != (size_t)kBoardMultisets * kBoardTRow || t.own_our7.size() != (size_t)kOwnMultisets * 96)
@@ -497,7 +469,7 @@ int selftest(char *msg, int msg_len) {
         if (t.nf[2].lookup(key) != 1608) return fail("six-high straight");
         // four deuces on the board side are impossible with a pair of deuces added twice
         if (t.board_t[0 * kBoardTRow + 0 * kBoardTPitch + 0] != 0) return fail("impossible multiset must be 0");
-        // own hand A A K K Q: m5 of ranks (10,11,11,12,12); plus pair (Q,Q) = full house aces over... kings full? AAKKQ+QQ -> AAA? no: AA KK QQQ -> QQQAA
+        // own hand Q K K A A (ranks 10,11,11,12,12) and the same hand plus the rank pair (Q,Q)
         const int r[5] = {10, 11, 11, 12, 12};
         const int m5 = r[0] + (r[1] + 1) * r[1] / 2 + (r[2] + 2) * (r[2] + 1) * r[2] / 6 +
                        (r[3] + 3) * (r[3] + 2) * (r[3] + 1) * r[3] / 24 + (r[4] + 4) * (r[4] + 3) * (r[4] + 2) * (r[4] + 1) * r[4] / 120;
@@ -530,8 +502,6 @@ TableImage make_image(const Tables &t) {
     im.off_task_hdr = append(t.flop_task_hdr.data(), t.flop_task_hdr.size() * 4);
     im.off_lanes = append(t.flop_lanes.data(), t.flop_lanes.size() * 4);
     im.off_nf4 = append(t.nf4_ranks.data(), t.nf4_ranks.size() * 2);
-    im.off_idx4 = append(t.idx4.data(), t.idx4.size() * 2);
-    im.off_key4 = append(t.key4.data(), t.key4.size() * 4);
     im.off_board_t = append(t.board_t.data(), t.board_t.size() * 2);
     im.off_board_opp5 = append(t.board_opp5.data(), t.board_opp5.size() * 2);
     im.off_own_our7 = append(t.own_our7.data(), t.own_our7.size() * 2);

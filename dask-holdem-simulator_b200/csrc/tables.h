@@ -70,11 +70,6 @@ struct Tables {
     std::vector<uint32_t> ref_lanes[2];
     // nf4_ranks[e] = the four ranks (4 bits each, ascending) of the e-th rank multiset, e = C(r0,1)+C(r1+1,2)+C(r2+2,3)+C(r3+3,4)
     std::vector<uint16_t> nf4_ranks;
-    // idx4[91 qp + pp] = index (same formula) of the multiset formed by two rank pairs, qp = (q1<=q2), pp = (x<=y), each
-    // numbered y(y+1)/2 + x: the expansion table of the rank-multiset flop kernel (kernels_hp_flop4.cu).
-    std::vector<uint16_t> idx4;
-    // key4[e] = sum of the additive rank keys of the e-th four-rank multiset (same numbering as nf4_ranks)
-    std::vector<uint32_t> key4;
     // Direct-indexed tables of the rank-multiset flop kernel, one contiguous row per situation (fetched with one bulk copy):
     //   board_t[b3][91][kBoardTPitch]  non-flush 7-card rank of board + rank pair q + rank pair p (symmetric in q, p),
     //                                  b3 = r0 + C(r1+1,2) + C(r2+2,3) over the sorted board ranks; 0 = impossible multiset
@@ -98,7 +93,7 @@ int selftest(char *msg, int msg_len);  // 0 = ok
 // Flat device image of the tables: one allocation, 16-byte aligned sections, offsets in bytes.
 struct TableImage {
     std::vector<uint8_t> bytes;
-    uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0, off_idx4 = 0, off_key4 = 0;
+    uint32_t off_flush = 0, off_pairs = 0, off_task_hdr = 0, off_lanes = 0, off_nf4 = 0;
     uint32_t off_board_t = 0, off_board_opp5 = 0, off_own_our7 = 0, off_own_rank5 = 0;
     uint32_t off_board4_t = 0, off_board4_opp6 = 0, off_own6_our7 = 0, off_own6_rank6 = 0;
     uint32_t n_tasks = 0;

@@ -45,6 +45,7 @@ SYMBOLS = {
     "holdem_hp_batch": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_batch_host": (_i, [_vp, _i64, _i, _vp]),
     "holdem_hp_batch_direct": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "holdem_hp_batch_peers": (_i, [_vp, _i64, _i, _vp, ctypes.POINTER(_vp), _i, _vp]),
     "holdem_hp_flop_variant": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_flop_phase_cycles": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "holdem_hp_turn_variant": (_i, [_vp, _i64, _i, _vp, _vp]),

@@ -114,6 +114,14 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
 int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
 int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out);
 
+/* holdem_hp_batch that also stores every result row into up to 8 other GPUs' buffers (peer memory mapped into this process:
+ * CUDA IPC / symmetric memory; NVLink stores issued by the kernels themselves, no separate collective).  peer_out is a HOST
+ * array of n_peers device pointers, peer_out[k] pointing at the row of peer k's [N,16] buffer that corresponds to row 0 of
+ * this call (i.e. already offset by this rank's first row).  The caller orders the peers (a barrier before the buffers are
+ * overwritten and one after this call's stream work); HandCalculations' multi-GPU layer (holdem_b200/sharded.py) does. */
+int holdem_hp_batch_peers(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *const *peer_out, int n_peers,
+                          void *stream);
+
 /* Same results as holdem_hp_batch computed by the plain (non-deduplicating) enumeration kernel: one opponent
  * evaluation per (opponent holding, runout) pair.  Kept as the independent second implementation the parity
  * tests cross-check the deduplicating flop / turn kernels against; it is also what holdem_hp_batch itself runs for

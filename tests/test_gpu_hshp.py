@@ -273,7 +273,8 @@ def _texture_situations(hb):
              ([26, 27], [0, 2, 17]), ([12, 25], [38, 51, 0]), ([5, 18], [31, 44, 6]), ([3, 4], [5, 6, 20]),
              ([12, 11], [10, 9, 8]), ([13, 26], [0, 1, 15]), ([0, 12], [13, 26, 39]), ([1, 14], [0, 13, 26]),
              ([12, 3], [0, 1, 2]), ([25, 38], [0, 1, 2]), ([12, 51], [0, 13, 3]), ([8, 9], [10, 11, 25]),
-             ([21, 47], [8, 34, 9]), ([7, 20], [33, 46, 6]), ([39, 40], [41, 42, 0]), ([50, 51], [49, 48, 47])]
+             ([21, 47], [8, 34, 9]), ([7, 20], [33, 46, 6]), ([39, 40], [41, 42, 0]), ([50, 51], [49, 48, 47]),
+             ([0, 1], [5, 18, 31]), ([44, 2], [5, 18, 31]), ([12, 25], [38, 11, 24]), ([0, 14], [28, 42, 4])]
     return hb.pack_situations([c[0] for c in cases], [c[1] for c in cases])
 
 
@@ -304,7 +305,8 @@ def test_hp_turn_variants_agree_and_match_oracle(hb, oracle):
     cases = [([0, 1], [2, 3, 4, 5]), ([13, 26], [2, 3, 4, 5]), ([12, 11], [2, 3, 4, 18]), ([25, 38], [2, 3, 4, 18]),
              ([0, 13], [2, 3, 15, 16]), ([12, 25], [38, 51, 0, 13]), ([5, 18], [31, 44, 6, 19]), ([7, 8], [9, 10, 24, 37]),
              ([39, 40], [41, 42, 43, 0]), ([39, 1], [41, 42, 43, 44]), ([50, 51], [49, 48, 47, 46]), ([14, 1], [31, 32, 33, 20]),
-             ([0, 12], [13, 26, 39, 1]), ([21, 47], [8, 34, 9, 35])]
+             ([0, 12], [13, 26, 39, 1]), ([21, 47], [8, 34, 9, 35]), ([0, 1], [5, 18, 31, 44]), ([44, 2], [5, 18, 31, 6]),
+             ([12, 25], [38, 11, 24, 37])]
     sit = np.concatenate([hb.pack_situations([c[0] for c in cases], [c[1] for c in cases]),
                           hb.random_situations(400, seed=821, n_board=4)])
     want = oracle.hp_batch(sit, "treys")
