@@ -498,7 +498,7 @@ def main():
                                "(numpy default_rng(20251019) deals)",
                    "global_situations": n_global, "parallelism": f"situation-sharded x{world}"
                    + ("" if world == 1 else (", result rows stored by the kernels into every rank's symmetric-memory buffer "
-                                             "over NVLink (fused compute + all-gather, two symmetric-memory barriers)"
+                                             "over NVLink (fused compute + all-gather, one symmetric-memory barrier per step)"
                                              if fused_used else ", in-place NCCL all-gather of the [N,16] u32 result")),
                    "nccl_allgather_path_value": allgather_value,
                    "l2": "256 MiB buffer written between timed iterations (L2 flush); inputs 0.5 MiB/GPU"},

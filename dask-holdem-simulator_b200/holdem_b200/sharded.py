@@ -7,8 +7,9 @@ makes every rank hold all rows.  There is no other data-path collective.
 
 Fused path (CUDA, one node): the result buffer is symmetric memory (torch.distributed._symmetric_memory, peer-mapped over
 NVLink/NVSwitch) and the HP kernels store every result row into all ranks' buffers themselves -- compute and all-gather are
-one launch, the transfer overlaps the computation row by row (holdem_hp_batch_peers).  Two symmetric-memory barriers
-order the ranks; NCCL is not involved.  `fused=None` tries this path and falls back to the all-gather when symmetric
+one launch, the transfer overlaps the computation row by row (holdem_hp_batch_peers).  One symmetric-memory barrier per call
+orders the ranks (two buffers alternate, so the barrier of the previous call also protects the buffer being overwritten);
+NCCL is not involved.  `fused=None` tries this path and falls back to the all-gather when symmetric
 memory is unavailable.
 """
 import ctypes
@@ -56,7 +57,9 @@ def _fused_peer_store(sit, mode, group, lo, hi, per, world, rank):
     k = ent["next"]
     ent["next"] = k ^ 1
     buf, hdl = ent["bufs"][k], ent["hdls"][k]
-    hdl.barrier(channel=0)                       # every rank is done reading this buffer's previous contents
+    # No barrier is needed before overwriting: this buffer was last used two calls ago, and every rank has since passed the
+    # barrier that ends the previous call -- which its stream reaches only after everything it enqueued on the result of
+    # that older call (consumers on other streams must order themselves against this one).
     n_local = hi - lo
     if n_local > 0:
         block = sit[lo:hi].contiguous()
