@@ -506,11 +506,11 @@ def main():
         "wall_s_timed_region": t_wall,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sit_np.nbytes) * world,
                 "d2h_bytes_per_step": int(host_out.nbytes) * world, "steps": e2e_steps,
-                "api": "holdem_hp_batch_host (C ABI, page-locked caller buffers used directly; chunked H2D/kernel/D2H on two "
-                       "streams)",
+                "api": "holdem_hp_batch_host (C ABI, page-locked caller buffers: one H2D copy of the rows, one launch, the kernels "
+                       "store the result rows straight into the caller's mapped host buffer)",
                 "pageable_caller_buffers": {"value": e2e_pageable, "unit": UNIT,
-                                            "what": "same call with pageable numpy arrays: the library stages through its own "
-                                                    "pinned buffers (two extra host memcpy per chunk)"}},
+                                            "what": "same call with pageable numpy arrays: 16,384-row chunks through the library's "
+                                                    "own pinned staging on two streams (two extra host memcpy per chunk)"}},
         "gpu_launches": 3 * args.steps,
         "gpu_launches_note": "per step: hp_flop_treys_v4_kernel + hp_turn_treys_kernel + hp_direct_kernel (the last two "
                              "exit at once when the batch holds no turn / river rows)",

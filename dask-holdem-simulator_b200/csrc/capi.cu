@@ -466,11 +466,36 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
     if (n < 0 || (n > 0 && (!h_sit || !h_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     int rc = check_mode(mode);
     if (rc) return rc;
-    rc = host_pipeline(h_sit, 8, h_out, 64, n, 1 << 14,
-                       [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
-                           return hp_dispatch(S, d_in, rows, mode, (uint32_t *)d_out, st);
-                       });
-    if (rc) return rc;
+    // Page-locked caller buffers: one H2D copy of the 8-byte rows, ONE launch over the whole batch, and the kernels store
+    // their 64-byte result rows straight into the caller's (mapped) host buffer -- the device-to-host transfer runs under
+    // the computation instead of after it.  HOLDEM_HOST_ZERO_COPY=0 selects the chunked copy pipeline instead.
+    static const bool zero_copy = !(getenv("HOLDEM_HOST_ZERO_COPY") && atoi(getenv("HOLDEM_HOST_ZERO_COPY")) == 0);
+    bool done = false;
+    if (zero_copy && n > 0) {
+        DeviceState *S = nullptr;
+        if ((rc = current_state(&S))) return rc;
+        cudaPointerAttributes ai, ao;
+        const bool pinned = cudaPointerGetAttributes(&ai, h_sit) == cudaSuccess && ai.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&ao, h_out) == cudaSuccess && ao.type == cudaMemoryTypeHost &&
+                            ao.devicePointer != nullptr;
+        cudaGetLastError();
+        if (pinned) {
+            std::lock_guard<std::mutex> lock(S->host_mu);
+            if ((rc = ensure_host_buffers(*S, 0, (size_t)n * 8))) return rc;
+            cudaStream_t st = S->streams[0];
+            CUDA_TRY(cudaMemcpyAsync(S->d_buf, h_sit, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(hp_dispatch(*S, S->d_buf, n, mode, (uint32_t *)ao.devicePointer, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            done = true;
+        }
+    }
+    if (!done) {
+        rc = host_pipeline(h_sit, 8, h_out, 64, n, 1 << 14,
+                           [&](DeviceState &S, uint8_t *d_in, int64_t rows, uint8_t *d_out, cudaStream_t st) {
+                               return hp_dispatch(S, d_in, rows, mode, (uint32_t *)d_out, st);
+                           });
+        if (rc) return rc;
+    }
     for (int64_t i = 0; i < n; ++i)
         if (h_out[i * 16 + 15] == HOLDEM_BAD_ROW) return fail(HOLDEM_ERR_BAD_INPUT, "situation %lld is malformed", (long long)i);
     return HOLDEM_OK;

@@ -324,7 +324,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             const uint32_t ms = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
             const uint32_t mbmask = m3 ? G.bmask[ms] : 0u;
             uint32_t c0 = 0, c1 = 0, c2 = 0;
-#pragma unroll
+#pragma unroll 2
             for (uint32_t p = tid; p < (uint32_t)kPairs4; p += kGroupThreads) {
                 const uint32_t pr = S.pairs[p];
                 const uint32_t i = pr & 0xFFu, j = pr >> 8;
