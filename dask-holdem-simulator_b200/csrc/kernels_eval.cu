@@ -409,7 +409,7 @@ cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int bloc
 // =====================================================================================================================
 // Integer issue micro-benchmark: eight independent chains per thread, each step one compare (ALU pipe) and one predicated
 // multiply-add (FMA pipe) -- the instruction pair the HP kernels are made of.  mix 0: compare + multiply-add pairs;
-// mix 1: multiply-adds only (FMA pipe); mix 2: logic ops only (ALU pipe).  Returns nothing; timed by the caller.
+// mix 1: multiply-adds only (FMA pipe); mix 2: add / xor pairs only (ALU pipe).  Returns nothing; timed by the caller.
 // =====================================================================================================================
 __global__ void __launch_bounds__(1024, 1)
 int_issue_kernel(int iters, int mix, uint32_t one, uint32_t *__restrict__ sink) {
@@ -435,8 +435,8 @@ int_issue_kernel(int iters, int mix, uint32_t one, uint32_t *__restrict__ sink) 
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[k]) : "r"(t));
-                asm volatile("and.b32 %0, %0, %1;" : "+r"(a[k]) : "r"(~one));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(t));          // IADD3 then LOP3: cannot be merged
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[k]) : "r"(a[(k + 1) & 7]));
             }
         }
     }
