@@ -103,6 +103,9 @@ def main():
     ap.add_argument("--situations", type=int, default=1000000)
     ap.add_argument("--config5", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--python-baseline", action="store_true", help="also time the reference-shaped pure-Python path (config 1)")
+    ap.add_argument("--python-baseline-opponents", type=int, default=40,
+                    help="opponent holdings of the 1081 to time (each = 990 runouts x 2 evaluate calls)")
     args = ap.parse_args()
     if args.config5:
         return config5(args)
@@ -132,6 +135,36 @@ def main():
                     "HandStrength_ms": 1e3 * t_hs, "HandPotential_ms": 1e3 * t_hp}
     HC.set_mode("treys")
     res["config1_single_flop_dropin"] = c1
+    if args.python_baseline:
+        # the same situation through the reference-shaped Python path on one host core: 1081 x 990 runouts, two pure-Python
+        # Treys evaluate() calls each (oracle/py_treys.py restates treys.Evaluator; treys itself cannot be installed offline)
+        import itertools
+        from oracle.py_treys import PyEvaluator, card_from_path
+        ev = PyEvaluator()
+        our, board = [14, 1], [31, 32, 33]
+        unseen = [c for c in range(52) if c not in our + board]
+        tc = {c: card_from_path(c) for c in range(52)}
+        t0 = time.perf_counter()
+        ours_now = ev.evaluate([tc[c] for c in board], [tc[c] for c in our])
+        hp = [[0, 0, 0], [0, 0, 0], [0, 0, 0]]
+        n_opp = 0
+        budget = args.python_baseline_opponents
+        for p in itertools.combinations(unseen, 2):
+            if n_opp == budget:
+                break
+            n_opp += 1
+            opp_now = ev.evaluate([tc[c] for c in board], [tc[c] for c in p])
+            idx = 0 if ours_now < opp_now else (1 if ours_now == opp_now else 2)
+            rest = [c for c in unseen if c not in p]
+            for q in itertools.combinations(rest, 2):
+                b5 = [tc[c] for c in board + list(q)]
+                a, b = ev.evaluate(b5, [tc[c] for c in our]), ev.evaluate(b5, [tc[c] for c in p])
+                hp[idx][0 if a < b else (1 if a == b else 2)] += 1
+        dt = time.perf_counter() - t0
+        res["config1_python_path_one_core"] = {
+            "opponent_holdings_timed": n_opp, "seconds": dt, "seconds_per_situation_extrapolated": dt * 1081 / n_opp,
+            "evaluate_calls": n_opp * (1 + 2 * 990) + 1,
+            "what": "HandPotential loop shape of the reference with a pure-Python Treys evaluator, testing/ExampleHS.py situation"}
 
     # ---- config 2: exhaustive sweep -----------------------------------------------------------------------------------------
     ms = timed(lambda: hb.exhaustive7(0), reps=5)

@@ -76,14 +76,15 @@ eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restri
 template <int NC>
 __global__ void __launch_bounds__(1024, 1)
 eval_batch_fast_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T,
-                       uint32_t row_bytes) {
+                       uint32_t row_bytes, uint32_t one) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int kIlp = 4;
     constexpr int kQueueCap = 256;   // per warp; drained when it holds >= 128 entries (four full passes of the warp)
     uint32_t *s_cardkey = reinterpret_cast<uint32_t *>(smem);                 // 64 entries (strict path)
     uint32_t *s_tab = s_cardkey + 64;                                         // 256 entries, indexed by the raw byte
-    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_tab + 256);            // [32 warps][kQueueCap]
-    uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 256 + 1024 + 32 * kQueueCap * 2);
+    uint32_t *s_slow = s_tab + 256;                                           // 512 bits: suit-counter pattern holds a flush
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_slow + 16);            // [32 warps][kQueueCap]
+    uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 256 + 1024 + 64 + 32 * kQueueCap * 2);
     uint16_t *s_disp = s_flush + kFlushEntries;
     uint16_t *s_val = s_disp + T.disp_entries[NC - 5];
     const NfHash &g = T.nf[NC - 5];
@@ -91,6 +92,16 @@ eval_batch_fast_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__r
     if (threadIdx.x < 256) {
         const uint32_t c = threadIdx.x, su = c / 13;
         s_tab[c] = c < 52 ? (c_rank_key[c % 13] | (su < 3 ? 1u << (23 + 3 * su) : 0u)) : 0u;
+    }
+    if (threadIdx.x < 16) {
+        // bit s of the table: the three 3-bit counters (clubs, diamonds, hearts) packed in s mean a flush --
+        // a counted suit holds >= 5, or so few cards are counted that spades hold >= 5
+        uint32_t word = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+            const uint32_t sv = threadIdx.x * 32 + b, c0 = sv & 7u, c1 = (sv >> 3) & 7u, c2 = sv >> 6;
+            if (c0 >= 5 || c1 >= 5 || c2 >= 5 || c0 + c1 + c2 <= (uint32_t)(NC - 5)) word |= 1u << b;
+        }
+        s_slow[threadIdx.x] = word;
     }
     {
         const uint4 *src;
@@ -109,52 +120,55 @@ eval_batch_fast_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__r
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *queue = s_queue + warp * kQueueCap;
     const char *tab_bytes = reinterpret_cast<const char *>(s_tab);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // 32-bit hand indices: the launcher splits batches of 2^31 hands or more
+    const uint32_t nn = (uint32_t)n, stride = gridDim.x * blockDim.x;
     // Deferred hands: entry = window-iteration << 7 | j << 5 | lane, relative to qbase (this warp's first hand of the window)
     uint32_t qn = 0, it = 0;
-    int64_t qbase = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    uint32_t qbase = blockIdx.x * blockDim.x + threadIdx.x - lane;
     auto drain = [&]() {
         __syncwarp();
         for (uint32_t e = lane; e < qn; e += 32) {
             const uint32_t q = queue[e];
-            const int64_t i = qbase + ((int64_t)(q >> 7) * kIlp + ((q >> 5) & 3u)) * stride + (q & 31u);
+            const uint32_t i = qbase + ((q >> 7) * kIlp + ((q >> 5) & 3u)) * stride + (q & 31u);
             out[i] = (uint16_t)eval_row<NC>(__ldg(cards + i), s_cardkey, s_flush, h);
         }
         __syncwarp();
     };
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base - threadIdx.x < n; base += kIlp * stride) {
+    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base - threadIdx.x < nn; base += kIlp * stride) {
         // the loop bound is block-uniform; lanes past n load a dummy hand and write nothing
         uint2 w[kIlp];
-        const uint2 *src = cards + base;
-        uint16_t *dst = out + base;
 #pragma unroll
         for (int j = 0; j < kIlp; ++j) {
-            const int64_t i = base + j * stride;
-            w[j] = i < n ? __ldg(src + j * stride) : make_uint2(0x03020100u, 0x00060504u);
+            const uint32_t i = base + j * stride;
+            w[j] = i < nn ? __ldg(cards + i) : make_uint2(0x03020100u, 0x00060504u);
         }
 #pragma unroll
         for (int j = 0; j < kIlp; ++j) {
-            const bool live = base + j * stride < n;
+            const uint32_t i = base + j * stride;
+            const bool live = i < nn;
             uint32_t sum = 0;
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
-                // byte k -> byte offset into the table: one permute (ALU pipe) and one multiply (FMA pipe)
+                // byte k -> byte offset into the table: one permute (ALU pipe) and one multiply (FMA pipe); the running sum
+                // is a multiply-add by a kernel argument equal to 1, so it issues on the FMA pipe as well
                 const uint32_t b = __byte_perm(k < 4 ? w[j].x : w[j].y, 0u, 0x4440u + (k & 3));
-                sum += *reinterpret_cast<const uint32_t *>(tab_bytes + b * row_bytes);
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(tab_bytes + b * row_bytes);
+                asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(sum) : "r"(v), "r"(one));
             }
             // any byte >= 52?  (b & 0x7F) + 76 sets bit 7 iff (b & 0x7F) >= 52; OR b itself catches b >= 128
             const uint32_t ymask = NC == 7 ? 0x00808080u : (NC == 6 ? 0x00008080u : 0x00000080u);
             const uint32_t badx = (((w[j].x & 0x7F7F7F7Fu) + 0x4C4C4C4Cu) | w[j].x) & 0x80808080u;
             const uint32_t bady = (((w[j].y & 0x7F7F7F7Fu) + 0x4C4C4C4Cu) | w[j].y) & ymask;
             const uint32_t s = sum >> 23;
-            const uint32_t ge5 = (s >> 2) & ((s >> 1) | s) & 0x49u;                      // a counted suit holds >= 5
-            const uint32_t counted = (s & 7u) + ((s >> 3) & 7u) + (s >> 6);               // cards not in spades
-            const bool slow = ((ge5 | badx | bady) != 0 || counted <= (uint32_t)(NC - 5)) && live;
+            const uint32_t flushbit = (s_slow[s >> 5] >> (s & 31u)) & 1u;
+            const bool slow = (flushbit | badx | bady) != 0 && live;
             const uint32_t r = nf_lookup(h, sum & 0x7FFFFFu);
-            if (live && !slow) dst[j * stride] = (uint16_t)r;
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, slow);
-            if (slow) queue[qn + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)((it << 7) | (j << 5) | lane);
-            qn += __popc(ballot);
+            if (live && !slow) out[i] = (uint16_t)r;
+            if (__any_sync(0xFFFFFFFFu, slow)) {
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, slow);
+                if (slow) queue[qn + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)((it << 7) | (j << 5) | lane);
+                qn += __popc(ballot);
+            }
         }
         ++it;
         if (qn >= 128 || it == 500) {
@@ -171,7 +185,7 @@ size_t eval_smem_bytes(const DevTables &T, int nc) {
     return 1024 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
 }
 size_t eval_fast_smem_bytes(const DevTables &T, int nc) {
-    return 256 + 1024 + 32 * 256 * 2 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
+    return 256 + 1024 + 64 + 32 * 256 * 2 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
 }
 
 template <int NC>
@@ -190,7 +204,11 @@ static cudaError_t launch_eval_nc(const DevTables &T, const uint8_t *cards, int6
             cudaError_t e = cudaFuncSetAttribute(eval_batch_fast_kernel<NC>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            eval_batch_fast_kernel<NC><<<sms, 1024, smem, st>>>(c2, n, out, T, 4u);
+            // 32-bit hand indices inside the kernel: batches of 2^31 hands or more go in pieces
+            constexpr int64_t kPiece = (int64_t)1 << 30;
+            for (int64_t off = 0; off < n; off += kPiece)
+                eval_batch_fast_kernel<NC><<<sms, 1024, smem, st>>>(c2 + off, n - off < kPiece ? n - off : kPiece, out + off, T,
+                                                                     4u, 1u);
         }
     } else {
         int blocks = (int)((n + 255) / 256);

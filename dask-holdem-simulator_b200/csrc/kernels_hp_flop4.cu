@@ -178,7 +178,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         if (!ok) {
             if (tid < 16) {
                 out[idx * 16 + tid] = 0xFFFFFFFFu;
-                for (int k = 0; k < peers.n; ++k) peers.p[k][idx * 16 + tid] = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)      // constant indices: the parameter struct stays in param space
+                    if (k < peers.n) peers.p[k][idx * 16 + tid] = 0xFFFFFFFFu;
             }
             continue;
         }
@@ -483,13 +485,21 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t tq_s = t_s + qcol;
                 const uint4 *pd = G.PD + G.g_pdbase[g] + p0;
                 uint32_t aL = 0, aG = 0, sL = 0, sG = 0;
+                // steps [0, nboth + n_s) have an add part (holdings with both cards in s, or one card a in s); the ones behind them
+                // are rank-level undo steps: no suited-table gather, half the compares
+                const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
 #pragma unroll 4
-                for (uint32_t t = p0; t < p1; ++t, ++pd) {
+                for (uint32_t t = p0; t < split; ++t, ++pd) {
                     const uint4 d = *pd;
                     // fold() is XOR-linear and the step's cards of s are disjoint from board + runout when the step is valid
                     const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
                     const uint32_t rn = lds_u16(tq_s + d.w);
                     flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
+                }
+#pragma unroll 4
+                for (uint32_t t = split; t < p1; ++t, ++pd) {
+                    const uint4 d = *pd;
+                    undo_step(sL, sG, our, lds_u16(tq_s + d.w), d.x, qb2, d.z, one);
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {   // wl = 0 on lanes past the end of the runout list
@@ -622,7 +632,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             } else if (tid < 15) v = G.cnt[6 + tid - 12];
             else v = 3u;
             out[idx * 16 + tid] = v;
-            for (int k = 0; k < peers.n; ++k) peers.p[k][idx * 16 + tid] = v;   // other GPUs' result buffers (NVLink stores)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)          // other GPUs' result buffers (NVLink stores)
+                if (k < peers.n) peers.p[k][idx * 16 + tid] = v;
         }
     }
 #undef HOLDEM_PROF

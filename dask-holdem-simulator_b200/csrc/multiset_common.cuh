@@ -55,6 +55,18 @@ __device__ __forceinline__ void flush_step(uint32_t &aL, uint32_t &aG, uint32_t 
         : "+r"(aL), "+r"(aG), "+r"(sL), "+r"(sG)
         : "r"(our), "r"(rf), "r"(rn), "r"(dx), "r"(qb2), "r"(wa), "r"(ws), "r"(one));
 }
+// The undo half alone, for the steps that have no add part (rank-level undo steps): valid as above;
+//   if (our < rn) sL += ws;  if (our > rn) sG += ws.
+__device__ __forceinline__ void undo_step(uint32_t &sL, uint32_t &sG, uint32_t our, uint32_t rn, uint32_t dx, uint32_t qb2,
+                                          uint32_t ws, uint32_t one) {
+    asm("{\n\t.reg .pred v, p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %4, %5;\n\t"
+        "setp.eq.u32 v, t, 0;\n\t"
+        "setp.lt.and.u32 p, %2, %3, v;\n\t@p mad.lo.u32 %0, %6, %7, %0;\n\t"
+        "setp.gt.and.u32 p, %2, %3, v;\n\t@p mad.lo.u32 %1, %6, %7, %1;\n\t}"
+        : "+r"(sL), "+r"(sG)
+        : "r"(our), "r"(rn), "r"(dx), "r"(qb2), "r"(ws), "r"(one));
+}
 // if (a < b) accL += w * m;  if (a > b) accG += w * m   (same pipe split)
 __device__ __forceinline__ void cmp_add(uint32_t &accL, uint32_t &accG, uint32_t a, uint32_t b, uint32_t w, uint32_t one) {
     asm("{\n\t.reg .pred p;\n\t"
