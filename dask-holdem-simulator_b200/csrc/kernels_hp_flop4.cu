@@ -73,7 +73,6 @@ struct Flop4Group {                    // one situation in flight
     uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair (row of DevTables::own_our7)
     uint16_t opp5nf[96];               // non-flush rank of board + rank pair (row of DevTables::board_opp5)
     unsigned long long bar[2];         // mbarriers: [0] the two small rows, [1] T
-    uint16_t W[kU * kU + 3];           // [i*47+j], i<j: our7 | cls << 13
     uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
     uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
@@ -185,7 +184,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             continue;
         }
         if (tid < 12) G.cnt[tid] = 0;
-        if (tid < 4) G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
+        if (tid < 4) { G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu; G.hist_none[tid] = 0; }
         if (tid >= 64 && tid < 160) G.qflush[tid - 64] = 0;
         if (warp == 0) {
             // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
@@ -313,59 +312,65 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         group_sync(gid);                                                                            // (B)
         HOLDEM_PROF(0)
+        // the suit in which we can still make a flush (>= 3 of hole + board), and the one the board is monotone in
+        const uint32_t f3 = (hsuit + 0x5555u) & 0x8888u;            // nibble >= 3
+        const uint32_t fs = f3 ? (uint32_t)(__ffs(f3) - 1) >> 2 : 4u;
+        const uint32_t fneed = f3 ? 5u - ((hsuit >> (4 * fs)) & 15u) : 9u;      // cards of fs a runout must bring (<= 0: we hold it)
+        const uint32_t hbmask = f3 ? (uint32_t)(known >> (13 * fs)) & 0x1FFFu : 0u;
+        const uint32_t m3 = (bsuit + 0x5555u) & 0x8888u;
+        const uint32_t ms = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
         {
-            // ---- W: our final rank with the pair as runout, flop class of the pair as a holding (no global memory) ---------
             mbar_wait(bar0_s, parity);                                 // (already complete: warp 1 waited before the barrier)
             const uint32_t ours_now = G.ours_now;
-            // the suit in which we can still make a flush (>= 3 of hole + board), and the one the board is monotone in
-            const uint32_t f3 = (hsuit + 0x5555u) & 0x8888u;            // nibble >= 3
-            const uint32_t fs = f3 ? (uint32_t)(__ffs(f3) - 1) >> 2 : 4u;
-            const uint32_t fneed = f3 ? 5u - ((hsuit >> (4 * fs)) & 15u) : 9u;
-            const uint32_t hbmask = f3 ? (uint32_t)(known >> (13 * fs)) & 0x1FFFu : 0u;
-            const uint32_t m3 = (bsuit + 0x5555u) & 0x8888u;
-            const uint32_t ms = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
-            const uint32_t mbmask = m3 ? G.bmask[ms] : 0u;
-            uint32_t c0 = 0, c1 = 0, c2 = 0;
-#pragma unroll 2
-            for (uint32_t p = tid; p < (uint32_t)kPairs4; p += kGroupThreads) {
-                const uint32_t pr = S.pairs[p];
-                const uint32_t i = pr & 0xFFu, j = pr >> 8;
-                const uint32_t ci = G.code[i], cj = G.code[j];
-                const uint32_t ri = ci >> 2, rj = cj >> 2, si = ci & 3u, sj = cj & 3u;
-                const uint32_t pp = tri(rj) + ri;
-                uint32_t our7 = G.our7nf[pp];
-                const uint32_t fbits = (si == fs ? 1u << ri : 0u) | (sj == fs ? 1u << rj : 0u);
-                if ((uint32_t)__popc(fbits) >= fneed) {            // this runout gives us a flush: its own generic entry
-                    our7 = S.flush[fold(hbmask | fbits)];
-                    G.ext[atomicAdd(&G.n_ext, 1u)] = pp | (our7 << 8);
+            // ---- hand strength: opponent holdings by flop class, from rank pairs (no per-pair table is built) ---------------------
+            if (warp < 3) {
+                const uint32_t pp = tid;                               // 96 threads, 91 rank pairs
+                const uint32_t xy = S.ppxy[min(pp, 90u)], x = xy & 15u, y = xy >> 4;
+                const uint32_t ux = G.u[x], uy = G.u[y];
+                const uint32_t cnt = pp < (uint32_t)kPP ? (x != y ? ux * uy : (ux ? choose2u(ux) : 0u)) : 0u;
+                const uint32_t cl = G.clsr[min(pp, 90u)];
+#pragma unroll
+                for (uint32_t c = 0; c < 3; ++c) {
+                    const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cl == c ? cnt : 0u);
+                    if (lane == 0 && v) atomicAdd(&G.cnt[6 + c], v);
+                }
+            }
+            if (ms < 4) {   // monotone board: a holding suited in that suit has flopped a flush -- move it to its true class
+                const uint32_t nsu = G.ns[ms], mbmask = G.bmask[ms];
+                for (uint32_t t = tid; t < choose2u(nsu); t += kGroupThreads) {
+                    const uint32_t pr = S.pairs[t];
+                    const uint32_t ra = G.code[G.Ls[ms][pr & 0xFFu]] >> 2, rb = G.code[G.Ls[ms][pr >> 8]] >> 2;
+                    const uint32_t opp5 = S.flush[fold(mbmask | (1u << ra) | (1u << rb))];
+                    const uint32_t cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
+                    atomicAdd(&G.cnt[6 + cls], 1u);
+                    atomicSub(&G.cnt[6 + G.clsr[tri(rb) + ra]], 1u);
+                }
+            }
+            // ---- runouts that give us a flush get their own entry of the generic part (their our7 is a suited-table rank) ---------
+            if (fneed <= 2) {
+                const uint32_t nfs = G.ns[fs], nnf = kU - nfs, nboth = choose2u(nfs);
+                const uint32_t total = (int)fneed == 2 ? nboth : ((int)fneed == 1 ? nboth + nfs * nnf : (uint32_t)kPairs4);
+                for (uint32_t t = tid; t < total; t += kGroupThreads) {
+                    uint32_t i, j;
+                    if ((int)fneed <= 0) {
+                        const uint32_t pr = S.pairs[t];
+                        i = pr & 0xFFu; j = pr >> 8;
+                    } else if (t < nboth) {
+                        const uint32_t pr = S.pairs[t];
+                        i = G.Ls[fs][pr & 0xFFu]; j = G.Ls[fs][pr >> 8];
+                    } else {
+                        const uint32_t t2 = t - nboth, a = t2 / nnf, z = t2 - a * nnf;
+                        const uint32_t x = G.Ls[fs][a], y = G.Lns[fs][z];
+                        i = min(x, y); j = max(x, y);
+                    }
+                    const uint32_t ci = G.code[i], cj = G.code[j];
+                    const uint32_t ri = ci >> 2, rj = cj >> 2;
+                    const uint32_t fbits = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
+                    const uint32_t pp = tri(rj) + ri;
+                    G.ext[atomicAdd(&G.n_ext, 1u)] = pp | ((uint32_t)S.flush[fold(hbmask | fbits)] << 8);
                     atomicAdd(&G.qflush[pp], 1u);
                 }
-                uint32_t cls = G.clsr[pp];
-                if (si == ms && sj == ms) {                        // monotone board and a suited holding: a flopped flush
-                    const uint32_t opp5 = S.flush[fold(mbmask | (1u << ri) | (1u << rj))];
-                    cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
-                }
-                c0 += cls == 0; c1 += cls == 1; c2 += cls == 2;
-                G.W[i * kU + j] = (uint16_t)(our7 | (cls << 13));
             }
-            c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
-            c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
-            c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
-            if (lane == 0) { atomicAdd(&G.cnt[6], c0); atomicAdd(&G.cnt[7], c1); atomicAdd(&G.cnt[8], c2); }
-            // ---- the "one card a in s" steps: x now, the class histogram over c is accumulated in the next phase ------------------
-            if (tid < 64) {
-                const uint32_t s = tid >> 4, ai = tid & 15u;
-                if (((bsuit >> (4 * s)) & 15u) >= 2 && ai < G.ns[s]) {
-                    const uint32_t nsu = G.ns[s];
-                    const uint32_t ra = G.code[G.Ls[s][ai]] >> 2;
-                    G.PD[G.pd_base[s] + choose2u(nsu) + ai] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, 0u, 0u);
-                }
-            }
-            if (tid < 4) G.hist_none[tid] = 0;
-        }
-        group_sync(gid);                                                                            // (C)
-        HOLDEM_PROF(1)
-        {
             // ---- step descriptors of the flush part ---------------------------------------------------------------------------------
             const uint32_t total = G.pd_total;
             for (uint32_t e = tid; e < total; e += kGroupThreads) {
@@ -379,26 +384,27 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t pr = S.pairs[t];
                     const uint32_t pa = G.Ls[s][pr & 0xFFu], pb = G.Ls[s][pr >> 8];
                     const uint32_t ra = G.code[pa] >> 2, rb = G.code[pb] >> 2;
-                    const uint32_t cls = G.W[pa * kU + pb] >> 13;
                     const uint32_t pp = tri(rb) + ra, bits = (1u << ra) | (1u << rb);
+                    uint32_t cls = G.clsr[pp];
+                    if (s == ms) {                                 // monotone board: this holding has flopped a flush
+                        const uint32_t opp5 = S.flush[fold(G.bmask[s] | bits)];
+                        cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
+                    }
                     G.PD[e] = make_uint4((bits << 17) | (2u * fold(bits)), 1u << (10 * cls), G.clsw[pp], pp * (kTPitch * 2));
-                } else if (t < nboth + nsu) {
-                    // written in the previous phase; y accumulates below
+                } else if (t < nboth + nsu) {                      // one card a in s, any card c outside s: the flop class of {a, c}
+                    const uint32_t ra = G.code[G.Ls[s][t - nboth]] >> 2;     // depends on ranks alone (four of the suit at most)
+                    uint32_t hist = 0;
+                    for (uint32_t y = 0; y < 13; ++y)
+                        hist += (G.u[y] - ((sm >> y) & 1u)) * G.clsw[tri(max(ra, y)) + min(ra, y)];
+                    G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), hist, 0u, 0u);
                 } else if (t < nboth + 14u * nsu) {                // undo step for {a, any c of rank y outside s}
                     t -= nboth + nsu;
                     const uint32_t ai = t / 13u, y = t - 13u * ai;
-                    const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
+                    const uint32_t ra = G.code[G.Ls[s][ai]] >> 2;
                     const uint32_t pp = tri(max(ra, y)) + min(ra, y);
-                    uint32_t wgt = 0, hist = 0;
-                    for (uint32_t pc = G.st[y]; pc < G.st[y + 1]; ++pc) {
-                        if ((G.code[pc] & 3u) == s) continue;
-                        ++wgt;
-                        const uint32_t i = min(pa, pc), j = max(pa, pc);
-                        hist += 1u << (10 * (G.W[i * kU + j] >> 13));
-                    }
-                    G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, wgt * G.clsw[pp], pp * (kTPitch * 2));
-                    if (hist) atomicAdd(&G.PD[G.pd_base[s] + nboth + ai].y, hist);
-                    if (((bsuit >> (4 * s)) & 15u) == 3) G.HA[ai * 13 + y] = hist;
+                    const uint32_t hist = (G.u[y] - ((sm >> y) & 1u)) * G.clsw[pp];
+                    G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, hist, pp * (kTPitch * 2));
+                    if (s == ms) G.HA[ai * 13 + y] = hist;
                 } else {                                           // undo step for a rank pair, neither card in s
                     const uint32_t pp = t - (nboth + 14u * nsu);
                     const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
@@ -409,6 +415,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             }
         }
+        HOLDEM_PROF(1)
         group_sync(gid);                                                                            // (D)
         mbar_wait(bar1_s, parity);                                     // T has landed
         parity ^= 1u;
@@ -473,7 +480,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         }
                         const uint32_t ci = G.code[i], cj = G.code[j];
                         const uint32_t ri = ci >> 2, rj = cj >> 2;
-                        our = G.W[i * kU + j] & 0x1FFFu;
+                        {   // our rank on board + this runout: a suited-table rank when it completes our flush
+                            const uint32_t fb = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
+                            our = (int)__popc(fb) >= (int)fneed ? (uint32_t)S.flush[fold(hbmask | fb)] : (uint32_t)G.our7nf[tri(rj) + ri];
+                        }
                         qbits = ((ci & 3u) == s ? 1u << ri : 0u) | ((cj & 3u) == s ? 1u << rj : 0u);
                         ppq = tri(rj) + ri;
                         wl = 1;
@@ -540,9 +550,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
                         if (qi < nq && !((qb2 >> (ra + 17)) & 1u)) {
                             const uint32_t rf = lds_u16(flush_s + (fqf ^ (2u * fold(1u << ra))));
-                            const uint32_t i = min(pa, zpos), j = max(pa, zpos);
-                            const uint32_t cl = G.W[i * kU + j] >> 13;
                             const uint32_t pp = tri(max(ra, rz)) + min(ra, rz);
+                            const uint32_t cl = G.clsr[pp];            // {a in s, z outside s}: no flopped flush
                             const uint32_t rn = lds_u16(tq_s + pp * (kTPitch * 2));
                             const uint32_t cr = G.clsr[pp];
 #pragma unroll
