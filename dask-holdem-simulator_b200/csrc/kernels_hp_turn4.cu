@@ -42,7 +42,6 @@ struct Turn4Group {
     uint16_t opp6nf[96];               // non-flush 6-card rank of board + rank pair (row of board4_opp6)
     uint16_t our7nf[16];               // non-flush rank of hole + board + river rank (row of own6_our7)
     unsigned long long bar[2];         // mbarriers: [0] the two small rows, [1] T
-    uint8_t W[kUT * kUT + 4];          // [i*46+j], i<j: turn class of the pair as a holding
     uint16_t O7[48];                   // our final rank per river card (position)
     uint32_t ext[48];                  // river cards that give us a flush: rank | our7 << 8
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr
@@ -263,17 +262,17 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             }
         }
         tsync(gid);                                                                                 // (B)
+        // the suit in which we can still make a flush (>= 4 of hole + board) and the one with >= 3 board cards
+        const uint32_t m3 = (bsuit + 0x5555u) & 0x8888u;
+        const uint32_t ms3 = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
+        const uint32_t mb = m3 ? (bsuit >> (4 * ms3)) & 15u : 0u;                // 3 or 4 board cards of that suit
         {
             mbar_wait(bar0_s, parity);
             const uint32_t ours_now = G.ours_now;
-            // the suit in which we can still make a flush (>= 4 of hole + board) and the one with >= 3 board cards
             const uint32_t f4 = (hsuit + 0x4444u) & 0x8888u;
             const uint32_t fs = f4 ? (uint32_t)(__ffs(f4) - 1) >> 2 : 4u;
-            const bool own_flush_any = f4 && ((hsuit >> (4 * fs)) & 15u) >= 5;   // cannot happen unpaired with ours_now flush; kept exact
+            const bool own_flush_any = f4 && ((hsuit >> (4 * fs)) & 15u) >= 5;
             const uint32_t hbmask = f4 ? (uint32_t)(known >> (13 * fs)) & 0x1FFFu : 0u;
-            const uint32_t m3 = (bsuit + 0x5555u) & 0x8888u;
-            const uint32_t ms3 = m3 ? (uint32_t)(__ffs(m3) - 1) >> 2 : 4u;
-            const uint32_t mb = m3 ? (bsuit >> (4 * ms3)) & 15u : 0u;            // 3 or 4 board cards of that suit
             const uint32_t mbmask = m3 ? G.bmask[ms3] : 0u;
             // ---- our final rank per river card -----------------------------------------------------------------------------------
             if (tid < (uint32_t)kUT) {
@@ -286,37 +285,36 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
                 G.O7[tid] = (uint16_t)our7;
             }
-            // ---- turn class of every unseen pair as a holding ---------------------------------------------------------------------
-            uint32_t c0 = 0, c1 = 0, c2 = 0;
-            for (uint32_t p = tid; p < (uint32_t)kPairsT; p += kGT) {
-                const uint32_t pr = S.pairs[p];
-                const uint32_t i = pr & 0xFFu, j = pr >> 8;
-                const uint32_t ci = G.code[i], cj = G.code[j];
-                const uint32_t ri = ci >> 2, rj = cj >> 2;
-                uint32_t cls = G.clsr[tri(rj) + ri];
-                const uint32_t pbits = ((ci & 3u) == ms3 ? 1u << ri : 0u) | ((cj & 3u) == ms3 ? 1u << rj : 0u);
-                if (mb + (uint32_t)__popc(pbits) >= 5) {         // the holding already has a flush on the turn
-                    const uint32_t opp6 = S.flush[fold(mbmask | pbits)];
-                    cls = ours_now < opp6 ? 0u : (ours_now == opp6 ? 1u : 2u);
-                }
-                c0 += cls == 0; c1 += cls == 1; c2 += cls == 2;
-                G.W[i * kUT + j] = (uint8_t)cls;
+            // ---- hand strength: opponent holdings by turn class, from rank pairs; holdings that already hold a flush (both cards
+            //      in a suit with three board cards, or one card in a suit with four) are moved to their true class ---------------
+            for (uint32_t pp = tid; pp < (uint32_t)kPPT; pp += kGT) {
+                const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
+                const uint32_t ux = G.u[x], uy = G.u[y];
+                const uint32_t cnt = x != y ? ux * uy : (ux ? choose2u(ux) : 0u);
+                const uint32_t cl = G.clsr[pp];
+                if (cnt && cl < 3) atomicAdd(&G.cnt[6 + cl], cnt);
             }
-            c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
-            c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
-            c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
-            if (lane == 0) { atomicAdd(&G.cnt[6], c0); atomicAdd(&G.cnt[7], c1); atomicAdd(&G.cnt[8], c2); }
-            // ---- the "one card a in s" steps: x now, the class histogram over c is accumulated in the next phase ------------------
-            {
-                const uint32_t s = tid >> 4, ai = tid & 15u;
-                if (((bsuit >> (4 * s)) & 15u) >= 3 && ai < G.ns[s]) {
-                    const uint32_t ra = G.code[G.Ls[s][ai]] >> 2;
-                    G.PD[G.pd_base[s] + choose2u(G.ns[s]) + ai] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, 0u, 0u);
+            if (ms3 < 4) {
+                const uint32_t nsu = G.ns[ms3], nns = kUT - nsu, nboth = choose2u(nsu);
+                const uint32_t total = mb == 4 ? nboth + nsu * nns : nboth;
+                for (uint32_t t = tid; t < total; t += kGT) {
+                    uint32_t ra, rb, bits;
+                    if (t < nboth) {
+                        const uint32_t pr = S.pairs[t];
+                        ra = G.code[G.Ls[ms3][pr & 0xFFu]] >> 2; rb = G.code[G.Ls[ms3][pr >> 8]] >> 2;
+                        bits = (1u << ra) | (1u << rb);
+                    } else {
+                        const uint32_t t2 = t - nboth, a = t2 / nns, z = t2 - a * nns;
+                        const uint32_t r1 = G.code[G.Ls[ms3][a]] >> 2, r2 = G.code[G.Lns[ms3][z]] >> 2;
+                        ra = min(r1, r2); rb = max(r1, r2);
+                        bits = 1u << r1;
+                    }
+                    const uint32_t opp6 = S.flush[fold(mbmask | bits)];
+                    const uint32_t cls = ours_now < opp6 ? 0u : (ours_now == opp6 ? 1u : 2u);
+                    atomicAdd(&G.cnt[6 + cls], 1u);
+                    atomicSub(&G.cnt[6 + G.clsr[tri(rb) + ra]], 1u);
                 }
             }
-        }
-        tsync(gid);                                                                                 // (C)
-        {
             // ---- step descriptors of the flush part (same layout as the flop kernel) -------------------------------------------------
             const uint32_t total = G.pd_total;
             for (uint32_t e = tid; e < total; e += kGT) {
@@ -326,29 +324,39 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     if (G.pd_len[q] && e >= G.pd_base[q]) s = q;
                 uint32_t t = e - G.pd_base[s];
                 const uint32_t nsu = G.ns[s], nboth = choose2u(nsu), sm = G.smask[s];
+                const uint32_t bs = (bsuit >> (4 * s)) & 15u;
                 if (t < nboth) {
                     const uint32_t pr = S.pairs[t];
-                    const uint32_t pa = G.Ls[s][pr & 0xFFu], pb = G.Ls[s][pr >> 8];
-                    const uint32_t ra = G.code[pa] >> 2, rb = G.code[pb] >> 2;
-                    const uint32_t cls = G.W[pa * kUT + pb];
+                    const uint32_t ra = G.code[G.Ls[s][pr & 0xFFu]] >> 2, rb = G.code[G.Ls[s][pr >> 8]] >> 2;
                     const uint32_t pp = tri(rb) + ra, bits = (1u << ra) | (1u << rb);
-                    G.PD[e] = make_uint4((bits << 17) | (2u * fold(bits)), 1u << (10 * cls), G.clsw[pp], pp * 32u);
-                } else if (t < nboth + nsu) {
-                } else if (t < nboth + 14u * nsu) {
-                    t -= nboth + nsu;
-                    const uint32_t ai = t / 13u, y = t - 13u * ai;
-                    const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
-                    const uint32_t pp = tri(max(ra, y)) + min(ra, y);
-                    uint32_t wgt = 0, hist = 0;
-                    for (uint32_t pc = G.st[y]; pc < G.st[y + 1]; ++pc) {
-                        if ((G.code[pc] & 3u) == s) continue;
-                        ++wgt;
-                        const uint32_t i = min(pa, pc), j = max(pa, pc);
-                        hist += 1u << (10 * G.W[i * kUT + j]);
+                    uint32_t cls = G.clsr[pp];
+                    if (bs >= 3) {                                 // the holding already has a flush on the turn
+                        const uint32_t opp6 = S.flush[fold(G.bmask[s] | bits)];
+                        cls = ours_now < opp6 ? 0u : (ours_now == opp6 ? 1u : 2u);
                     }
-                    G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u, wgt * G.clsw[pp], pp * 32u);
-                    if (hist) atomicAdd(&G.PD[G.pd_base[s] + nboth + ai].y, hist);
-                    if (((bsuit >> (4 * s)) & 15u) == 4) G.HA[ai * 13 + y] = hist;
+                    G.PD[e] = make_uint4((bits << 17) | (2u * fold(bits)), 1u << (10 * cls), G.clsw[pp], pp * 32u);
+                } else if (t < nboth + 14u * nsu) {
+                    // one card a in s (t < nboth + nsu: the add step of a, all c at once; else the undo step of (a, rank y of c)):
+                    // the class of {a, c} is the flush class of a when the board has four of s, else it depends on ranks alone
+                    const bool add_step = t < nboth + nsu;
+                    const uint32_t t2 = t - nboth - (add_step ? 0u : nsu);
+                    const uint32_t ai = add_step ? t2 : t2 / 13u, y0 = add_step ? 0u : t2 - 13u * ai, y1 = add_step ? 13u : y0 + 1u;
+                    const uint32_t ra = G.code[G.Ls[s][ai]] >> 2;
+                    uint32_t fcw = 0;
+                    if (bs == 4) {
+                        const uint32_t opp6 = S.flush[fold(G.bmask[s] | (1u << ra))];
+                        fcw = 1u << (10 * (ours_now < opp6 ? 0u : (ours_now == opp6 ? 1u : 2u)));
+                    }
+                    uint32_t hist = 0;
+                    for (uint32_t y = y0; y < y1; ++y)
+                        hist += (G.u[y] - ((sm >> y) & 1u)) * (bs == 4 ? fcw : G.clsw[tri(max(ra, y)) + min(ra, y)]);
+                    if (add_step) G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), hist, 0u, 0u);
+                    else {
+                        const uint32_t pp = tri(max(ra, y0)) + min(ra, y0);
+                        G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), 0u,
+                                             (G.u[y0] - ((sm >> y0) & 1u)) * G.clsw[pp], pp * 32u);
+                        if (bs == 4) G.HA[ai * 13 + y0] = hist;
+                    }
                 } else {
                     const uint32_t pp = t - (nboth + 14u * nsu);
                     const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
@@ -458,8 +466,13 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                                 ha = G.HA[ai * 13 + rz];
                                 cw = wl * G.clsw[pp];
                             } else {
-                                const uint32_t i = min(pa, zpos), j = max(pa, zpos);
-                                ha = 1u << (10 * G.W[i * kUT + j]);
+                                uint32_t cl = G.clsr[pp];                    // {a in s, z outside s}: a flush already when the board
+                                if (mb == 4 && s == ms3) {                   // has four of s
+                                    const uint32_t opp6 = lds_u16(flush_s + 2u * fold(G.bmask[s] | (1u << ra)));
+                                    const uint32_t on = G.ours_now;
+                                    cl = on < opp6 ? 0u : (on == opp6 ? 1u : 2u);
+                                }
+                                ha = 1u << (10 * cl);
                                 cw = G.clsw[pp];
                             }
 #pragma unroll
