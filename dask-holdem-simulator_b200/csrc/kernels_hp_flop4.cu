@@ -36,9 +36,8 @@
 // rank bits) and the colex pair list, then per group (~33 KB): T[91][91] u16 (symmetric) = non-flush rank of board + rank
 // pair q + rank pair p, our7nf[91] and opp5nf[91] -- three rows of direct-indexed tables (tables.h: board_t, own_our7,
 // board_opp5; indexed by the board's / the five known cards' rank multiset) that one thread fetches with cp.async.bulk
-// onto mbarriers at the start of the situation, so the kernel performs no hash lookups at all; W[47][47] u16 = our7 |
-// cls << 13 per unseen pair; the runouts that give us a flush; PD[<=320] 16-byte step descriptors of the flush part, per
-// suit ordered
+// onto mbarriers at the start of the situation, so the kernel performs no hash lookups at all; the runouts that give us a
+// flush; PD[<=320] 16-byte step descriptors of the flush part, per suit ordered
 // [both cards in s | one card a in s | undo steps (a, rank of c) | undo steps (rank pair), no card in s].
 // Flush part mapping: a warp task = 32 runouts Q of one (suit, cards-of-Q-in-suit) group x a segment of <= 64 steps;
 // lanes own Q (its rank, suit mask and T row live in registers), the warp walks the steps with one broadcast 16-byte load
@@ -109,6 +108,7 @@ __device__ __forceinline__ void group_sync(uint32_t gid) { group_sync_n<kGroupTh
 
 }  // namespace
 
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
                         int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers) {
@@ -141,7 +141,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     int saw_other = 0;
     uint32_t t_prev = 0;
 #define HOLDEM_PROF(slot)                                                        \
-    if (prof != nullptr && tid == 0) {                                           \
+    if (kProf && tid == 0) {                                                     \
         const uint32_t t_now = (uint32_t)clock64();                              \
         G.prof[slot] += t_now - t_prev;                                          \
         t_prev = t_now;                                                          \
@@ -149,7 +149,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 
     for (int64_t idx = (int64_t)blockIdx.x * kGroups + gid; idx < n; idx += (int64_t)gridDim.x * kGroups) {
         group_sync(gid);                                                                            // (A)
-        if (prof != nullptr && tid == 0) t_prev = (uint32_t)clock64();
+        if (kProf && tid == 0) t_prev = (uint32_t)clock64();
         uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
         uint32_t cb[8];
 #pragma unroll
@@ -498,7 +498,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // steps [0, nboth + n_s) have an add part (holdings with both cards in s, or one card a in s); the ones behind them
                 // are rank-level undo steps: no suited-table gather, half the compares
                 const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
-#pragma unroll 4
+#pragma unroll 2
                 for (uint32_t t = p0; t < split; ++t, ++pd) {
                     const uint4 d = *pd;
                     // fold() is XOR-linear and the step's cards of s are disjoint from board + runout when the step is valid
@@ -506,7 +506,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t rn = lds_u16(tq_s + d.w);
                     flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
                 }
-#pragma unroll 4
+#pragma unroll 2
                 for (uint32_t t = split; t < p1; ++t, ++pd) {
                     const uint4 d = *pd;
                     undo_step(sL, sG, our, lds_u16(tq_s + d.w), d.x, qb2, d.z, one);
@@ -648,7 +648,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     }
 #undef HOLDEM_PROF
     if (saw_other && tid == 0) atomicOr(other_rows, saw_other);
-    if (prof != nullptr && tid == 0)
+    if (kProf && tid == 0)
         for (int k = 0; k < 4; ++k) atomicAdd(prof + k, (unsigned long long)G.prof[k]);
 }
 
@@ -656,13 +656,16 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Flop4Smem);
-    cudaError_t e = cudaFuncSetAttribute(hp_flop_treys_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = prof ? cudaFuncSetAttribute(hp_flop_treys_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(hp_flop_treys_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t blocks = sms;
     if (blocks * kGroups > n) blocks = (n + kGroups - 1) / kGroups;
     e = cudaMemsetAsync(other_rows_flag, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    hp_flop_treys_v4_kernel<<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers);
+    // the phase clocks are compiled out of the production instance: the kernel is sensitive to its code size
+    if (prof) hp_flop_treys_v4_kernel<true><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers);
+    else hp_flop_treys_v4_kernel<false><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers);
     return cudaGetLastError();
 }
 

@@ -393,7 +393,13 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t s = G.g_sq[g] & 3u, qtype = (G.g_sq[g] >> 2) & 3u;
                 const bool rank_lanes = (G.g_sq[g] >> 4) != 0;
                 const uint32_t p0 = seg * seglen, p1 = min(np, p0 + seglen);
-                const uint32_t qi = chunk * 32 + lane;
+                // a chunk with few river lanes left (<= 16) is spread over the warp: each gets 32 / p2 lanes, lane stripe k of them
+                // takes the steps p0 + k, p0 + k + nstr, ...
+                const uint32_t live = min(32u, nq - chunk * 32);
+                const uint32_t p2 = live > 16 ? 32u : (live <= 1 ? 1u : 1u << (32 - __clz(live - 1)));
+                const uint32_t nstr = 32u / p2, stripe = lane / p2;
+                const bool primary = stripe == 0;                 // the lane that also does the per-task extras
+                const uint32_t qi = (lane & (p2 - 1)) < live ? chunk * 32 + (lane & (p2 - 1)) : nq;
                 const uint32_t nsu = G.ns[s], sm = G.smask[s];
                 uint32_t our = 0, fqf = 0, qb2 = 0, zpos = 0xFFu, rz = 0, qcol = 0, wl = 0, rq = 99;
                 if (qi < nq) {
@@ -425,18 +431,28 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 uint32_t aL = 0, aG = 0, sL = 0, sG = 0;
                 // steps [0, nboth + n_s) have an add part (holdings with both cards in s, or one card a in s); the ones behind them
                 // are rank-level undo steps: no suited-table gather, half the compares
-                const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
+                if (nstr > 1) {
+                    pd += stripe;
+                    for (uint32_t t = p0 + stripe; t < p1; t += nstr, pd += nstr) {
+                        const uint4 d = *pd;
+                        const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
+                        const uint32_t rn = lds_u16(tq_s + d.w);
+                        flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
+                    }
+                } else {
+                    const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
 #pragma unroll 4
-                for (uint32_t t = p0; t < split; ++t, ++pd) {
-                    const uint4 d = *pd;
-                    const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
-                    const uint32_t rn = lds_u16(tq_s + d.w);
-                    flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
-                }
+                    for (uint32_t t = p0; t < split; ++t, ++pd) {
+                        const uint4 d = *pd;
+                        const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
+                        const uint32_t rn = lds_u16(tq_s + d.w);
+                        flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
+                    }
 #pragma unroll 4
-                for (uint32_t t = split; t < p1; ++t, ++pd) {
-                    const uint4 d = *pd;
-                    undo_step(sL, sG, our, lds_u16(tq_s + d.w), d.x, qb2, d.z, one);
+                    for (uint32_t t = split; t < p1; ++t, ++pd) {
+                        const uint4 d = *pd;
+                        undo_step(sL, sG, our, lds_u16(tq_s + d.w), d.x, qb2, d.z, one);
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -444,7 +460,7 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     accG[c] += (((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu)) * wl;
                 }
                 const uint32_t need = 5u - (((bsuit >> (4 * s)) & 15u) + qtype);
-                if (seg == 0 && need == 0 && qi < nq) {
+                if (seg == 0 && need == 0 && qi < nq && primary) {
                     const uint32_t rf = lds_u16(flush_s + fqf);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -457,7 +473,7 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     // all wl cards of rank rz at once = the class histogram HA[a][rz] and wl undo steps of (ra, rz))
                     for (uint32_t ai = 0; ai < nsu; ++ai) {
                         const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
-                        if (wl != 0) {
+                        if (wl != 0 && primary) {
                             const uint32_t rf = lds_u16(flush_s + (fqf ^ (2u * fold(1u << ra))));
                             const uint32_t pp = tri(max(ra, rz)) + min(ra, rz);
                             const uint32_t rn = lds_u16(tq_s + pp * 32u);
