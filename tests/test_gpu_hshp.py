@@ -320,3 +320,35 @@ def test_hp_turn_variants_agree_and_match_oracle(hb, oracle):
     d_big = torch.from_numpy(big).cuda()
     assert torch.equal(hb.hand_potential_counts(d_big, "treys", turn_variant=4),
                        hb.hand_potential_counts(d_big, "treys", turn_variant=3))
+
+
+def test_hp_batch_peers_replicates_rows(hb, oracle):
+    """holdem_hp_batch_peers: the kernels store every result row into the peer buffers as well (over NVLink when the peers are
+    other GPUs' symmetric memory; here two more buffers on the same device stand in).  Mixed streets, both modes, with a row
+    offset into the peer buffers as the sharded layer uses it."""
+    import ctypes
+    from holdem_b200 import _lib
+    from holdem_b200.api import _enter
+    parts = [hb.random_situations(300, seed=901), hb.random_situations(200, seed=902, n_board=4),
+             hb.random_situations(50, seed=903, n_board=5)]
+    sit = np.concatenate(parts)
+    sit = sit[np.random.default_rng(9).permutation(len(sit))]
+    sit[7, 1] = sit[7, 0]                                  # one malformed row: must be marked in every buffer
+    n, off = len(sit), 11
+    d_sit = torch.from_numpy(sit).cuda()
+    for mode in ("treys", "reference"):
+        sub = d_sit if mode == "treys" else d_sit[:96].contiguous()
+        m = sub.shape[0]
+        want = hb.hand_potential_counts(sub, mode)
+        mine = torch.zeros((m, 16), dtype=torch.int32, device="cuda")
+        peers = [torch.full((m + 2 * off, 16), 7, dtype=torch.int32, device="cuda") for _ in range(2)]
+        lib, st = _enter(sub)
+        arr = (ctypes.c_void_p * 2)(*[p.data_ptr() + off * 64 for p in peers])
+        _lib.check(lib.holdem_hp_batch_peers(sub.data_ptr(), m, hb.mode_id(mode), mine.data_ptr(), arr, 2, st))
+        torch.cuda.synchronize()
+        assert torch.equal(mine, want), mode
+        for p in peers:
+            assert torch.equal(p[off:off + m], want), mode
+            assert bool((p[:off] == 7).all()) and bool((p[off + m:] == 7).all()), mode   # nothing outside the block is touched
+    assert np.array_equal(_u32(want[8:32]), oracle.hp_batch(sit[8:32], "reference"))       # (row 7 is the malformed one)
+    assert bool((want[7] == -1).all())
