@@ -364,10 +364,16 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
 // Treys mode: the deduplicating flop kernel takes every 3-card-board row and flags what else it saw; turn rows go to the
 // deduplicating turn kernel, river rows (HS only) to the plain-enumeration kernel.  Both exit at once when not needed.  Reference mode: plain enumeration only.
 static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out,
-                               cudaStream_t st, const PeerOut &peers = PeerOut{}) {
+                               cudaStream_t st, const PeerOut &peers = PeerOut{}, int **flag_out = nullptr) {
+    // flag word of this call: bit 0 / 1 = the flop kernel met turn / river rows, bit 2 = some kernel marked a malformed row
+    // (flag_out receives its address when every kernel of the call maintains bit 2, else nullptr)
     if (mode == HOLDEM_MODE_REFERENCE) {
-        cudaError_t e = launch_hp_ref(S.T, d_sit, n, d_out, S.sms, st);
+        int *rflag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+        cudaError_t e = cudaMemsetAsync(rflag, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
+        e = launch_hp_ref(S.T, d_sit, n, d_out, S.sms, rflag, st);
+        if (e != cudaSuccess) return e;
+        if (flag_out) *flag_out = rflag;
         return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, nullptr, st);
     }
     int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
@@ -385,6 +391,7 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     if (e != cudaSuccess) return e;
     e = launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
     if (e != cudaSuccess) return e;
+    if (flag_out) *flag_out = fused ? flag : nullptr;
     // river rows only (exits at once when there are none); every row when an earlier kernel was selected
     return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, fused ? flag : nullptr, st);
 }
@@ -484,9 +491,13 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
             if ((rc = ensure_host_buffers(*S, 0, (size_t)n * 8))) return rc;
             cudaStream_t st = S->streams[0];
             CUDA_TRY(cudaMemcpyAsync(S->d_buf, h_sit, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(hp_dispatch(*S, S->d_buf, n, mode, (uint32_t *)ao.devicePointer, st));
+            int *d_flag = nullptr;
+            int h_flag = 4;
+            CUDA_TRY(hp_dispatch(*S, S->d_buf, n, mode, (uint32_t *)ao.devicePointer, st, PeerOut{}, &d_flag));
+            if (d_flag) CUDA_TRY(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             done = true;
+            if (!(h_flag & 4)) return HOLDEM_OK;      // no kernel marked a malformed row: nothing to look for in the results
         }
     }
     if (!done) {

@@ -175,6 +175,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         ok = ok && __popcll(known) == 5;
         if (!ok) {
+            if (tid == 0) atomicOr(other_rows, 4);          // bit 2: a malformed row was marked
             if (tid < 16) {
                 out[idx * 16 + tid] = 0xFFFFFFFFu;
 #pragma unroll

@@ -65,7 +65,8 @@ __device__ __forceinline__ LitHand r_one_card(uint32_t c) {
 }  // namespace
 
 __global__ void __launch_bounds__(kRThreads)
-hp_ref_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T, uint32_t one) {
+hp_ref_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T, uint32_t one,
+              int *__restrict__ bad_flag) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RefSmem &S = *reinterpret_cast<RefSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -100,6 +101,7 @@ hp_ref_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__
         known |= bset;
         ok = ok && nb >= 3 && __popcll(known) == nb + 2;
         if (!ok) {
+            if (tid == 0 && bad_flag != nullptr) atomicOr(bad_flag, 4);   // bit 2: a malformed row was marked
             if (tid < 16) out[idx * 16 + tid] = 0xFFFFFFFFu;
             continue;
         }
@@ -351,7 +353,8 @@ hp_ref_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__
     }
 }
 
-cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st) {
+cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *bad_flag,
+                          cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(RefSmem);
     cudaError_t e = cudaFuncSetAttribute(hp_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -364,7 +367,7 @@ cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uin
     }
     int64_t blocks = (int64_t)sms * bps;
     if (blocks > n) blocks = n;
-    hp_ref_kernel<<<(int)blocks, kRThreads, smem, st>>>(sit, n, out, T, 1u);
+    hp_ref_kernel<<<(int)blocks, kRThreads, smem, st>>>(sit, n, out, T, 1u, bad_flag);
     return cudaGetLastError();
 }
 

@@ -79,7 +79,7 @@ __device__ __forceinline__ void tsync(uint32_t gid) { group_sync_n<kGT>(gid); }
 
 __global__ void __launch_bounds__(kThreadsT, 1)
 hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                        const int *__restrict__ run_flag, uint32_t one, PeerOut peers) {
+                        int *__restrict__ run_flag, uint32_t one, PeerOut peers) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     if (run_flag != nullptr && !(*run_flag & 1)) return;   // the flop kernel saw no turn rows
     Turn4Smem &S = *reinterpret_cast<Turn4Smem *>(smem_raw);
@@ -133,6 +133,7 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         ok = ok && __popcll(known) == 6;
         if (!ok) {
+            if (tid == 0 && run_flag != nullptr) atomicOr(run_flag, 4);   // bit 2: a malformed row was marked
             if (tid < 16) {
                 out[idx * 16 + tid] = 0xFFFFFFFFu;
 #pragma unroll
@@ -575,7 +576,7 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 }
 
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    const int *run_flag, const PeerOut &peers, cudaStream_t st) {
+                                    int *run_flag, const PeerOut &peers, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Turn4Smem);
     static_assert(sizeof(Turn4Smem) <= 227 * 1024, "fifteen situation groups must fit the 227 KB of one CTA");

@@ -190,7 +190,7 @@ struct HpSmem {
 template <int MODE>
 __global__ void __launch_bounds__(kHpThreads)
 hp_direct_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                 const int *__restrict__ run_flag, int skip_boards) {
+                 int *__restrict__ run_flag, int skip_boards) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     HpSmem &S = *reinterpret_cast<HpSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -203,6 +203,7 @@ hp_direct_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restric
         Situation s = parse_situation(sit, idx);
         if (skip_boards && s.board[4] == 0xFFu) continue;  // 3- and 4-card boards are done by the flop / turn kernels
         if (!s.ok) {
+            if (tid == 0 && run_flag != nullptr) atomicOr(run_flag, 4);   // bit 2: a malformed row was marked
             if (tid < 16) out[idx * 16 + tid] = 0xFFFFFFFFu;
             continue;
         }
@@ -335,7 +336,7 @@ hp_direct_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restric
 }
 
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
-                             const int *run_flag, int skip_boards, cudaStream_t st) {
+                             int *run_flag, int skip_boards, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(HpSmem);
     cudaError_t e;

@@ -32,7 +32,7 @@ cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, i
 // run_flag: optional device int; the kernel exits at once unless bit 1 is set.  skip_boards: leave 3- and 4-card-board rows
 // alone (they belong to the flop / turn kernels).
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
-                             const int *run_flag, int skip_boards, cudaStream_t st);
+                             int *run_flag, int skip_boards, cudaStream_t st);
 // Treys-mode turn rows only; exits at once unless bit 0 of *run_flag is set (the flop kernel saw 4-card boards).
 cudaError_t launch_hp_turn_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                  const int *run_flag, cudaStream_t st);
@@ -48,13 +48,15 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
 
 // Rank-multiset turn kernel (kernels_hp_turn4.cu): same contract as launch_hp_turn_treys, bit-identical counts, the default.
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    const int *run_flag, const PeerOut &peers, cudaStream_t st);
+                                    int *run_flag, const PeerOut &peers, cudaStream_t st);
 // Copies result rows of `out` to the peers: all rows (run_flag == nullptr) or, when run_flag is given, the five-card-board rows
 // and only if bit 1 of *run_flag is set (the rows the plain-enumeration kernel produced).
 cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *out, const PeerOut &peers, int sms,
                                  const int *run_flag, cudaStream_t st);
 
 // HOLDEM_MODE_REFERENCE, all streets: 4-set walk for the regular runouts + arithmetic ranking of the irregular ones.
-cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
+// bad_flag: optional device int, bit 2 is set when a malformed row was marked (every HP kernel does this on its flag word).
+cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *bad_flag,
+                          cudaStream_t st);
 
 }  // namespace holdem

@@ -229,6 +229,12 @@ def test_host_entry_chunked_pipeline_matches_device_entry(hb):
         pin_out = torch.zeros((n, 16), dtype=torch.int32, pin_memory=True)
         got = hb.hand_potential_counts_host(pin_in.numpy(), mode, out=pin_out.numpy().view(np.uint32))
         assert np.array_equal(got, dev), mode
+        keep = pin_in.numpy()[n - 3].copy()            # a malformed row far into the batch is reported on this path too
+        pin_in.numpy()[n - 3, 1] = pin_in.numpy()[n - 3, 0]   # (the kernels raise a device flag; no host-side scan otherwise)
+        with pytest.raises(hb.HoldemError):
+            hb.hand_potential_counts_host(pin_in.numpy(), mode, out=pin_out.numpy().view(np.uint32))
+        assert bool((pin_out[n - 3] == -1).all())
+        pin_in.numpy()[n - 3] = keep
     big = hb.random_situations((1 << 20) + 12345, seed=405, n_board=5)
     assert np.array_equal(hb.hand_strength_counts_host(big, "treys"),
                           _u32(hb.hand_strength_counts(torch.from_numpy(big).cuda(), "treys")))
