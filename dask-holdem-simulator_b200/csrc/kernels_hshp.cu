@@ -9,6 +9,7 @@
 //                   independent second implementation the deduplicating flop / turn kernels (kernels_hp_flop.cu,
 //                   kernels_hp_turn.cu) are checked against, and the production path for HOLDEM_MODE_REFERENCE (all
 //                   streets) and for Treys-mode river rows (HS only).
+#include <cstdlib>
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -156,6 +157,8 @@ hs_kernel(const uint8_t *__restrict__ sit, int64_t n, int mode, uint32_t *__rest
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                             cudaStream_t st) {
     if (n == 0) return cudaSuccess;
+    static const bool old_kernel = getenv("HOLDEM_HS_KERNEL") && atoi(getenv("HOLDEM_HS_KERNEL")) == 1;
+    if (mode == kModeTreys && !old_kernel) return launch_hs_treys_v4(T, sit, n, out, sms, st);
     int64_t blocks = (n + kHsWarps - 1) / kHsWarps;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     hs_kernel<<<(int)blocks, kHsWarps * 32, 0, st>>>(sit, n, mode, out, T);

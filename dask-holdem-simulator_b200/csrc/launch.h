@@ -29,6 +29,9 @@ cudaError_t launch_int_issue(int iters, int mix, int blocks, int threads, cudaSt
 
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                             cudaStream_t st);
+// Treys-mode hand strength from rank pairs (kernels_hs4.cu): same results, what launch_hs_batch runs for HOLDEM_MODE_TREYS
+// unless HOLDEM_HS_KERNEL=1 selects the holding-by-holding kernel.
+cudaError_t launch_hs_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
 // run_flag: optional device int; the kernel exits at once unless bit 1 is set.  skip_boards: leave 3- and 4-card-board rows
 // alone (they belong to the flop / turn kernels).
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,

@@ -358,3 +358,21 @@ def test_hp_batch_peers_replicates_rows(hb, oracle):
             assert bool((p[:off] == 7).all()) and bool((p[off + m:] == 7).all()), mode   # nothing outside the block is touched
     assert np.array_equal(_u32(want[8:32]), oracle.hp_batch(sit[8:32], "reference"))       # (row 7 is the malformed one)
     assert bool((want[7] == -1).all())
+
+
+def test_hs_flush_board_textures_match_oracle(hb, oracle):
+    """Treys-mode hand strength comes from rank pairs plus a correction for holdings that make a flush with the board: boards with
+    three, four and five cards of a suit (hole cards inside and outside it, paired boards) against the oracle, row by row."""
+    cases = [([14, 1], [31, 32, 33]), ([0, 1], [2, 3, 4]), ([13, 26], [2, 3, 4]), ([0, 1], [2, 3, 4, 5]), ([13, 26], [2, 3, 4, 5]),
+             ([12, 11], [2, 3, 4, 18]), ([25, 38], [2, 3, 4, 18]), ([39, 1], [41, 42, 43, 44]), ([0, 1], [2, 3, 4, 5, 6]),
+             ([13, 26], [2, 3, 4, 5, 7]), ([12, 25], [0, 2, 4, 6, 8]), ([11, 13], [0, 2, 4, 6, 21]), ([0, 13], [26, 27, 28, 29, 30]),
+             ([20, 39], [40, 13, 35, 30, 28]), ([5, 18], [31, 44, 6, 19, 32]), ([50, 51], [49, 48, 47, 46, 45]),
+             ([12, 10], [51, 50, 49, 48, 47]), ([0, 14], [39, 40, 41, 42, 1])]
+    for nb in (3, 4, 5):
+        sub = [c for c in cases if len(c[1]) == nb]
+        sit = np.concatenate([hb.pack_situations([c[0] for c in sub], [c[1] for c in sub]),
+                              hb.random_situations(2000, seed=930 + nb, n_board=nb)])
+        got = _u32(hb.hand_strength_counts(torch.from_numpy(sit).cuda(), "treys"))
+        want = oracle.hs_batch(sit, "treys")
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (nb, sit[bad[:5]], got[bad[:5]], want[bad[:5]])
