@@ -91,7 +91,6 @@ struct Flop4Group {                    // one situation in flight
     uint8_t Ls[4][16];                 // positions of the unseen cards of suit s
     uint8_t Lns[4][48];                // positions of the unseen cards not of suit s
     uint8_t ns[4];
-    uint8_t st[16];                    // first position of each rank
     uint8_t u[16];                     // unseen cards per rank
     uint8_t clsr[96];                  // per rank pair: flop class from ranks alone (3 = impossible pair)
 };
@@ -196,12 +195,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             const uint32_t ltm = (1u << lane) - 1u;
             if (in0) G.code[__popc(m0 & ltm)] = (uint8_t)lane;
             if (in1) G.code[__popc(m0) + __popc(m1 & ltm)] = (uint8_t)(lane + 32);
-            {   // rank r owns codes 4r..4r+3: start position = unseen codes below 4r
+            {   // rank r owns codes 4r..4r+3
                 const uint32_t c4 = 4 * min(lane, 13u);
-                const uint32_t below = c4 < 32 ? __popc(m0 & ((1u << c4) - 1u))
-                                               : __popc(m0) + __popc(m1 & ((1u << (c4 - 32)) - 1u));
                 const uint32_t cnt_r = lane < 13 ? (c4 < 32 ? __popc((m0 >> c4) & 15u) : __popc((m1 >> (c4 - 32)) & 15u)) : 0u;
-                if (lane < 14) G.st[lane] = (uint8_t)below;
                 if (lane < 13) G.u[lane] = (uint8_t)cnt_r;
                 const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 10 ? cnt_r << (3 * lane) : 0u);
                 const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (lane >= 10 && lane < 13) ? cnt_r << (3 * lane - 30) : 0u);

@@ -61,7 +61,6 @@ struct Turn4Group {
     uint8_t Ls[4][16];
     uint8_t Lns[4][48];
     uint8_t ns[4];
-    uint8_t st[16];
     uint8_t u[16];
     uint8_t clsr[96];
 };
@@ -156,10 +155,7 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             if (in1) G.code[__popc(m0) + __popc(m1 & ltm)] = (uint8_t)(lane + 32);
             {
                 const uint32_t c4 = 4 * min(lane, 13u);
-                const uint32_t below = c4 < 32 ? __popc(m0 & ((1u << c4) - 1u))
-                                               : __popc(m0) + __popc(m1 & ((1u << (c4 - 32)) - 1u));
                 const uint32_t cnt_r = lane < 13 ? (c4 < 32 ? __popc((m0 >> c4) & 15u) : __popc((m1 >> (c4 - 32)) & 15u)) : 0u;
-                if (lane < 14) G.st[lane] = (uint8_t)below;
                 if (lane < 13) G.u[lane] = (uint8_t)cnt_r;
                 const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 10 ? cnt_r << (3 * lane) : 0u);
                 const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (lane >= 10 && lane < 13) ? cnt_r << (3 * lane - 30) : 0u);
