@@ -512,7 +512,7 @@ def main():
                                             "what": "same call with pageable numpy arrays: 16,384-row chunks through the library's "
                                                     "own pinned staging on two streams (two extra host memcpy per chunk)"}},
         "gpu_launches": 3 * args.steps,
-        "gpu_launches_note": "per step: hp_flop_treys_v4_kernel + hp_turn_treys_kernel + hp_direct_kernel (the last two "
+        "gpu_launches_note": "per step: hp_flop_treys_v4_kernel + hp_turn_treys_v4_kernel + hs_treys_v4_kernel<river rows> (the last two "
                              "exit at once when the batch holds no turn / river rows)",
         "other_implementations": alt,
         "roofline": roofline,

@@ -389,7 +389,10 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
                  : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st);
     if (e != cudaSuccess) return e;
-    e = launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st);
+    // five-card boards (hand strength only): the rank-pair kernel; HOLDEM_HS_KERNEL=1 keeps the holding-by-holding enumeration
+    static const bool old_hs = getenv("HOLDEM_HS_KERNEL") && atoi(getenv("HOLDEM_HS_KERNEL")) == 1;
+    e = old_hs ? launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st)
+               : launch_hp_river_rows(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
     if (flag_out) *flag_out = fused ? flag : nullptr;
     // river rows only (exits at once when there are none); every row when an earlier kernel was selected

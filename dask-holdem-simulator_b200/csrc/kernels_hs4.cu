@@ -32,8 +32,13 @@ __device__ __forceinline__ uint32_t cls_of(uint32_t ours, uint32_t theirs) {   /
 
 }  // namespace
 
+// kHpRows: second pass of holdem_hp_batch for the rows the flop / turn kernels left (five-card boards: hand strength only).
+// Writes 16-word HP rows (ahead tied behind | nine zeros | HPTotal | 5), skips every other row, exits at once unless bit 1 of
+// *run_flag is set and raises bit 2 when it marks a malformed row.
+template <bool kHpRows>
 __global__ void __launch_bounds__(kHs4Warps * 32)
-hs_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T) {
+hs_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T, int *__restrict__ run_flag) {
+    if (kHpRows && run_flag != nullptr && (*run_flag & 2) == 0) return;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_warps = (int64_t)gridDim.x * kHs4Warps;
     // the lane's three rank pairs
@@ -51,8 +56,9 @@ hs_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restr
         uint32_t cb[8];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cb[k] = (w.x >> (8 * k)) & 0xFFu; cb[4 + k] = (w.y >> (8 * k)) & 0xFFu; }
+        if (kHpRows && cb[6] == 0xFFu) continue;          // a flop or turn row: done by the HP kernels of those streets
         // board length: 3, 4 or 5 contiguous cards
-        const uint32_t nb = cb[5] == 0xFFu ? 3u : (cb[6] == 0xFFu ? 4u : 5u);
+        const uint32_t nb = kHpRows ? 5u : (cb[5] == 0xFFu ? 3u : (cb[6] == 0xFFu ? 4u : 5u));
         bool ok = true;
         uint64_t known = 0, bset = 0;
         uint32_t bsuit = 0;
@@ -71,7 +77,10 @@ hs_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restr
         }
         ok = ok && (uint32_t)__popcll(known) == nb + 2;
         if (!ok) {
-            if (lane < 3) out[idx * 3 + lane] = 0xFFFFFFFFu;
+            if (kHpRows) {
+                if (lane < 16) out[idx * 16 + lane] = 0xFFFFFFFFu;
+                if (lane == 0 && run_flag != nullptr) atomicOr(run_flag, 4);
+            } else if (lane < 3) out[idx * 3 + lane] = 0xFFFFFFFFu;
             continue;
         }
         // ---- table rows: lane 0 sorts the ranks and forms the multiset indices ------------------------------------------------
@@ -179,7 +188,12 @@ hs_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restr
         }
 #pragma unroll
         for (uint32_t c = 0; c < 3; ++c) acc[c] = __reduce_add_sync(0xFFFFFFFFu, acc[c]);
-        if (lane < 3) out[idx * 3 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
+        if (kHpRows) {
+            if (lane < 16) {
+                const uint32_t k = lane < 3 ? lane : (lane >= 12 && lane < 15 ? lane - 12 : 3u);
+                out[idx * 16 + lane] = k < 3 ? (k == 0 ? acc[0] : (k == 1 ? acc[1] : acc[2])) : (lane == 15 ? 5u : 0u);
+            }
+        } else if (lane < 3) out[idx * 3 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
     }
 }
 
@@ -187,7 +201,16 @@ cudaError_t launch_hs_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n
     if (n == 0) return cudaSuccess;
     int64_t blocks = (n + kHs4Warps - 1) / kHs4Warps;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-    hs_treys_v4_kernel<<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T);
+    hs_treys_v4_kernel<false><<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hp_river_rows(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *run_flag,
+                                 cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int64_t blocks = (n + kHs4Warps - 1) / kHs4Warps;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    hs_treys_v4_kernel<true><<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T, run_flag);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,9 @@ cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, i
 // Treys-mode hand strength from rank pairs (kernels_hs4.cu): same results, what launch_hs_batch runs for HOLDEM_MODE_TREYS
 // unless HOLDEM_HS_KERNEL=1 selects the holding-by-holding kernel.
 cudaError_t launch_hs_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
+// The same kernel as the last pass of holdem_hp_batch (treys mode): HP rows (hand strength only) for the five-card-board rows.
+cudaError_t launch_hp_river_rows(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *run_flag,
+                                 cudaStream_t st);
 // run_flag: optional device int; the kernel exits at once unless bit 1 is set.  skip_boards: leave 3- and 4-card-board rows
 // alone (they belong to the flop / turn kernels).
 cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
