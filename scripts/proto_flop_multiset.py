@@ -244,6 +244,85 @@ def flop_counts(hole, board):
     return row, n_items
 
 
+def turn_counts(hole, board):
+    """The same identity with four board cards and ONE river card q (kernels_hp_turn4.cu), in its plain form: generic sum over
+    (river card, rank pair) plus one add / undo item per (river card, holding) that makes a flush with board + q."""
+    known = set(hole) | set(board)
+    U = sorted((c for c in range(52) if c not in known), key=lambda c: (c % 13, c // 13))
+    n = len(U)
+    assert n == 46
+    rk = [c % 13 for c in U]
+    su = [c // 13 for c in U]
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    our7 = evaluate_rows([list(hole) + list(board) + [U[q]] for q in range(n)], 7)
+    opp6 = dict(zip(pairs, evaluate_rows([list(board) + [U[i], U[j]] for i, j in pairs], 6)))
+    ours_now = int(evaluate_rows([list(hole) + list(board)], 6)[0])
+    cls = {p: (0 if ours_now < v else (1 if ours_now == v else 2)) for p, v in opp6.items()}
+    tot = [sum(1 for p in pairs if cls[p] == i) for i in range(3)]
+    brk = [c % 13 for c in board]
+    u = [rk.count(r) for r in range(13)]
+    rank_pairs = [(x, y) for y in range(13) for x in range(y + 1)]
+
+    def valid(ms):
+        return all(ms.count(r) <= 4 for r in set(ms))
+    clsr = [None] * 91
+    rows6 = [(k, nonflush_cards(brk + [x, y])) for k, (x, y) in enumerate(rank_pairs) if valid(brk + [x, y])]
+    for (k, _), v in zip(rows6, evaluate_rows([r for _, r in rows6], 6)):
+        clsr[k] = 0 if ours_now < v else (1 if ours_now == v else 2)
+    T = np.zeros((13, 91), dtype=np.int64)
+    rows7 = [((rq, pk), nonflush_cards(brk + [rq, x, y])) for rq in range(13) for pk, (x, y) in enumerate(rank_pairs)
+             if valid(brk + [rq, x, y])]
+    for ((rq, pk), _), v in zip(rows7, evaluate_rows([r for _, r in rows7], 7)):
+        T[rq, pk] = v
+    lt, gt = [0, 0, 0], [0, 0, 0]
+    for q in range(n):                                  # generic part
+        o = int(our7[q])
+        for pk, (x, y) in enumerate(rank_pairs):
+            mx, my = u[x] - (x == rk[q]), u[y] - (y == rk[q])
+            nn = mx * my if x != y else mx * (mx - 1) // 2
+            if nn <= 0:
+                continue
+            R, c = T[rk[q], pk], clsr[pk]
+            if o < R: lt[c] += nn
+            elif o > R: gt[c] += nn
+    cache = {}
+
+    def flush_rank(mask):
+        if mask not in cache:
+            rs = [r for r in range(13) if mask >> r & 1]
+            cache[mask] = min(int(v) for v in evaluate_rows([list(c) for c in itertools.combinations(rs, 5)], 5))
+        return cache[mask]
+    n_items = 0
+    for s in range(4):                                  # flush part
+        b_s = sum(1 for c in board if c // 13 == s)
+        bmask = sum(1 << (c % 13) for c in board if c // 13 == s)
+        for q in range(n):
+            k = b_s + (su[q] == s)
+            if k < 3:
+                continue
+            fq = bmask | ((1 << rk[q]) if su[q] == s else 0)
+            o = int(our7[q])
+            for (a, b) in pairs:
+                if q in (a, b) or (su[a] == s) + (su[b] == s) < 5 - k:
+                    continue
+                n_items += 1
+                Rf = flush_rank(fq | sum(1 << rk[t] for t in (a, b) if su[t] == s))
+                pk = pp_index(rk[a], rk[b])
+                Rn, ct, cr = T[rk[q], pk], cls[(a, b)], clsr[pk]
+                if o < Rf: lt[ct] += 1
+                elif o > Rf: gt[ct] += 1
+                if o < Rn: lt[cr] -= 1
+                elif o > Rn: gt[cr] -= 1
+    row = np.zeros(16, dtype=np.int64)
+    row[0:3] = tot
+    for i in range(3):
+        row[3 + 3 * i + 0], row[3 + 3 * i + 2] = lt[i], gt[i]
+        row[3 + 3 * i + 1] = 44 * tot[i] - lt[i] - gt[i]
+    row[12:15] = tot
+    row[15] = 4
+    return row, n_items
+
+
 def main():
     import random
     rng = random.Random(7)
