@@ -229,8 +229,8 @@ int holdem_init(int device) {
         S.T.disp_entries[i] = (uint32_t)t.nf[i].disp.size();
         S.T.val_entries[i] = (uint32_t)t.nf[i].val.size();
     }
-    CUDA_TRY(cudaMalloc(&S.flags, kFlagRing * sizeof(int)));
-    CUDA_TRY(cudaMemset(S.flags, 0, kFlagRing * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&S.flags, 4 * kFlagRing * sizeof(int)));     // 16-byte slots: flag word + work counters
+    CUDA_TRY(cudaMemset(S.flags, 0, 4 * kFlagRing * sizeof(int)));
     S.sms = prop.multiProcessorCount;
     S.ready = true;
     return HOLDEM_OK;
@@ -368,7 +368,7 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     // flag word of this call: bit 0 / 1 = the flop kernel met turn / river rows, bit 2 = some kernel marked a malformed row
     // (flag_out receives its address when every kernel of the call maintains bit 2, else nullptr)
     if (mode == HOLDEM_MODE_REFERENCE) {
-        int *rflag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+        int *rflag = S.flags + 4 * (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
         cudaError_t e = cudaMemsetAsync(rflag, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
         e = launch_hp_ref(S.T, d_sit, n, d_out, S.sms, rflag, st);
@@ -376,7 +376,7 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
         if (flag_out) *flag_out = rflag;
         return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, nullptr, st);
     }
-    int *flag = S.flags + (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    int *flag = S.flags + 4 * (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     // HOLDEM_FLOP_KERNEL=3 / 2 and HOLDEM_TURN_KERNEL=3 select the earlier kernels (kept for A/B measurements and cross-checks)
     static const int impl = getenv("HOLDEM_FLOP_KERNEL") ? atoi(getenv("HOLDEM_FLOP_KERNEL")) : 4;
     static const int timpl = getenv("HOLDEM_TURN_KERNEL") ? atoi(getenv("HOLDEM_TURN_KERNEL")) : 4;
@@ -443,7 +443,7 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if (variant < 2 || variant > 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
-    int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    int *flag = S->flags + 4 * (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, nullptr, PeerOut{}, (cudaStream_t)stream));
     else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, flag, variant, (cudaStream_t)stream));
     return HOLDEM_OK;
@@ -465,7 +465,7 @@ int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || !d_cycles || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    int *flag = S->flags + (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    int *flag = S->flags + 4 * (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
     CUDA_TRY(cudaMemsetAsync(d_cycles, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
     CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (unsigned long long *)d_cycles, PeerOut{},
                                      (cudaStream_t)stream));

@@ -62,6 +62,7 @@ constexpr int kSeg = 64;           // longest step segment of a flush task (pack
 constexpr int kPD = 320;           // step descriptors per situation: at most 3 x 66 (rainbow) or 45 + 14 x 11 + 91 + 66
 constexpr int kMaxGroups = 12;
 constexpr int kProfSlots = 8;
+constexpr int kClaim = 4;           // situations a group claims from the global work counter at a time
 
 struct Flop4Group {                    // one situation in flight
     uint4 PD[kPD];                     // x = 2 * (rank bits of the step's cards in s) << 16 | 2 * fold(those bits),
@@ -86,6 +87,7 @@ struct Flop4Group {                    // one situation in flight
     uint32_t HA[16 * 13];              // monotone boards: class histogram (10-bit fields) of {a, c} over the c of one rank outside s
     uint32_t upack[2];                 // unseen cards per rank, 3 bits each (64-bit)
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
+    uint32_t next_claim[2];            // first row of the claim being worked on / of the next one (alternating)
     uint32_t prof[kProfSlots];
     uint8_t code[48];                  // unseen cards, rank*4+suit, ascending
     uint8_t Ls[4][16];                 // positions of the unseen cards of suit s
@@ -110,7 +112,8 @@ __device__ __forceinline__ void group_sync(uint32_t gid) { group_sync_n<kGroupTh
 template <bool kProf>
 __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                        int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers) {
+                        int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers,
+                        unsigned int *__restrict__ work_counter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Flop4Smem &S = *reinterpret_cast<Flop4Smem *>(smem_raw);
     const uint32_t gid = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
@@ -146,7 +149,18 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         t_prev = t_now;                                                          \
     }
 
-    for (int64_t idx = (int64_t)blockIdx.x * kGroups + gid; idx < n; idx += (int64_t)gridDim.x * kGroups) {
+    // Situations are claimed kClaim at a time from a global counter, so that groups which draw expensive boards (monotone
+    // flops cost ~3x a rainbow one) simply take fewer: every SM finishes within a few situations of the others.  The next claim
+    // is fetched while the current one is being worked on.  (work_counter == nullptr: static striding.)
+    const uint32_t n_all_groups = gridDim.x * kGroups, my_group = blockIdx.x * kGroups + gid;
+    uint32_t claim_it = 0;
+    if (tid == 0) G.next_claim[0] = work_counter ? atomicAdd(work_counter, (unsigned)kClaim) : my_group * kClaim;
+    for (;; ++claim_it) {
+    group_sync(gid);
+    const int64_t claim_base = G.next_claim[claim_it & 1];
+    if (claim_base >= n) break;
+    bool next_claimed = false;
+    for (int64_t idx = claim_base; idx < n && idx < claim_base + kClaim; ++idx) {
         group_sync(gid);                                                                            // (A)
         if (kProf && tid == 0) t_prev = (uint32_t)clock64();
         uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
@@ -414,6 +428,12 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         HOLDEM_PROF(1)
         group_sync(gid);                                                                            // (D)
+        if (!next_claimed) {                                           // fetch the next claim under this situation's tasks
+            if (tid == 0)
+                G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaim)
+                                                                : ((claim_it + 1) * n_all_groups + my_group) * kClaim;
+            next_claimed = true;
+        }
         mbar_wait(bar1_s, parity);                                     // T has landed
         parity ^= 1u;
         HOLDEM_PROF(2)
@@ -643,6 +663,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (k < peers.n) peers.p[k][idx * 16 + tid] = v;
         }
     }
+    if (!next_claimed && tid == 0)                                     // every row of the claim belonged to another kernel
+        G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaim)
+                                                        : ((claim_it + 1) * n_all_groups + my_group) * kClaim;
+    }
 #undef HOLDEM_PROF
     if (saw_other && tid == 0) atomicOr(other_rows, saw_other);
     if (kProf && tid == 0)
@@ -651,6 +675,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st) {
+    // other_rows_flag points at a 16-byte slot: [0] the flag word, [1] the work counter of this kernel, [2] of the turn kernel
+    if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Flop4Smem);
     cudaError_t e = prof ? cudaFuncSetAttribute(hp_flop_treys_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -658,11 +684,13 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (e != cudaSuccess) return e;
     int64_t blocks = sms;
     if (blocks * kGroups > n) blocks = (n + kGroups - 1) / kGroups;
-    e = cudaMemsetAsync(other_rows_flag, 0, sizeof(int), st);
+    e = cudaMemsetAsync(other_rows_flag, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return e;
     // the phase clocks are compiled out of the production instance: the kernel is sensitive to its code size
-    if (prof) hp_flop_treys_v4_kernel<true><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers);
-    else hp_flop_treys_v4_kernel<false><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers);
+    if (prof) hp_flop_treys_v4_kernel<true><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
+                                                                                    reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
+    else hp_flop_treys_v4_kernel<false><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
+                                                                                    reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
     return cudaGetLastError();
 }
 
