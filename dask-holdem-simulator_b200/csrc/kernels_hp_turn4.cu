@@ -35,6 +35,7 @@ constexpr int kPPT = 91;
 constexpr int kSegT = 64;
 constexpr int kPDT = 320;            // 45 + 14 * 10 + 91 at most for the one suit with >= 3 board cards, 2 x 55 for two suits with 2
 constexpr int kMaxGroupsT = 8;
+constexpr int kClaimT = 8;           // situations a group claims from the global work counter at a time
 
 struct Turn4Group {
     uint4 PD[kPDT];                    // step descriptors, as in kernels_hp_flop4.cu; w = byte offset of row pp of T
@@ -57,6 +58,7 @@ struct Turn4Group {
     uint32_t HA[16 * 13];
     uint32_t upack[2];
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
+    uint32_t next_claim[2];
     uint8_t code[48];
     uint8_t Ls[4][16];
     uint8_t Lns[4][48];
@@ -78,7 +80,7 @@ __device__ __forceinline__ void tsync(uint32_t gid) { group_sync_n<kGT>(gid); }
 
 __global__ void __launch_bounds__(kThreadsT, 1)
 hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                        int *__restrict__ run_flag, uint32_t one, PeerOut peers) {
+                        int *__restrict__ run_flag, uint32_t one, PeerOut peers, unsigned int *__restrict__ work_counter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     if (run_flag != nullptr && !(*run_flag & 1)) return;   // the flop kernel saw no turn rows
     Turn4Smem &S = *reinterpret_cast<Turn4Smem *>(smem_raw);
@@ -106,7 +108,16 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     const uint32_t t_s = (uint32_t)__cvta_generic_to_shared(G.T);
     uint32_t parity = 0;
 
-    for (int64_t idx = (int64_t)blockIdx.x * kNG + gid; idx < n; idx += (int64_t)gridDim.x * kNG) {
+    // situations are claimed kClaimT at a time from a global counter (see kernels_hp_flop4.cu); nullptr = static striding
+    const uint32_t n_all_groups = gridDim.x * kNG, my_group = blockIdx.x * kNG + gid;
+    uint32_t claim_it = 0;
+    if (tid == 0) G.next_claim[0] = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT) : my_group * kClaimT;
+    for (;; ++claim_it) {
+    tsync(gid);
+    const int64_t claim_base = G.next_claim[claim_it & 1];
+    if (claim_base >= n) break;
+    bool next_claimed = false;
+    for (int64_t idx = claim_base; idx < n && idx < claim_base + kClaimT; ++idx) {
         tsync(gid);                                                                                 // (A)
         uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
         uint32_t cb[8];
@@ -365,6 +376,12 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             }
         }
         tsync(gid);                                                                                 // (D)
+        if (!next_claimed) {
+            if (tid == 0)
+                G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT)
+                                                                : ((claim_it + 1) * n_all_groups + my_group) * kClaimT;
+            next_claimed = true;
+        }
         mbar_wait(bar1_s, parity);
         parity ^= 1u;
 
@@ -569,6 +586,10 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (k < peers.n) peers.p[k][idx * 16 + tid] = v;
         }
     }
+    if (!next_claimed && tid == 0)
+        G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT)
+                                                        : ((claim_it + 1) * n_all_groups + my_group) * kClaimT;
+    }
 }
 
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
@@ -580,7 +601,10 @@ cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (e != cudaSuccess) return e;
     int64_t blocks = sms;
     if (blocks * kNG > n) blocks = (n + kNG - 1) / kNG;
-    hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u, peers);
+    // run_flag, when given, is the call's 16-byte slot: [0] flag word, [2] this kernel's work counter (zeroed with the slot)
+    if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
+    hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u, peers,
+                                                                  run_flag ? reinterpret_cast<unsigned int *>(run_flag) + 2 : nullptr);
     return cudaGetLastError();
 }
 
