@@ -425,6 +425,16 @@ def main():
                                   "what": "hp_direct_kernel: one real evaluation (shared-memory table gathers) per (holding, "
                                           "runout) pair -- the literal shape of the reference loop"},
         }
+    def _eval_ncu_counters():
+        # what bounds the evaluator below HBM speed: the L1/shared data path (ncu --set full, profiles/)
+        try:
+            c = json.load(open(os.path.join(ROOT, "profiles", "hot_kernel_counters.json")))["eval_batch_fast_kernel<7>"]
+        except Exception:
+            return None
+        return {k: c.get(k) for k in ("warp_instructions_per_32_hands", "shared_wavefronts_per_32_hands",
+                                      "lsu_data_pipe_wavefront_pct", "shared_wavefront_pct", "issue_active_pct",
+                                      "alu_pipe_pct", "fmaheavy_pipe_pct", "capture")}
+
     extras = {}
     if not args.no_extras:
         # batched 7-card evaluator fed from HBM: 10 algorithmic bytes per evaluation
@@ -459,7 +469,8 @@ def main():
                          "traffic": (lambda t: t.get("dram_bytes_read", 0) + t.get("dram_bytes_write", 0) if t else None)(
                              traffic.get("eval_batch_fast_kernel<7>")),
                          "note": "inputs 256 MiB + outputs 64 MiB per launch (> 126 MB L2); traffic from the committed ncu "
-                                 "capture (profiles/traffic.json)"}}
+                                 "capture (profiles/traffic.json)",
+                         "ncu": _eval_ncu_counters()}}
         del hands, out16
         # exhaustive sweep, hands generated in-kernel (BASELINE.json configs[1])
         hb.exhaustive7(local_rank)

@@ -3,8 +3,6 @@
 //
 // Replaces treys.Evaluator.evaluate (reached from HandCalculations.py:229-240, pokerlib_to_treys.py:15-21) and
 // CalculateHandRankValue (HandCalculations.py:45-82) for batches of hands.
-#include <cstdlib>
-
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -69,142 +67,11 @@ eval_batch_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restri
     }
 }
 
-// Fast path for large batches.  The per-card table word (one copy per lane) carries the additive rank key in its low 23 bits and three
+// Fast path for large batches.  The per-card table word carries the additive rank key in its low 23 bits and three
 // 3-bit suit counters above it (clubs, diamonds, hearts; spades = NC - the rest), so one shared-memory gather and one
 // add per card yield both the rank multiset key and the suit histogram; no card set is built.  Hands that hold a flush
-// (about 3 %) or an out-of-range card are deferred to a per-warp queue and finished by eval_row() with all lanes of
-// the warp busy, so the rare path costs well under one instruction per hand.  Duplicate cards are NOT detected here
-// (neither does Treys); the strict kernel above does that.
-constexpr uint32_t kFastTabWords = 52 * 32;
-
-template <int NC, bool kPrefetch>
-__global__ void __launch_bounds__(1024, 1)
-eval_batch_fast_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T,
-                       uint32_t row_bytes, uint32_t one) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kIlp = 4;
-    constexpr int kQueueCap = 256;   // per warp; drained when it holds >= 128 entries (four full passes of the warp)
-    uint32_t *s_cardkey = reinterpret_cast<uint32_t *>(smem);                 // 64 entries (strict path)
-    // [52 cards][32 lanes]: every lane reads its own copy of the card word, so the seven gathers of a hand cost one
-    // shared-memory wavefront each whatever the cards are (a single 52-word table costs ~3 with random cards).  Bytes
-    // above 51 index past the table into the sections behind it -- still inside this CTA's shared memory (a byte of 255
-    // reaches 33 KB; the smallest layout is 54 KB) -- and the hand goes to the strict path anyway.
-    uint32_t *s_tab = s_cardkey + 64;
-    uint32_t *s_slow = s_tab + kFastTabWords;                                 // 512 bits: suit-counter pattern holds a flush
-    uint16_t *s_queue = reinterpret_cast<uint16_t *>(s_slow + 16);            // [32 warps][kQueueCap]
-    uint16_t *s_flush = reinterpret_cast<uint16_t *>(smem + 256 + kFastTabWords * 4 + 64 + 32 * kQueueCap * 2);
-    uint16_t *s_disp = s_flush + kFlushEntries;
-    uint16_t *s_val = s_disp + T.disp_entries[NC - 5];
-    const NfHash &g = T.nf[NC - 5];
-    if (threadIdx.x < 64) s_cardkey[threadIdx.x] = threadIdx.x < 52 ? c_rank_key[threadIdx.x % 13] : 0u;
-    for (uint32_t i = threadIdx.x; i < kFastTabWords; i += blockDim.x) {
-        const uint32_t c = row_bytes == 4 ? i : i >> 5, su = c / 13;
-        s_tab[i] = c < 52 ? c_rank_key[c % 13] | (su < 3 ? 1u << (23 + 3 * su) : 0u) : 0u;
-    }
-    if (threadIdx.x < 16) {
-        // bit s of the table: the three 3-bit counters (clubs, diamonds, hearts) packed in s mean a flush --
-        // a counted suit holds >= 5, or so few cards are counted that spades hold >= 5
-        uint32_t word = 0;
-        for (uint32_t b = 0; b < 32; ++b) {
-            const uint32_t sv = threadIdx.x * 32 + b, c0 = sv & 7u, c1 = (sv >> 3) & 7u, c2 = sv >> 6;
-            if (c0 >= 5 || c1 >= 5 || c2 >= 5 || c0 + c1 + c2 <= (uint32_t)(NC - 5)) word |= 1u << b;
-        }
-        s_slow[threadIdx.x] = word;
-    }
-    {
-        const uint4 *src;
-        uint4 *dst;
-        src = reinterpret_cast<const uint4 *>(T.flush); dst = reinterpret_cast<uint4 *>(s_flush);
-        for (uint32_t i = threadIdx.x; i < kFlushEntries / 8; i += blockDim.x) dst[i] = src[i];
-        src = reinterpret_cast<const uint4 *>(g.disp); dst = reinterpret_cast<uint4 *>(s_disp);
-        for (uint32_t i = threadIdx.x; i < T.disp_entries[NC - 5] / 8; i += blockDim.x) dst[i] = src[i];
-        src = reinterpret_cast<const uint4 *>(g.val); dst = reinterpret_cast<uint4 *>(s_val);
-        for (uint32_t i = threadIdx.x; i < T.val_entries[NC - 5] / 8; i += blockDim.x) dst[i] = src[i];
-    }
-    NfHash h = g;
-    h.disp = s_disp;
-    h.val = s_val;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint16_t *queue = s_queue + warp * kQueueCap;
-    const char *tab_bytes = reinterpret_cast<const char *>(s_tab + (row_bytes == 4 ? 0u : lane));
-    // 32-bit hand indices: the launcher splits batches of 2^31 hands or more
-    const uint32_t nn = (uint32_t)n, stride = gridDim.x * blockDim.x;
-    // Deferred hands: entry = window-iteration << 7 | j << 5 | lane, relative to qbase (this warp's first hand of the window)
-    uint32_t qn = 0, it = 0;
-    uint32_t qbase = blockIdx.x * blockDim.x + threadIdx.x - lane;
-    auto drain = [&]() {
-        __syncwarp();
-        for (uint32_t e = lane; e < qn; e += 32) {
-            const uint32_t q = queue[e];
-            const uint32_t i = qbase + ((q >> 7) * kIlp + ((q >> 5) & 3u)) * stride + (q & 31u);
-            out[i] = (uint16_t)eval_row<NC>(__ldg(cards + i), s_cardkey, s_flush, h);
-        }
-        __syncwarp();
-    };
-    uint2 wnext[kIlp];
-    if (kPrefetch) {
-#pragma unroll
-        for (int j = 0; j < kIlp; ++j) {
-            const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + j * stride;
-            wnext[j] = i < nn ? __ldg(cards + i) : make_uint2(0x03020100u, 0x00060504u);
-        }
-    }
-    for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base - threadIdx.x < nn; base += kIlp * stride) {
-        // the loop bound is block-uniform; lanes past n load a dummy hand and write nothing
-        uint2 w[kIlp];
-#pragma unroll
-        for (int j = 0; j < kIlp; ++j) {
-            if (kPrefetch) {
-                // the words of this pass were requested one pass ago; request the next pass now
-                w[j] = wnext[j];
-                const uint32_t i = base + (kIlp + j) * stride;
-                wnext[j] = i < nn ? __ldg(cards + i) : make_uint2(0x03020100u, 0x00060504u);
-            } else {
-                const uint32_t i = base + j * stride;
-                w[j] = i < nn ? __ldg(cards + i) : make_uint2(0x03020100u, 0x00060504u);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kIlp; ++j) {
-            const uint32_t i = base + j * stride;
-            const bool live = i < nn;
-            uint32_t sum = 0;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                // byte k -> byte offset into the table: one permute (ALU pipe) and one multiply (FMA pipe); the running sum
-                // is a multiply-add by a kernel argument equal to 1, so it issues on the FMA pipe as well
-                const uint32_t b = __byte_perm(k < 4 ? w[j].x : w[j].y, 0u, 0x4440u + (k & 3));
-                const uint32_t v = *reinterpret_cast<const uint32_t *>(tab_bytes + b * row_bytes);
-                asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(sum) : "r"(v), "r"(one));
-            }
-            // any byte >= 52?  (b & 0x7F) + 76 sets bit 7 iff (b & 0x7F) >= 52; OR b itself catches b >= 128
-            const uint32_t ymask = NC == 7 ? 0x00808080u : (NC == 6 ? 0x00008080u : 0x00000080u);
-            const uint32_t badx = (((w[j].x & 0x7F7F7F7Fu) + 0x4C4C4C4Cu) | w[j].x) & 0x80808080u;
-            const uint32_t bady = (((w[j].y & 0x7F7F7F7Fu) + 0x4C4C4C4Cu) | w[j].y) & ymask;
-            const uint32_t s = sum >> 23;
-            const uint32_t flushbit = (s_slow[s >> 5] >> (s & 31u)) & 1u;
-            const bool slow = (flushbit | badx | bady) != 0 && live;
-            const uint32_t r = nf_lookup(h, sum & 0x7FFFFFu);
-            if (live && !slow) out[i] = (uint16_t)r;
-            if (__any_sync(0xFFFFFFFFu, slow)) {
-                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, slow);
-                if (slow) queue[qn + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)((it << 7) | (j << 5) | lane);
-                qn += __popc(ballot);
-            }
-        }
-        ++it;
-        if (qn >= 128 || it == 500) {
-            drain();
-            qn = 0;
-            it = 0;
-            qbase = base + kIlp * stride - lane;
-        }
-    }
-    drain();
-}
-
-// Second form of the fast path: fewer instructions per hand.
+// (about 3 % of 7-card hands) or an out-of-range byte are deferred and finished by eval_row() 32 at a time.  Duplicate
+// cards are NOT detected here (neither does Treys); the strict kernel above does that.
 //  * the card table is [52 rows of 256 bytes][32 lane words]: one PRMT builds lane * 4 | byte << 8, the whole byte offset,
 //    so a card costs a permute, a gather and a multiply-add (no address multiply);
 //  * a deferred hand (flush pattern or out-of-range byte) only sets a bit in a per-lane 32-bit window (bit = hand number
@@ -216,7 +83,7 @@ constexpr int kStackCap = 160;   // hand numbers per warp: up to 31 carried over
 
 template <int NC>
 __global__ void __launch_bounds__(1024, 1)
-eval_batch_fast2_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T,
+eval_batch_fast_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__restrict__ out, DevTables T,
                         uint32_t one) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int kIlp = 4;
@@ -358,13 +225,10 @@ eval_batch_fast2_kernel(const uint2 *__restrict__ cards, int64_t n, uint16_t *__
 size_t eval_smem_bytes(const DevTables &T, int nc) {
     return 1024 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
 }
-size_t eval_fast2_smem_bytes(const DevTables &T, int nc) {
+size_t eval_fast_smem_bytes(const DevTables &T, int nc) {
     size_t b = 256 + kTab2Bytes + 64 + 32 * kStackCap * 4 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
     const size_t reach = 256 + 256 * 256;   // where a card byte of 255 lands
     return b < reach ? reach : b;
-}
-size_t eval_fast_smem_bytes(const DevTables &T, int nc) {
-    return 256 + kFastTabWords * 4 + 64 + 32 * 256 * 2 + 2 * (size_t)(kFlushEntries + T.disp_entries[nc - 5] + T.val_entries[nc - 5]);
 }
 
 template <int NC>
@@ -379,27 +243,17 @@ static cudaError_t launch_eval_nc(const DevTables &T, const uint8_t *cards, int6
             if (e != cudaSuccess) return e;
             eval_batch_kernel<NC, true><<<sms, 1024, smem, st>>>(c2, n, out, T);
         } else {
-            size_t smem = eval_fast_smem_bytes(T, NC);
-            static const int variant = [] { const char *v = getenv("HOLDEM_EVAL_VARIANT"); return v ? atoi(v) : 4; }();
-            if (variant & 4) {
-                smem = eval_fast2_smem_bytes(T, NC);
-                cudaError_t e = cudaFuncSetAttribute(eval_batch_fast2_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)smem);
-                if (e != cudaSuccess) return e;
-                constexpr int64_t kPiece = (int64_t)1 << 30;
-                for (int64_t off = 0; off < n; off += kPiece)
-                    eval_batch_fast2_kernel<NC><<<sms, 1024, smem, st>>>(c2 + off, n - off < kPiece ? n - off : kPiece, out + off,
-                                                                          T, 1u);
-                return cudaGetLastError();
-            }
-            auto kern = (variant & 2) ? eval_batch_fast_kernel<NC, true> : eval_batch_fast_kernel<NC, false>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            // the kernel masks value-table slots with a compile-time constant (16 / 15 / 13 slot bits, tables.cpp)
+            if (T.val_entries[NC - 5] != (NC == 7 ? 65536u : (NC == 6 ? 32768u : 8192u))) return cudaErrorInvalidValue;
+            const size_t smem = eval_fast_smem_bytes(T, NC);
+            cudaError_t e = cudaFuncSetAttribute(eval_batch_fast_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
             if (e != cudaSuccess) return e;
             // 32-bit hand indices inside the kernel: batches of 2^31 hands or more go in pieces
             constexpr int64_t kPiece = (int64_t)1 << 30;
             for (int64_t off = 0; off < n; off += kPiece)
-                kern<<<sms, 1024, smem, st>>>(c2 + off, n - off < kPiece ? n - off : kPiece, out + off, T,
-                                              (variant & 1) ? 128u : 4u, 1u);
+                eval_batch_fast_kernel<NC><<<sms, 1024, smem, st>>>(c2 + off, n - off < kPiece ? n - off : kPiece, out + off, T,
+                                                                     1u);
         }
     } else {
         int blocks = (int)((n + 255) / 256);
