@@ -116,6 +116,35 @@ def test_eval_large_batch_fast_and_strict_paths(hb, oracle, n_cards):
     assert (fast[bad_card] == 0).all() and (strict[bad_card] == 0).all() and (strict[dup] == 0).all()
 
 
+@pytest.mark.parametrize("n_cards", [5, 7])
+def test_eval_fast_path_deferral_extremes(hb, oracle, n_cards):
+    """The fast kernel defers flush-pattern hands through per-lane windows and a per-warp stack.  Dense runs of flushes
+    overflow the stack (each lane then finishes its own hands), sparse ones are carried from window to window, and
+    a batch of nothing but deferred hands must still come out right: compared with the strict kernel on every row and
+    with the oracle on a sample."""
+    n = 1_000_003
+    rng = np.random.default_rng(77 + n_cards)
+    rows = _random_hands(n, n_cards, seed=900 + n_cards)
+    suited = (13 * rng.integers(0, 4, n)[:, None] + np.argsort(rng.random((n, 13)), axis=1)[:, :n_cards]).astype(np.uint8)
+    dense = np.zeros(n, dtype=bool)
+    dense[100_000:400_000] = True                                  # every hand deferred
+    dense[400_000:600_000] = rng.random(200_000) < 0.5             # half of them
+    dense[600_000:700_000] = (np.arange(100_000) % 151_552) < 64   # short bursts
+    rows[dense, :n_cards] = suited[dense]
+    rows[700_000:700_512, 0] = 200                                 # a run of out-of-range bytes
+    d = torch.from_numpy(rows).cuda()
+    fast = hb.evaluate(d, n_cards).cpu().numpy().astype(np.uint16)
+    strict = hb.evaluate(d, n_cards, strict=True).cpu().numpy().astype(np.uint16)
+    assert np.array_equal(fast, strict)
+    assert (fast[700_000:700_512] == 0).all() and (fast[:700_000] != 0).all()
+    sample = np.r_[0:2000, 100_000:102_000, 400_000:402_000, n - 2000:n]
+    assert np.array_equal(fast[sample], oracle.treys_evaluate_batch(rows[sample], n_cards))
+    # all-deferred batch, just above the size at which the fast kernel is chosen
+    m = 148 * 2048 + 5
+    d2 = torch.from_numpy(np.ascontiguousarray(rows[100_000:100_000 + m])).cuda()
+    assert torch.equal(hb.evaluate(d2, n_cards), hb.evaluate(d2, n_cards, strict=True))
+
+
 def test_showdown_whole_table(hb, oracle):
     """all 22 seats of a hand in one evaluator launch; winners under the correct rule and under the
     reference's max() rule (GameBoard.py:210)."""
