@@ -3,6 +3,8 @@
 //
 // Replaces treys.Evaluator.evaluate (reached from HandCalculations.py:229-240, pokerlib_to_treys.py:15-21) and
 // CalculateHandRankValue (HandCalculations.py:45-82) for batches of hands.
+#include <cstdlib>
+
 #include "device_common.cuh"
 #include "launch.h"
 
@@ -402,11 +404,167 @@ exhaustive7_kernel(unsigned long long *__restrict__ hist, unsigned long long *__
         if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
 }
 
+// Second form of the sweep.  A warp fixes the five highest cards c2 < ... < c6 (a 5-subset of 50 values, enumerated in
+// colex order) and its lanes run over the C(c2, 2) pairs c0 < c1 below them, 32 per pass: the five-card part of the
+// key / suit-counter word and of the card set is warp-uniform and carried from tuple to tuple (only c2 moves between most
+// successive tuples), so a hand costs two conflict-free card gathers, one add and the two hash gathers.  A flush is only
+// possible when the five high cards hold three of a suit (warp-uniform test); then the suit-counter pattern of the sum
+// picks the lanes that go to the suited table.  Chunks of 16 tuples are dealt to the CTAs round-robin (3.6 % spread of
+// work between SMs) and claimed by the warps of a CTA from a shared-memory counter, heaviest (= last in colex) first.
+constexpr uint32_t kTuples5 = 2118760;            // C(50, 5)
+constexpr uint32_t kTup = 16;
+constexpr uint32_t kTupChunks = (kTuples5 + kTup - 1) / kTup;
+constexpr uint32_t kSweepPairs = 1128;            // C(48, 2): c1 <= 46 < c2 <= 47
+constexpr uint32_t kSweepHead = kTab2Bytes + 64 + 50 * 8 * 4 + 2272 + 16 + 7464 * 4;
+
+__global__ void __launch_bounds__(1024, 1)
+exhaustive7_tuple_kernel(unsigned long long *__restrict__ hist, unsigned long long *__restrict__ sums, DevTables T) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_tab = smem;                                                    // [52 rows of 256 B][32 lane words]
+    uint32_t *s_slow = reinterpret_cast<uint32_t *>(s_tab + kTab2Bytes);      // 512 bits: 7-card suit-counter pattern holds a flush
+    uint32_t *s_binom = s_slow + 16;                                          // [50][8]
+    uint16_t *s_pairs = reinterpret_cast<uint16_t *>(s_binom + 50 * 8);       // colex pairs, c0 | c1 << 8
+    uint32_t *s_ctr = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_pairs) + 2272);
+    uint32_t *s_hist = s_ctr + 4;                                             // [7464]
+    uint16_t *s_flush = reinterpret_cast<uint16_t *>(s_hist + 7464);
+    uint16_t *s_disp = s_flush + kFlushEntries;
+    uint16_t *s_val = s_disp + T.disp_entries[2];
+    for (uint32_t i = threadIdx.x; i < 52 * 32; i += blockDim.x) {
+        const uint32_t c = i >> 5, su = c / 13;
+        *reinterpret_cast<uint32_t *>(s_tab + c * 256 + (i & 31u) * 4) =
+            c_rank_key[c % 13] | (su < 3 ? 1u << (23 + 3 * su) : 0u);
+    }
+    if (threadIdx.x < 16) {
+        uint32_t word = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+            const uint32_t sv = threadIdx.x * 32 + b, c0 = sv & 7u, c1 = (sv >> 3) & 7u, c2 = sv >> 6;
+            if (c0 >= 5 || c1 >= 5 || c2 >= 5 || c0 + c1 + c2 <= 2u) word |= 1u << b;
+        }
+        s_slow[threadIdx.x] = word;
+    }
+    if (threadIdx.x < 50) {  // Pascal row per thread
+        uint64_t v = 1;
+        const int nrow = threadIdx.x;
+        for (int k = 0; k < 8; ++k) {
+            s_binom[nrow * 8 + k] = k > nrow ? 0u : (uint32_t)v;
+            v = v * (uint64_t)(nrow - k) / (uint64_t)(k + 1);
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < kSweepPairs; i += blockDim.x) s_pairs[i] = T.pairs[i];
+    if (threadIdx.x == 0) s_ctr[0] = 0;
+    for (uint32_t i = threadIdx.x; i < 7464; i += blockDim.x) s_hist[i] = 0;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(T.flush);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_flush);
+        for (uint32_t i = threadIdx.x; i < kFlushEntries / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(T.nf[2].disp); dst = reinterpret_cast<uint4 *>(s_disp);
+        for (uint32_t i = threadIdx.x; i < T.disp_entries[2] / 8; i += blockDim.x) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(T.nf[2].val); dst = reinterpret_cast<uint4 *>(s_val);
+        for (uint32_t i = threadIdx.x; i < T.val_entries[2] / 8; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const NfHash &h = T.nf[2];
+    const uint32_t lane = threadIdx.x & 31, lane4 = lane * 4;
+    const uint8_t *tab_lane = s_tab + lane4;
+    auto word_of = [&](uint32_t c) { return *reinterpret_cast<const uint32_t *>(tab_lane + c * 256); };
+    // this CTA's chunks: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint32_t nk = blockIdx.x < kTupChunks ? (kTupChunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+    unsigned long long sum = 0, sumsq = 0;
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&s_ctr[0], 1u);
+        k = __shfl_sync(0xFFFFFFFFu, k, 0);
+        if (k >= nk) break;
+        uint32_t q = (blockIdx.x + gridDim.x * (nk - 1 - k)) * kTup;
+        const uint32_t qend = q + kTup < kTuples5 ? q + kTup : kTuples5;
+        // unrank q among the 5-subsets of {0..49} (combinatorial number system)
+        int d[5];
+        {
+            uint32_t rem = q;
+            int hi = 49;
+#pragma unroll
+            for (int j = 4; j >= 0; --j) {
+                int v = hi;
+                while (s_binom[v * 8 + j + 1] > rem) --v;
+                d[j] = v;
+                rem -= s_binom[v * 8 + j + 1];
+                hi = v - 1;
+            }
+        }
+        bool fresh = true;
+        uint32_t hi4_sum = 0;
+        uint64_t hi4_set = 0;
+        for (; q < qend; ++q) {
+            if (fresh) {  // c3..c6 changed
+                hi4_sum = word_of(d[1] + 2) + word_of(d[2] + 2) + word_of(d[3] + 2) + word_of(d[4] + 2);
+                hi4_set = card_bit(d[1] + 2) | card_bit(d[2] + 2) | card_bit(d[3] + 2) | card_bit(d[4] + 2);
+            }
+            const uint32_t c2 = d[0] + 2;
+            const uint32_t hi_sum = hi4_sum + word_of(c2);
+            const uint64_t hi_set = hi4_set | card_bit(c2);
+            // three of a suit among the five high cards?  (spades are the cards not counted)
+            const uint32_t sc = hi_sum >> 23, a0 = sc & 7u, a1 = (sc >> 3) & 7u, a2 = sc >> 6;
+            const bool flush_possible = a0 >= 3 || a1 >= 3 || a2 >= 3 || a0 + a1 + a2 <= 2u;
+            const uint32_t npairs = (c2 * (c2 - 1)) >> 1;
+            for (uint32_t p = lane; p < npairs; p += 32) {
+                const uint32_t pr = s_pairs[p];
+                // byte offsets lane * 4 | card << 8 of the two low cards
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(s_tab + __byte_perm(pr, lane4, 0x5504u));
+                const uint32_t w1 = *reinterpret_cast<const uint32_t *>(s_tab + __byte_perm(pr, lane4, 0x5514u));
+                const uint32_t tot = hi_sum + w0 + w1;
+                const uint32_t key = tot & 0x7FFFFFu;
+                const uint32_t b = (key * h.mul_b) >> h.bshift;
+                const uint32_t slot = (((key * h.mul_s) >> h.sshift) + s_disp[b]) & 0xFFFFu;
+                uint32_t r = s_val[slot];
+                if (flush_possible) {
+                    const uint32_t s = tot >> 23;
+                    if ((s_slow[s >> 5] >> (s & 31u)) & 1u)
+                        r = s_flush[flush_mask(hi_set | card_bit(pr & 0xFFu) | card_bit(pr >> 8), 5)];
+                }
+                atomicAdd(&s_hist[r], 1u);
+                sum += r;
+                sumsq += (unsigned long long)(r * r);
+            }
+            // successor in colex order
+            if (d[0] + 1 < d[1]) { d[0]++; fresh = false; }
+            else {
+                fresh = true;
+                if (d[1] + 1 < d[2]) { d[1]++; d[0] = 0; }
+                else if (d[2] + 1 < d[3]) { d[2]++; d[0] = 0; d[1] = 1; }
+                else if (d[3] + 1 < d[4]) { d[3]++; d[0] = 0; d[1] = 1; d[2] = 2; }
+                else { d[4]++; d[0] = 0; d[1] = 1; d[2] = 2; d[3] = 3; }
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
+        sumsq += __shfl_down_sync(0xFFFFFFFFu, sumsq, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&sums[0], sum);
+        atomicAdd(&sums[1], sumsq);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 7463; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
 cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(hist, 0, 7463 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(sums, 0, 2 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
+    static const bool chunked = [] { const char *v = getenv("HOLDEM_EXHAUSTIVE_KERNEL"); return v && atoi(v) == 1; }();
+    if (!chunked) {
+        if (T.val_entries[2] != 65536u) return cudaErrorInvalidValue;   // the kernel masks slots with 0xFFFF
+        const size_t smem2 = kSweepHead + 2 * (size_t)(kFlushEntries + T.disp_entries[2] + T.val_entries[2]);
+        e = cudaFuncSetAttribute(exhaustive7_tuple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return e;
+        exhaustive7_tuple_kernel<<<sms, 1024, smem2, st>>>(reinterpret_cast<unsigned long long *>(hist),
+                                                          reinterpret_cast<unsigned long long *>(sums), T);
+        return cudaGetLastError();
+    }
     size_t smem = (64 + 53 * 8 + 7464) * 4 + 2 * (size_t)(kFlushEntries + T.disp_entries[2] + T.val_entries[2]);
     e = cudaFuncSetAttribute(exhaustive7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
