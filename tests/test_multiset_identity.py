@@ -38,3 +38,20 @@ def test_rank_multiset_identity_turn_matches_oracle(oracle):
         got, n_items = P.turn_counts(hole, board)
         assert np.array_equal(got, want[k]), (hole, board, got, want[k])
         assert n_items < 45540
+
+
+def test_reference_mode_identity_matches_literal_oracle(oracle):
+    """The same identity for mode="reference" (scripts/proto_ref_multiset.py): literal 9-category ranker written as
+    rank-count category + flush override, regular runouts plus the three kinds of runouts that repeat a hole card or one of
+    the opponent's own cards; equals the literal oracle on monotone / two-tone / rainbow-paired boards."""
+    import proto_ref_multiset as R
+    assert R.check_ranker(trials=1500)
+    sits = [([14, 1], [31, 32, 33]),      # testing/ExampleHS.py (golden counts of SURVEY 8c)
+            ([0, 1], [2, 3, 4]),          # monotone board, we hold the straight flush
+            ([12, 25], [38, 51, 0])]      # rainbow board, paired
+    want = oracle.hp_batch(oracle.pack_situations(sits), "reference").astype(np.int64)
+    assert want[0][3:12].tolist() == [334713, 148530, 172965, 70272, 265983, 130617, 27162, 16905, 104109]
+    for k, (hole, board) in enumerate(sits):
+        got, n_items = R.ref_flop_counts(hole, board)
+        assert np.array_equal(got[:15], want[k][:15]), (hole, board, got, want[k])
+        assert n_items < 1081 * 1176 // 4
