@@ -239,6 +239,68 @@ void ehs_hp_counts_treys_cached(const int *our, const int *board, int nb, uint32
         }
 }
 
+/* Flop counts of mode 0 once more, now with BOTH final ranks cached: ours per runout (as above) and the
+ * opponent's per 4-set of unseen cards -- the opponent's final hand is board + holding + runout, which
+ * depends only on the union of the two pairs, so the C(47,4) = 178,365 distinct seven-card hands are
+ * evaluated once each instead of 1081 x 990 = 1,070,190 times.  The loop itself keeps the reference's
+ * shape (HandCalculations.py:193-218: holdings outside, runouts inside).  Checked equal to
+ * ehs_hp_counts(mode 0) in tests/test_oracle_ehs.py; this is what lets the GPU suite compare ALL
+ * 65,536 bench situations with the oracle. */
+static int choose_tab[48][5];
+static void choose_init(void) {
+    if (choose_tab[4][4]) return;
+    for (int n = 0; n < 48; n++) {
+        choose_tab[n][0] = 1;
+        for (int k = 1; k < 5; k++) choose_tab[n][k] = n == 0 ? 0 : choose_tab[n - 1][k - 1] + choose_tab[n - 1][k];
+    }
+}
+void ehs_hp_counts_treys_4set(const int *our, const int *board, uint32_t *hp9, uint32_t *hptotal3) {
+    int known[8], deck[52];
+    static __thread int16_t ourcache[47][47];
+    static __thread int16_t oppcache[178365];
+    static __thread uint8_t cls[47][47];
+    choose_init();
+    memset(hp9, 0, 9 * sizeof(uint32_t));
+    memset(hptotal3, 0, 3 * sizeof(uint32_t));
+    known[0] = our[0]; known[1] = our[1];
+    for (int i = 0; i < 3; i++) known[2 + i] = board[i];
+    int nd = deck_without(known, 5, deck);
+    if (nd != 47) return; /* malformed situation: all-zero counts */
+    int ourrank = rank_of(0, our, board, 3);
+    int c7[7] = {board[0], board[1], board[2], 0, 0, 0, 0};
+    for (int w = 0; w < nd; w++)
+        for (int x = w + 1; x < nd; x++) {
+            int two[2] = {deck[w], deck[x]};
+            int nboard[5] = {board[0], board[1], board[2], deck[w], deck[x]};
+            ourcache[w][x] = (int16_t)rank_of(0, our, nboard, 5);      /* :210 */
+            int opprank = rank_of(0, two, board, 3);                   /* :194 */
+            cls[w][x] = (uint8_t)(ourrank > opprank ? 0 : (ourrank == opprank ? 1 : 2));
+            hptotal3[cls[w][x]]++;                                     /* :203 */
+            for (int y = x + 1; y < nd; y++)
+                for (int z = y + 1; z < nd; z++) {
+                    c7[3] = deck[w]; c7[4] = deck[x]; c7[5] = deck[y]; c7[6] = deck[z];
+                    oppcache[w + choose_tab[x][2] + choose_tab[y][3] + choose_tab[z][4]] = (int16_t)-treys_evaluate(c7, 7);
+                }
+        }
+    for (int i = 0; i < nd; i++)
+        for (int j = i + 1; j < nd; j++) {                             /* :193 */
+            int index = cls[i][j];
+            for (int a = 0; a < nd; a++) {
+                if (a == i || a == j) continue;
+                for (int b = a + 1; b < nd; b++) {                     /* :207-209 */
+                    if (b == i || b == j) continue;
+                    /* sorted union of {i<j} and {a<b} */
+                    int w = i < a ? i : a, z = j > b ? j : b;
+                    int m1 = i < a ? a : i, m2 = j > b ? b : j;
+                    int x = m1 < m2 ? m1 : m2, y = m1 < m2 ? m2 : m1;
+                    int ourbest = ourcache[a][b];
+                    int oppbest = oppcache[w + choose_tab[x][2] + choose_tab[y][3] + choose_tab[z][4]];
+                    hp9[index * 3 + (ourbest > oppbest ? 0 : (ourbest == oppbest ? 1 : 2))]++; /* :213-218 */
+                }
+            }
+        }
+}
+
 /* ---- batch drivers over packed situations uint8 [N,8]: h0 h1 b0..b4 (0xFF = absent) pad ------------
  * out rows are uint32 [16]: ahead tied behind | HP[9] row-major | HPTotal[3] | n_board  (include/holdem_b200.h) */
 static int unpack(const uint8_t *row, int *our, int *board) {
@@ -258,17 +320,24 @@ void ehs_hs_batch(int mode, const uint8_t *sit, int64_t n, uint32_t *out /* [n,3
     }
 }
 
-void ehs_hp_batch(int mode, const uint8_t *sit, int64_t n, uint32_t *out /* [n,16] */) {
+/* cache: 0 = our rank cached per runout only (one opponent evaluation per (holding, runout) pair, the
+ * reference's loop shape -- what the CPU baseline times), 1 = also the opponent's rank per 4-set (flop rows). */
+void ehs_hp_batch_ex(int mode, int cache, const uint8_t *sit, int64_t n, uint32_t *out /* [n,16] */) {
     treys_init();
     for (int64_t s = 0; s < n; s++) {
         int our[2], board[5];
         int nb = unpack(sit + 8 * s, our, board);
         uint32_t *o = out + 16 * s;
-        if (mode == 0) ehs_hp_counts_treys_cached(our, board, nb, o + 3, o + 12);
+        if (mode == 0 && nb == 3 && cache) ehs_hp_counts_treys_4set(our, board, o + 3, o + 12);
+        else if (mode == 0) ehs_hp_counts_treys_cached(our, board, nb, o + 3, o + 12);
         else ehs_hp_counts(1, our, board, nb, o + 3, o + 12);
         o[0] = o[12]; o[1] = o[13]; o[2] = o[14]; /* HPTotal == HS counts (same loop, :168-173 vs :196-203) */
         o[15] = (uint32_t)nb;
     }
+}
+
+void ehs_hp_batch(int mode, const uint8_t *sit, int64_t n, uint32_t *out /* [n,16] */) {
+    ehs_hp_batch_ex(mode, 0, sit, n, out);
 }
 
 void lit_category_batch(const uint8_t *rows, int ncards, int stride, int64_t n, uint8_t *out) {

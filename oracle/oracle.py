@@ -66,6 +66,10 @@ def lib():
             L.ehs_hp_counts.restype = None
             L.ehs_hp_counts_treys_cached.argtypes = [i32p, i32p, ctypes.c_int, u32p, u32p]
             L.ehs_hp_counts_treys_cached.restype = None
+            L.ehs_hp_counts_treys_4set.argtypes = [i32p, i32p, u32p, u32p]
+            L.ehs_hp_counts_treys_4set.restype = None
+            L.ehs_hp_batch_ex.argtypes = [ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int64, u32p]
+            L.ehs_hp_batch_ex.restype = None
             L.ehs_hs_batch.argtypes = [ctypes.c_int, u8p, ctypes.c_int64, u32p]
             L.ehs_hs_batch.restype = None
             L.ehs_hp_batch.argtypes = [ctypes.c_int, u8p, ctypes.c_int64, u32p]
@@ -151,13 +155,17 @@ def hs_counts(our, board, mode):
 
 
 def hp_counts(our, board, mode, cached=True):
-    """-> (HP 3x3 list of ints, HPTotal list of 3 ints)."""
+    """-> (HP 3x3 list of ints, HPTotal list of 3 ints).  cached: False = the plain loop, True = our rank cached per
+    runout, "4set" = also the opponent's rank cached per 4-set of unseen cards (treys mode, flop only)."""
     o, _ = _ints(our)
     b, nb = _ints(board)
     hp = (ctypes.c_uint32 * 9)()
     tot = (ctypes.c_uint32 * 3)()
     m = _mode(mode)
-    if m == MODE_TREYS and cached:
+    if m == MODE_TREYS and cached == "4set":
+        assert nb == 3
+        lib().ehs_hp_counts_treys_4set(o, b, hp, tot)
+    elif m == MODE_TREYS and cached:
         lib().ehs_hp_counts_treys_cached(o, b, nb, hp, tot)
     else:
         lib().ehs_hp_counts(m, o, b, nb, hp, tot)
@@ -182,12 +190,42 @@ def hs_batch(sit: np.ndarray, mode) -> np.ndarray:
     return out
 
 
-def hp_batch(sit: np.ndarray, mode) -> np.ndarray:
-    """-> uint32 [N,16]: ahead tied behind | HP[9] | HPTotal[3] | n_board."""
+def hp_batch(sit: np.ndarray, mode, cache4: bool = False) -> np.ndarray:
+    """-> uint32 [N,16]: ahead tied behind | HP[9] | HPTotal[3] | n_board.
+    cache4=True: treys-mode flop rows use the 4-set cache (~6x fewer evaluations; same counts)."""
     sit = np.ascontiguousarray(sit, dtype=np.uint8)
     out = np.zeros((sit.shape[0], 16), dtype=np.uint32)
-    lib().ehs_hp_batch(_mode(mode), sit.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), sit.shape[0],
-                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    lib().ehs_hp_batch_ex(_mode(mode), int(bool(cache4)), sit.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                          sit.shape[0], out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    return out
+
+
+def _hp_chunk(args):
+    sit_bytes, n, mode, cache4 = args
+    sit = np.frombuffer(sit_bytes, dtype=np.uint8).reshape(n, 8)
+    return hp_batch(sit, mode, cache4).tobytes()
+
+
+def hp_batch_parallel(sit: np.ndarray, mode, cache4: bool = True, procs: int = None) -> np.ndarray:
+    """hp_batch over all host cores (one forked process per core, rows dealt round-robin)."""
+    import multiprocessing as mp
+    sit = np.ascontiguousarray(sit, dtype=np.uint8)
+    n = sit.shape[0]
+    if procs is None:
+        try:
+            procs = len(os.sched_getaffinity(0))
+        except Exception:
+            procs = os.cpu_count() or 1
+    procs = max(1, min(procs, n))
+    lib()
+    out = np.zeros((n, 16), dtype=np.uint32)
+    if procs == 1:
+        return hp_batch(sit, mode, cache4)
+    parts_in = [np.ascontiguousarray(sit[i::procs]) for i in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        parts = pool.map(_hp_chunk, [(p.tobytes(), len(p), mode, cache4) for p in parts_in])
+    for i, p in enumerate(parts):
+        out[i::procs] = np.frombuffer(p, dtype=np.uint32).reshape(-1, 16)
     return out
 
 

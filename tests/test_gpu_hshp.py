@@ -118,6 +118,18 @@ def test_hp_full_size_properties(hb):
     assert torch.equal(rows[sl], direct)
 
 
+def test_hp_treys_all_65536_vs_oracle(hb, oracle):
+    """EVERY row of the headline workload (BASELINE.json configs[2]: 65,536 random flop situations, seed 20251019)
+    against the C oracle -- made affordable by the oracle's 4-set cache (oracle/ehs_oracle.c:
+    ehs_hp_counts_treys_4set, itself checked against the plain loop in tests/test_oracle_ehs.py), all host cores."""
+    n = 65536
+    sit = hb.random_situations(n, seed=20251019)
+    got = _u32(hb.hand_potential_counts(torch.from_numpy(sit).cuda(), "treys"))
+    want = oracle.hp_batch_parallel(sit, "treys", cache4=True)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad[:8], got[bad[:2]], want[bad[:2]])
+
+
 def test_dropin_handcalculations(hb):
     import HandCalculations as HC
     our_hs, board_hs = torch.tensor([0, 13]), torch.tensor([26, 27, 28, 29, 30])     # testing/ExampleHS.py:4-5

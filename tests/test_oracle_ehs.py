@@ -22,6 +22,25 @@ def test_hp_flop_regression_and_cache_equivalence():
     assert float(ppot) == 87.47679138183594 and float(npot) == 467.04071044921875
 
 
+def test_hp_flop_4set_cache_equals_plain_loop():
+    """The 4-set cache (178,365 opponent evaluations per situation) against the plain loop (1,070,190) on every
+    board texture, including our own flush draws; and the batch driver's two cache settings against each other."""
+    import numpy as np
+    cases = [([14, 1], [31, 32, 33]),            # monotone board, we hold none of it
+             ([0, 13], [26, 27, 28]),
+             ([5, 7], [1, 3, 9]),                # monotone, we hold two of the suit
+             ([5, 20], [1, 3, 30]),              # two-tone
+             ([12, 25], [0, 14, 28]),            # rainbow, paired with nothing
+             ([12, 25], [11, 24, 37]),           # trips on board
+             ([24, 48], [26, 2, 16])]
+    for our, board in cases:
+        plain = O.hp_counts(our, board, "treys", cached=False)
+        assert O.hp_counts(our, board, "treys", cached="4set") == plain, (our, board)
+    sit = O.pack_situations(cases)
+    assert np.array_equal(O.hp_batch(sit, "treys", cache4=True), O.hp_batch(sit, "treys", cache4=False))
+    assert np.array_equal(O.hp_batch_parallel(sit, "treys", procs=2), O.hp_batch(sit, "treys"))
+
+
 def test_hp_turn_and_river():
     our, board = [25, 50], [19, 30, 22, 37]
     hp, tot = O.hp_counts(our, board, "treys", cached=False)
