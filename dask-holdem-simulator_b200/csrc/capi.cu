@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -11,6 +12,10 @@
 #include "device_common.cuh"
 #include "launch.h"
 #include "tables.h"
+
+namespace holdem {
+std::atomic<unsigned long long> g_kernel_launches{0};
+}
 
 namespace {
 
@@ -34,7 +39,7 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 struct DeviceState {
-    bool ready = false;
+    std::atomic<bool> ready{false};
     int sms = 0;
     uint8_t *image = nullptr;
     DevTables T;
@@ -45,10 +50,43 @@ struct DeviceState {
     uint8_t *d_buf = nullptr;
     size_t d_buf_bytes = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
-    int *flags = nullptr;       // ring of device ints handed to the two-pass HP dispatch (one per call)
+    // Ring of 16-byte device slots (flag word + work counters) handed to the HP dispatch, one per call.  A slot is reused
+    // only behind the event recorded at the end of the call that used it last (stream-ordered wait, no host block), so any
+    // number of calls may be in flight on any number of streams.
+    int *flags = nullptr;
+    cudaEvent_t slot_done[1024] = {};
+    bool slot_used[1024] = {};
     unsigned flag_next = 0;
+    std::mutex flag_mu;
 };
 constexpr unsigned kFlagRing = 1024;
+
+struct FlagSlot {           // RAII: acquire() under the device's flag mutex, release() records the slot's event on the stream
+    DeviceState *S = nullptr;
+    unsigned idx = 0;
+    cudaStream_t st = nullptr;
+    int *ptr = nullptr;
+    std::unique_lock<std::mutex> lock;
+    cudaError_t acquire(DeviceState &state, cudaStream_t stream) {
+        S = &state;
+        st = stream;
+        lock = std::unique_lock<std::mutex>(state.flag_mu);
+        idx = state.flag_next++ % kFlagRing;
+        ptr = state.flags + 4 * idx;
+        if (state.slot_used[idx]) return cudaStreamWaitEvent(stream, state.slot_done[idx], 0);
+        cudaError_t e = cudaEventCreateWithFlags(&state.slot_done[idx], cudaEventDisableTiming);
+        if (e == cudaSuccess) state.slot_used[idx] = true;
+        return e;
+    }
+    cudaError_t release() {
+        cudaError_t e = S ? cudaEventRecord(S->slot_done[idx], st) : cudaSuccess;
+        S = nullptr;
+        if (lock.owns_lock()) lock.unlock();
+        return e;
+    }
+    ~FlagSlot() { if (S) release(); }
+};
+
 
 constexpr int kMaxDevices = 64;
 DeviceState g_dev[kMaxDevices];
@@ -173,6 +211,10 @@ int holdem_selftest_tables(void) {
 
 int holdem_init(int device) {
     if (device < 0 || device >= kMaxDevices) return fail(HOLDEM_ERR_BAD_ARG, "device index %d out of range", device);
+    if (g_dev[device].ready.load(std::memory_order_acquire)) {     // fast path: no lock, no device-count query
+        CUDA_TRY(cudaSetDevice(device));
+        return HOLDEM_OK;
+    }
     std::lock_guard<std::mutex> lock(g_init_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -232,7 +274,7 @@ int holdem_init(int device) {
     CUDA_TRY(cudaMalloc(&S.flags, 4 * kFlagRing * sizeof(int)));     // 16-byte slots: flag word + work counters
     CUDA_TRY(cudaMemset(S.flags, 0, 4 * kFlagRing * sizeof(int)));
     S.sms = prop.multiProcessorCount;
-    S.ready = true;
+    S.ready.store(true, std::memory_order_release);
     return HOLDEM_OK;
 }
 
@@ -361,42 +403,52 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
     return HOLDEM_OK;
 }
 
-// Treys mode: the deduplicating flop kernel takes every 3-card-board row and flags what else it saw; turn rows go to the
-// deduplicating turn kernel, river rows (HS only) to the plain-enumeration kernel.  Both exit at once when not needed.  Reference mode: plain enumeration only.
+// Which implementation serves each street of a Treys-mode HP call.  Production = {4, 4, 0}; the others are reached through the
+// explicit *_variant entry points only (A/B measurements and independent cross-checks).
+struct HpImpl {
+    int flop = 4;      // 4 rank-multiset kernel, 3 / 2 the 4-set kernels
+    int turn = 4;      // 4 rank-multiset kernel, 3 the 3-set walk
+    int river = 0;     // 0 rank-pair HS kernel in its HP-row form, 1 plain enumeration
+};
+
+// Treys mode: the flop kernel takes every 3-card-board row and flags what else it saw; turn rows go to the turn kernel, river
+// rows (HS only) to the rank-pair kernel.  Both exit at once when not needed.  Reference mode: hp_ref_kernel, all streets.
 static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out,
-                               cudaStream_t st, const PeerOut &peers = PeerOut{}, int **flag_out = nullptr) {
+                               cudaStream_t st, const PeerOut &peers = PeerOut{}, int **flag_out = nullptr,
+                               const HpImpl &impl = HpImpl{}) {
     // flag word of this call: bit 0 / 1 = the flop kernel met turn / river rows, bit 2 = some kernel marked a malformed row
     // (flag_out receives its address when every kernel of the call maintains bit 2, else nullptr)
+    FlagSlot slot;
+    cudaError_t e = slot.acquire(S, st);
+    if (e != cudaSuccess) return e;
+    int *flag = slot.ptr;
     if (mode == HOLDEM_MODE_REFERENCE) {
-        int *rflag = S.flags + 4 * (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-        cudaError_t e = cudaMemsetAsync(rflag, 0, sizeof(int), st);
+        e = cudaMemsetAsync(flag, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
-        e = launch_hp_ref(S.T, d_sit, n, d_out, S.sms, rflag, st);
+        e = launch_hp_ref(S.T, d_sit, n, d_out, S.sms, flag, st);
         if (e != cudaSuccess) return e;
-        if (flag_out) *flag_out = rflag;
-        return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, nullptr, st);
+        if (flag_out) *flag_out = flag;
+        e = launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, nullptr, st);
+        if (e != cudaSuccess) return e;
+        return slot.release();
     }
-    int *flag = S.flags + 4 * (__atomic_fetch_add(&S.flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    // HOLDEM_FLOP_KERNEL=3 / 2 and HOLDEM_TURN_KERNEL=3 select the earlier kernels (kept for A/B measurements and cross-checks)
-    static const int impl = getenv("HOLDEM_FLOP_KERNEL") ? atoi(getenv("HOLDEM_FLOP_KERNEL")) : 4;
-    static const int timpl = getenv("HOLDEM_TURN_KERNEL") ? atoi(getenv("HOLDEM_TURN_KERNEL")) : 4;
-    const bool old_flop = impl == 2 || impl == 3, old_turn = timpl == 3;
+    const bool old_flop = impl.flop == 2 || impl.flop == 3, old_turn = impl.turn == 3;
     const bool fused = !old_flop && !old_turn;          // the production kernels store their rows into the peers themselves
     const PeerOut none{};
-    cudaError_t e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl, st)
-                             : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st);
+    e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl.flop, st)
+                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st);
     if (e != cudaSuccess) return e;
     e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
                  : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st);
     if (e != cudaSuccess) return e;
-    // five-card boards (hand strength only): the rank-pair kernel; HOLDEM_HS_KERNEL=1 keeps the holding-by-holding enumeration
-    static const bool old_hs = getenv("HOLDEM_HS_KERNEL") && atoi(getenv("HOLDEM_HS_KERNEL")) == 1;
-    e = old_hs ? launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st)
-               : launch_hp_river_rows(S.T, d_sit, n, d_out, S.sms, flag, st);
+    e = impl.river == 1 ? launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st)
+                        : launch_hp_river_rows(S.T, d_sit, n, d_out, S.sms, flag, st);
     if (e != cudaSuccess) return e;
     if (flag_out) *flag_out = fused ? flag : nullptr;
     // river rows only (exits at once when there are none); every row when an earlier kernel was selected
-    return launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, fused ? flag : nullptr, st);
+    e = launch_rows_to_peers(d_sit, n, d_out, peers, S.sms, fused ? flag : nullptr, st);
+    if (e != cudaSuccess) return e;
+    return slot.release();
 }
 
 int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream) {
@@ -443,9 +495,11 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     if (variant < 2 || variant > 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
-    int *flag = S->flags + 4 * (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
-    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, nullptr, PeerOut{}, (cudaStream_t)stream));
-    else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, flag, variant, (cudaStream_t)stream));
+    FlagSlot slot;
+    CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
+    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream));
+    else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, slot.ptr, variant, (cudaStream_t)stream));
+    CUDA_TRY(slot.release());
     return HOLDEM_OK;
 }
 
@@ -465,21 +519,22 @@ int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || !d_cycles || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    int *flag = S->flags + 4 * (__atomic_fetch_add(&S->flag_next, 1u, __ATOMIC_RELAXED) % kFlagRing);
+    FlagSlot slot;
+    CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
     CUDA_TRY(cudaMemsetAsync(d_cycles, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
-    CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, flag, (unsigned long long *)d_cycles, PeerOut{},
+    CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, (unsigned long long *)d_cycles, PeerOut{},
                                      (cudaStream_t)stream));
+    CUDA_TRY(slot.release());
     return HOLDEM_OK;
 }
 
-int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out) {
+static int hp_batch_host_impl(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out, bool zero_copy) {
     if (n < 0 || (n > 0 && (!h_sit || !h_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     int rc = check_mode(mode);
     if (rc) return rc;
     // Page-locked caller buffers: one H2D copy of the 8-byte rows, ONE launch over the whole batch, and the kernels store
     // their 64-byte result rows straight into the caller's (mapped) host buffer -- the device-to-host transfer runs under
-    // the computation instead of after it.  HOLDEM_HOST_ZERO_COPY=0 selects the chunked copy pipeline instead.
-    static const bool zero_copy = !(getenv("HOLDEM_HOST_ZERO_COPY") && atoi(getenv("HOLDEM_HOST_ZERO_COPY")) == 0);
+    // the computation instead of after it.  holdem_hp_batch_host_staged selects the chunked copy pipeline instead.
     bool done = false;
     if (zero_copy && n > 0) {
         DeviceState *S = nullptr;
@@ -512,6 +567,117 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
     }
     for (int64_t i = 0; i < n; ++i)
         if (h_out[i * 16 + 15] == HOLDEM_BAD_ROW) return fail(HOLDEM_ERR_BAD_INPUT, "situation %lld is malformed", (long long)i);
+    return HOLDEM_OK;
+}
+
+int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out) {
+    return hp_batch_host_impl(h_sit, n, mode, h_out, true);
+}
+
+int holdem_hp_batch_host_staged(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out) {
+    return hp_batch_host_impl(h_sit, n, mode, h_out, false);
+}
+
+int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, int turn_variant, int river_variant,
+                            uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (flop_variant < 2 || flop_variant > 4 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
+        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..4, turn 3..4, river 0..1)");
+    HpImpl impl;
+    impl.flop = flop_variant; impl.turn = turn_variant; impl.river = river_variant;
+    CUDA_TRY(hp_dispatch(*S, d_sit, n, HOLDEM_MODE_TREYS, d_out, (cudaStream_t)stream, PeerOut{}, nullptr, impl));
+    return HOLDEM_OK;
+}
+
+int holdem_hs_batch_variant(const uint8_t *d_sit, int64_t n, int mode, int variant, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if ((rc = check_mode(mode))) return rc;
+    if (variant < 0 || variant > 1) return fail(HOLDEM_ERR_BAD_ARG, "unknown HS kernel variant %d", variant);
+    CUDA_TRY(launch_hs_batch(S->T, d_sit, n, mode, d_out, S->sms, (cudaStream_t)stream, variant));
+    return HOLDEM_OK;
+}
+
+int holdem_exhaustive7_variant(int variant, uint64_t *d_hist, uint64_t *d_sums, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (!d_hist || !d_sums) return fail(HOLDEM_ERR_BAD_ARG, "null pointer");
+    if (variant < 0 || variant > 1) return fail(HOLDEM_ERR_BAD_ARG, "unknown sweep kernel variant %d", variant);
+    CUDA_TRY(launch_exhaustive7(S->T, d_hist, d_sums, S->sms, (cudaStream_t)stream, variant));
+    return HOLDEM_OK;
+}
+
+// ---- board-shared table evaluation ------------------------------------------------------------------------------------------
+int holdem_table_hp_batch(const uint8_t *d_hole, const uint8_t *d_board, int64_t hands, int seats, int n_board, int mode,
+                          uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (hands < 0 || (hands > 0 && (!d_hole || !d_board || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative size");
+    if (seats < 1 || seats > 22) return fail(HOLDEM_ERR_BAD_ARG, "seats must be 1..22 (GameBoard.MAX_PLAYERS = 22), got %d", seats);
+    if (n_board < 3 || n_board > 5) return fail(HOLDEM_ERR_BAD_ARG, "n_board must be 3, 4 or 5 (got %d)", n_board);
+    if ((rc = check_mode(mode))) return rc;
+    if (hands == 0) return HOLDEM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = hands * seats;
+    uint8_t *d_sit = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_sit, (size_t)n * 8, st));           // stream-ordered scratch: the expanded situation rows
+    cudaError_t e = launch_table_rows(d_hole, d_board, hands, seats, n_board, d_sit, S->sms, st);
+    if (e == cudaSuccess) e = hp_dispatch(*S, d_sit, n, mode, d_out, st);
+    cudaFreeAsync(d_sit, st);
+    CUDA_TRY(e);
+    return HOLDEM_OK;
+}
+
+// ---- result-row hash, decision tree, wire-format packing (kernels_aux.cu) ------------------------------------------------
+unsigned long long holdem_kernel_launches(void) { return holdem::g_kernel_launches.load(std::memory_order_relaxed); }
+
+int holdem_rows_hash(const uint32_t *d_rows, int64_t n, int words_per_row, int64_t first_row, uint64_t *d_hash, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || !d_hash || words_per_row < 1 || (n > 0 && !d_rows)) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or bad size");
+    CUDA_TRY(launch_rows_hash(d_rows, n, words_per_row, first_row, d_hash, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_decide_batch(const double *d_hs, const double *d_ppot, const double *d_npot, const uint8_t *d_pos, int pos_all,
+                        int64_t n, int8_t *d_action, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_hs || !d_ppot || !d_npot || !d_action))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (!d_pos && (pos_all < 0 || pos_all > 2))
+        return fail(HOLDEM_ERR_BAD_ARG, "Invalid position. Expected 'SB', 'BB', or 'NONE'.");   /* Decision.py:8-9 */
+    CUDA_TRY(launch_decide(d_hs, d_ppot, d_npot, d_pos, pos_all, n, d_action, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_decide_from_counts(const uint32_t *d_rows, const uint8_t *d_pos, int pos_all, int64_t n, int8_t *d_action,
+                              double *d_hs_ppot_npot, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_rows || !d_action))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (!d_pos && (pos_all < 0 || pos_all > 2))
+        return fail(HOLDEM_ERR_BAD_ARG, "Invalid position. Expected 'SB', 'BB', or 'NONE'.");
+    CUDA_TRY(launch_decide_from_counts(d_rows, d_pos, pos_all, n, d_action, d_hs_ppot_npot, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
+int holdem_pack_rank_major(const int64_t *d_hole, const int64_t *d_board, int n_board, int64_t n, uint8_t *d_sit, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || n_board < 3 || n_board > 5 || (n > 0 && (!d_hole || !d_board || !d_sit)))
+        return fail(HOLDEM_ERR_BAD_ARG, "null pointer, negative n or n_board outside 3..5");
+    CUDA_TRY(launch_pack_rank_major(d_hole, d_board, n_board, n, d_sit, S->sms, (cudaStream_t)stream));
     return HOLDEM_OK;
 }
 

@@ -243,7 +243,7 @@ static cudaError_t launch_eval_nc(const DevTables &T, const uint8_t *cards, int6
             cudaError_t e = cudaFuncSetAttribute(eval_batch_kernel<NC, true>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            eval_batch_kernel<NC, true><<<sms, 1024, smem, st>>>(c2, n, out, T);
+            count_launch(); eval_batch_kernel<NC, true><<<sms, 1024, smem, st>>>(c2, n, out, T);
         } else {
             // the kernel masks value-table slots with a compile-time constant (16 / 15 / 13 slot bits, tables.cpp)
             if (T.val_entries[NC - 5] != (NC == 7 ? 65536u : (NC == 6 ? 32768u : 8192u))) return cudaErrorInvalidValue;
@@ -253,14 +253,14 @@ static cudaError_t launch_eval_nc(const DevTables &T, const uint8_t *cards, int6
             if (e != cudaSuccess) return e;
             // 32-bit hand indices inside the kernel: batches of 2^31 hands or more go in pieces
             constexpr int64_t kPiece = (int64_t)1 << 30;
-            for (int64_t off = 0; off < n; off += kPiece)
+            for (int64_t off = 0; off < n; off += kPiece, count_launch())
                 eval_batch_fast_kernel<NC><<<sms, 1024, smem, st>>>(c2 + off, n - off < kPiece ? n - off : kPiece, out + off, T,
                                                                      1u);
         }
     } else {
         int blocks = (int)((n + 255) / 256);
         if (blocks > sms * 8) blocks = sms * 8;
-        eval_batch_kernel<NC, false><<<blocks, 256, 1024, st>>>(c2, n, out, T);
+        count_launch(); eval_batch_kernel<NC, false><<<blocks, 256, 1024, st>>>(c2, n, out, T);
     }
     return cudaGetLastError();
 }
@@ -301,7 +301,7 @@ cudaError_t launch_category_batch(const uint8_t *cards, int n_cards, int row_str
     if (n == 0) return cudaSuccess;
     int blocks = (int)((n + 255) / 256);
     if (blocks > sms * 8) blocks = sms * 8;
-    category_batch_kernel<<<blocks, 256, 0, st>>>(cards, n_cards, row_stride, n, out);
+    count_launch(); category_batch_kernel<<<blocks, 256, 0, st>>>(cards, n_cards, row_stride, n, out);
     return cudaGetLastError();
 }
 
@@ -550,25 +550,25 @@ exhaustive7_tuple_kernel(unsigned long long *__restrict__ hist, unsigned long lo
         if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
 }
 
-cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st) {
+cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st, int variant) {
     cudaError_t e = cudaMemsetAsync(hist, 0, 7463 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(sums, 0, 2 * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
-    static const bool chunked = [] { const char *v = getenv("HOLDEM_EXHAUSTIVE_KERNEL"); return v && atoi(v) == 1; }();
+    const bool chunked = variant == 1;
     if (!chunked) {
         if (T.val_entries[2] != 65536u) return cudaErrorInvalidValue;   // the kernel masks slots with 0xFFFF
         const size_t smem2 = kSweepHead + 2 * (size_t)(kFlushEntries + T.disp_entries[2] + T.val_entries[2]);
         e = cudaFuncSetAttribute(exhaustive7_tuple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return e;
-        exhaustive7_tuple_kernel<<<sms, 1024, smem2, st>>>(reinterpret_cast<unsigned long long *>(hist),
+        count_launch(); exhaustive7_tuple_kernel<<<sms, 1024, smem2, st>>>(reinterpret_cast<unsigned long long *>(hist),
                                                           reinterpret_cast<unsigned long long *>(sums), T);
         return cudaGetLastError();
     }
     size_t smem = (64 + 53 * 8 + 7464) * 4 + 2 * (size_t)(kFlushEntries + T.disp_entries[2] + T.val_entries[2]);
     e = cudaFuncSetAttribute(exhaustive7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    exhaustive7_kernel<<<sms, 1024, smem, st>>>(reinterpret_cast<unsigned long long *>(hist),
+    count_launch(); exhaustive7_kernel<<<sms, 1024, smem, st>>>(reinterpret_cast<unsigned long long *>(hist),
                                                reinterpret_cast<unsigned long long *>(sums), T);
     return cudaGetLastError();
 }
@@ -623,7 +623,7 @@ cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int bloc
     }
     cudaError_t e = cudaFuncSetAttribute(smem_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, table_bytes);
     if (e != cudaSuccess) return e;
-    smem_gather_kernel<<<blocks, threads, table_bytes, st>>>(table_bytes / 2, iters, pattern, sink);
+    count_launch(); smem_gather_kernel<<<blocks, threads, table_bytes, st>>>(table_bytes / 2, iters, pattern, sink);
     return cudaGetLastError();
 }
 
@@ -673,7 +673,7 @@ cudaError_t launch_int_issue(int iters, int mix, int blocks, int threads, cudaSt
         cudaError_t e = cudaMalloc(&sink, 4);
         if (e != cudaSuccess) return e;
     }
-    int_issue_kernel<<<blocks, threads, 0, st>>>(iters, mix, 1u, sink);
+    count_launch(); int_issue_kernel<<<blocks, threads, 0, st>>>(iters, mix, 1u, sink);
     return cudaGetLastError();
 }
 

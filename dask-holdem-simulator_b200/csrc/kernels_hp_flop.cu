@@ -516,7 +516,7 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
         if (blocks3 > n) blocks3 = n;
         e3 = cudaMemsetAsync(other_rows_flag, 0, sizeof(int), st);
         if (e3 != cudaSuccess) return e3;
-        hp_flop_treys_v3_kernel<<<(int)blocks3, kThreads, smem3, st>>>(sit, n, out, T, other_rows_flag, 1u);
+        count_launch(); hp_flop_treys_v3_kernel<<<(int)blocks3, kThreads, smem3, st>>>(sit, n, out, T, other_rows_flag, 1u);
         return cudaGetLastError();
     }
     const size_t smem = sizeof(FlopSmem);
@@ -532,7 +532,7 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
     if (blocks > n) blocks = n;
     e = cudaMemsetAsync(other_rows_flag, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    hp_flop_treys_kernel<<<(int)blocks, kThreads, smem, st>>>(sit, n, out, T, other_rows_flag);
+    count_launch(); hp_flop_treys_kernel<<<(int)blocks, kThreads, smem, st>>>(sit, n, out, T, other_rows_flag);
     return cudaGetLastError();
 }
 

@@ -687,6 +687,7 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
     e = cudaMemsetAsync(other_rows_flag, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return e;
     // the phase clocks are compiled out of the production instance: the kernel is sensitive to its code size
+    count_launch();
     if (prof) hp_flop_treys_v4_kernel<true><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
                                                                                     reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
     else hp_flop_treys_v4_kernel<false><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,

@@ -367,7 +367,7 @@ cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uin
     }
     int64_t blocks = (int64_t)sms * bps;
     if (blocks > n) blocks = n;
-    hp_ref_kernel<<<(int)blocks, kRThreads, smem, st>>>(sit, n, out, T, 1u, bad_flag);
+    count_launch(); hp_ref_kernel<<<(int)blocks, kRThreads, smem, st>>>(sit, n, out, T, 1u, bad_flag);
     return cudaGetLastError();
 }
 

@@ -247,7 +247,7 @@ cudaError_t launch_hp_turn_treys(const DevTables &T, const uint8_t *sit, int64_t
     }
     int64_t blocks = (int64_t)sms * bps;
     if (blocks > n) blocks = n;
-    hp_turn_treys_kernel<<<(int)blocks, kTThreads, smem, st>>>(sit, n, out, T, run_flag, 1u);
+    count_launch(); hp_turn_treys_kernel<<<(int)blocks, kTThreads, smem, st>>>(sit, n, out, T, run_flag, 1u);
     return cudaGetLastError();
 }
 

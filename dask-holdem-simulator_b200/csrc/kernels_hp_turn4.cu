@@ -603,7 +603,7 @@ cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (blocks * kNG > n) blocks = (n + kNG - 1) / kNG;
     // run_flag, when given, is the call's 16-byte slot: [0] flag word, [2] this kernel's work counter (zeroed with the slot)
     if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
-    hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u, peers,
+    count_launch(); hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u, peers,
                                                                   run_flag ? reinterpret_cast<unsigned int *>(run_flag) + 2 : nullptr);
     return cudaGetLastError();
 }
@@ -628,7 +628,7 @@ cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *
     if (n == 0 || peers.n == 0) return cudaSuccess;
     int64_t blocks = (n * 16 + 255) / 256;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-    rows_to_peers_kernel<<<(int)blocks, 256, 0, st>>>(sit, n, out, peers, run_flag);
+    count_launch(); rows_to_peers_kernel<<<(int)blocks, 256, 0, st>>>(sit, n, out, peers, run_flag);
     return cudaGetLastError();
 }
 

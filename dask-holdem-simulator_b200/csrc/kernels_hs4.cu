@@ -201,7 +201,7 @@ cudaError_t launch_hs_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n
     if (n == 0) return cudaSuccess;
     int64_t blocks = (n + kHs4Warps - 1) / kHs4Warps;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-    hs_treys_v4_kernel<false><<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T, nullptr);
+    count_launch(); hs_treys_v4_kernel<false><<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T, nullptr);
     return cudaGetLastError();
 }
 
@@ -210,7 +210,7 @@ cudaError_t launch_hp_river_rows(const DevTables &T, const uint8_t *sit, int64_t
     if (n == 0) return cudaSuccess;
     int64_t blocks = (n + kHs4Warps - 1) / kHs4Warps;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-    hs_treys_v4_kernel<true><<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T, run_flag);
+    count_launch(); hs_treys_v4_kernel<true><<<(int)blocks, kHs4Warps * 32, 0, st>>>(sit, n, out, T, run_flag);
     return cudaGetLastError();
 }
 

@@ -155,13 +155,12 @@ hs_kernel(const uint8_t *__restrict__ sit, int64_t n, int mode, uint32_t *__rest
 }
 
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
-                            cudaStream_t st) {
+                            cudaStream_t st, int variant) {
     if (n == 0) return cudaSuccess;
-    static const bool old_kernel = getenv("HOLDEM_HS_KERNEL") && atoi(getenv("HOLDEM_HS_KERNEL")) == 1;
-    if (mode == kModeTreys && !old_kernel) return launch_hs_treys_v4(T, sit, n, out, sms, st);
+    if (mode == kModeTreys && variant == 0) return launch_hs_treys_v4(T, sit, n, out, sms, st);
     int64_t blocks = (n + kHsWarps - 1) / kHsWarps;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
-    hs_kernel<<<(int)blocks, kHsWarps * 32, 0, st>>>(sit, n, mode, out, T);
+    count_launch(); hs_kernel<<<(int)blocks, kHsWarps * 32, 0, st>>>(sit, n, mode, out, T);
     return cudaGetLastError();
 }
 
@@ -347,11 +346,11 @@ cudaError_t launch_hp_direct(const DevTables &T, const uint8_t *sit, int64_t n, 
     if (mode == kModeTreys) {
         e = cudaFuncSetAttribute(hp_direct_kernel<kModeTreys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hp_direct_kernel<kModeTreys><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_boards);
+        count_launch(); hp_direct_kernel<kModeTreys><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_boards);
     } else {
         e = cudaFuncSetAttribute(hp_direct_kernel<kModeReference>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hp_direct_kernel<kModeReference><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_boards);
+        count_launch(); hp_direct_kernel<kModeReference><<<(int)blocks, kHpThreads, smem, st>>>(sit, n, out, T, run_flag, skip_boards);
     }
     return cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // launch.h -- host-callable launchers of the kernels (internal to the library; the public surface is
 // include/holdem_b200.h).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -17,18 +18,25 @@ struct PeerOut {
 
 constexpr uint32_t kFlushEntries = 8192;
 
+// Every kernel launch of the library is counted (process-wide); holdem_kernel_launches() reports the total, so callers
+// (bench.py's gpu_launches) report a measured count instead of a formula.
+extern std::atomic<unsigned long long> g_kernel_launches;
+inline void count_launch() { g_kernel_launches.fetch_add(1ull, std::memory_order_relaxed); }
+
 // strict: also detect duplicate cards inside a row (builds the card set; ~1.5x the instructions of the fast path).
 cudaError_t launch_eval_batch(const DevTables &T, const uint8_t *cards, int n_cards, int64_t n, uint16_t *out,
                               int sms, bool strict, cudaStream_t st);
 cudaError_t launch_category_batch(const uint8_t *cards, int n_cards, int row_stride, int64_t n, uint8_t *out,
                                   int sms, cudaStream_t st);
-cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st);
+// variant 0 = tuple kernel (production), 1 = the older chunk-per-thread kernel.
+cudaError_t launch_exhaustive7(const DevTables &T, uint64_t *hist, uint64_t *sums, int sms, cudaStream_t st, int variant = 0);
 cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int blocks, int threads, cudaStream_t st);
 // 16 warp instructions per thread per iteration; mix 0 = compare + predicated multiply-add, 1 = FMA pipe only, 2 = ALU pipe only
 cudaError_t launch_int_issue(int iters, int mix, int blocks, int threads, cudaStream_t st);
 
+// variant 0 = production (treys: rank-pair kernel; reference: per-holding kernel), 1 = the per-holding kernel for both modes.
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
-                            cudaStream_t st);
+                            cudaStream_t st, int variant = 0);
 // Treys-mode hand strength from rank pairs (kernels_hs4.cu): same results, what launch_hs_batch runs for HOLDEM_MODE_TREYS
 // unless HOLDEM_HS_KERNEL=1 selects the holding-by-holding kernel.
 cudaError_t launch_hs_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
@@ -64,5 +72,17 @@ cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *
 // bad_flag: optional device int, bit 2 is set when a malformed row was marked (every HP kernel does this on its flag word).
 cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *bad_flag,
                           cudaStream_t st);
+
+// kernels_aux.cu: content hash of result rows, the Decision.py threshold tree, rank-major wire ints -> situation rows.
+cudaError_t launch_rows_hash(const uint32_t *rows, int64_t n, int words, int64_t first_row, uint64_t *out, int sms,
+                             cudaStream_t st);
+cudaError_t launch_decide(const double *hs, const double *ppot, const double *npot, const uint8_t *pos, int pos_all,
+                          int64_t n, int8_t *out, int sms, cudaStream_t st);
+cudaError_t launch_decide_from_counts(const uint32_t *rows, const uint8_t *pos, int pos_all, int64_t n, int8_t *out,
+                                      double *hs_ppot_npot, int sms, cudaStream_t st);
+cudaError_t launch_table_rows(const uint8_t *hole, const uint8_t *board, int64_t hands, int seats, int n_board,
+                              uint8_t *sit, int sms, cudaStream_t st);
+cudaError_t launch_pack_rank_major(const int64_t *hole, const int64_t *board, int n_board, int64_t n, uint8_t *sit,
+                                   int sms, cudaStream_t st);
 
 }  // namespace holdem

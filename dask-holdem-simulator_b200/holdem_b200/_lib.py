@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libholdem_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODE_TREYS = 0
 MODE_REFERENCE = 1
 HP_ROW = 16
@@ -44,6 +44,16 @@ SYMBOLS = {
     "holdem_hs_batch_host": (_i, [_vp, _i64, _i, _vp]),
     "holdem_hp_batch": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_batch_host": (_i, [_vp, _i64, _i, _vp]),
+    "holdem_hp_batch_host_staged": (_i, [_vp, _i64, _i, _vp]),
+    "holdem_hp_batch_variant": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "holdem_hs_batch_variant": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
+    "holdem_exhaustive7_variant": (_i, [_i, _vp, _vp, _vp]),
+    "holdem_rows_hash": (_i, [_vp, _i64, _i, _i64, _vp, _vp]),
+    "holdem_decide_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "holdem_decide_from_counts": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "holdem_pack_rank_major": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "holdem_kernel_launches": (ctypes.c_ulonglong, []),
+    "holdem_table_hp_batch": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "holdem_hp_batch_direct": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_batch_peers": (_i, [_vp, _i64, _i, _vp, ctypes.POINTER(_vp), _i, _vp]),
     "holdem_hp_flop_variant": (_i, [_vp, _i64, _i, _vp, _vp]),

@@ -13,7 +13,9 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib
+import contextlib
+
+from . import _lib, _ops
 from ._lib import MODE_REFERENCE, MODE_TREYS, HP_ROW, HS_ROW
 
 __all__ = [
@@ -21,6 +23,7 @@ __all__ = [
     "hand_potential_counts", "flop_phase_cycles", "exhaustive7", "hs_from_counts", "potentials_from_counts",
     "normalised_potentials", "ehs_from_counts", "evaluate_host", "category_host", "hand_strength_counts_host",
     "hand_potential_counts_host", "smem_gather_microbench", "int_issue_microbench", "EVALS_PER_FLOP_SITUATION",
+    "rows_hash", "rows_hash_host", "table_hand_potential_counts", "kernel_launches", "pack_rank_major",
 ]
 
 # algorithmic evaluations per situation
@@ -46,79 +49,136 @@ def _require_cuda(t: torch.Tensor, name: str, dtype, cols=None):
     return t
 
 
+@contextlib.contextmanager
 def _enter(t: torch.Tensor):
-    """Initialise the library on the tensor's device; returns (lib, raw stream handle)."""
+    """ctypes binding: make the tensor's device current for the duration of the C call (the caller's current device is
+    restored afterwards), initialise the library there once; yields (lib, raw handle of torch's current stream)."""
     dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
-    torch.cuda.set_device(dev)
-    lib = _lib.init(dev)
-    return lib, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        lib = _lib.load() if dev in _lib._inited else _lib.init(dev)
+        yield lib, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ops_ns(binding):
+    """binding: "ops" (default) = torch.ops.holdem.* (csrc/torch_ops.cpp), "ctypes" = the plain C-ABI binding."""
+    if binding == "ops":
+        return _ops.load()
+    if binding != "ctypes":
+        raise ValueError("binding must be 'ops' or 'ctypes'")
+    return None
 
 
 # ---- device entry points ---------------------------------------------------------------------------------------------
-def evaluate(cards: torch.Tensor, n_cards: int, out: torch.Tensor = None, strict: bool = False) -> torch.Tensor:
+def evaluate(cards: torch.Tensor, n_cards: int, out: torch.Tensor = None, strict: bool = False,
+             binding: str = "ops") -> torch.Tensor:
     """Treys rank (1..7462, lower is better) of each row's first n_cards (5/6/7) cards.  cards: uint8 [N,8].
     Rows with a card > 51 give 0.  strict=True also gives 0 for rows with duplicate cards (the large-batch fast path
     does not look for duplicates, exactly like Treys)."""
     _require_cuda(cards, "cards", torch.uint8, 8)
     if n_cards not in (5, 6, 7):
         raise KeyError(n_cards)  # treys.Evaluator.hand_size_map
+    ops = _ops_ns(binding)
+    if ops is not None and out is None:
+        return ops.eval(cards, n_cards, strict)
     if out is None:
         out = torch.empty(cards.shape[0], dtype=torch.int16, device=cards.device)
-    lib, st = _enter(cards)
-    fn = lib.holdem_eval_batch_strict if strict else lib.holdem_eval_batch
-    _lib.check(fn(cards.data_ptr(), n_cards, cards.shape[0], out.data_ptr(), st))
+    with _enter(cards) as (lib, st):
+        fn = lib.holdem_eval_batch_strict if strict else lib.holdem_eval_batch
+        _lib.check(fn(cards.data_ptr(), n_cards, cards.shape[0], out.data_ptr(), st))
     return out
 
 
-def category(cards: torch.Tensor, n_cards: int) -> torch.Tensor:
+def category(cards: torch.Tensor, n_cards: int, binding: str = "ops") -> torch.Tensor:
     """Literal CalculateHandRankValue category 0..8 of each row's first n_cards (2..9) cards, duplicates allowed."""
     _require_cuda(cards, "cards", torch.uint8)
     if cards.dim() != 2 or cards.shape[1] < n_cards:
         raise ValueError("cards must be [N, >= n_cards]")
+    ops = _ops_ns(binding)
+    if ops is not None:
+        return ops.category(cards, n_cards)
     out = torch.empty(cards.shape[0], dtype=torch.uint8, device=cards.device)
-    lib, st = _enter(cards)
-    _lib.check(lib.holdem_category_batch(cards.data_ptr(), n_cards, cards.shape[1], cards.shape[0],
-                                         out.data_ptr(), st))
+    with _enter(cards) as (lib, st):
+        _lib.check(lib.holdem_category_batch(cards.data_ptr(), n_cards, cards.shape[1], cards.shape[0],
+                                             out.data_ptr(), st))
     return out
 
 
-def hand_strength_counts(sit: torch.Tensor, mode="treys") -> torch.Tensor:
-    """(ahead, tied, behind) per situation: int32 [N,3].  sit: uint8 [N,8] rows h0 h1 b0..b4(0xFF) pad."""
+def hand_strength_counts(sit: torch.Tensor, mode="treys", variant: int = None, binding: str = "ops") -> torch.Tensor:
+    """(ahead, tied, behind) per situation: int32 [N,3].  sit: uint8 [N,8] rows h0 h1 b0..b4(0xFF) pad.
+    variant (A/B measurements): 0 = production kernel, 1 = one evaluation per opponent holding."""
     _require_cuda(sit, "sit", torch.uint8, 8)
+    ops = _ops_ns(binding)
+    if ops is not None and variant is None:
+        return ops.hs(sit, mode_id(mode))
     out = torch.empty((sit.shape[0], HS_ROW), dtype=torch.int32, device=sit.device)
-    lib, st = _enter(sit)
-    _lib.check(lib.holdem_hs_batch(sit.data_ptr(), sit.shape[0], mode_id(mode), out.data_ptr(), st))
+    with _enter(sit) as (lib, st):
+        if variant is None:
+            _lib.check(lib.holdem_hs_batch(sit.data_ptr(), sit.shape[0], mode_id(mode), out.data_ptr(), st))
+        else:
+            _lib.check(lib.holdem_hs_batch_variant(sit.data_ptr(), sit.shape[0], mode_id(mode), int(variant),
+                                                   out.data_ptr(), st))
     return out
 
 
 def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = None,
-                          direct: bool = False, flop_variant: int = None, turn_variant: int = None) -> torch.Tensor:
+                          direct: bool = False, flop_variant: int = None, turn_variant: int = None,
+                          variants=None, binding: str = "ops") -> torch.Tensor:
     """HS + HP counts per situation: int32 [N,16] = ahead tied behind | HP[3][3] | HPTotal[3] | n_board.
     `out` may be a [N,16] int32 view into a larger buffer (e.g. this rank's slice of an all-gather buffer).
     direct=True forces the plain-enumeration kernel (the independent second implementation).  flop_variant (treys mode,
     flop rows only; 4 = rank-multiset kernel, 3 / 2 = the 4-set kernels) runs one named implementation of the flop kernel
     for A/B measurements; rows of other streets are then left as they are in `out`.  turn_variant (4 = rank-multiset
-    kernel, 3 = 3-set walk) does the same for turn rows."""
+    kernel, 3 = 3-set walk) does the same for turn rows.  variants=(flop, turn, river) runs a whole mixed-street treys batch
+    through named kernels (holdem_hp_batch_variant)."""
     _require_cuda(sit, "sit", torch.uint8, 8)
+    plain = not direct and flop_variant is None and turn_variant is None and variants is None
+    ops = _ops_ns(binding)
+    if ops is not None and plain and out is None:
+        return ops.hp(sit, mode_id(mode))
     if out is None:
         out = torch.empty((sit.shape[0], HP_ROW), dtype=torch.int32, device=sit.device)
     else:
         _require_cuda(out, "out", torch.int32, HP_ROW)
         if out.shape[0] != sit.shape[0] or out.device != sit.device:
             raise ValueError("out must be [N,16] on the same device as sit")
-    lib, st = _enter(sit)
-    if turn_variant is not None:
-        if mode_id(mode) != MODE_TREYS or direct or flop_variant is not None:
-            raise ValueError("turn_variant applies to mode='treys' alone")
-        _lib.check(lib.holdem_hp_turn_variant(sit.data_ptr(), sit.shape[0], int(turn_variant), out.data_ptr(), st))
+    if ops is not None and plain:
+        ops.hp_out(sit, mode_id(mode), out)
         return out
-    if flop_variant is not None:
-        if mode_id(mode) != MODE_TREYS or direct:
-            raise ValueError("flop_variant applies to mode='treys' without direct=True")
-        _lib.check(lib.holdem_hp_flop_variant(sit.data_ptr(), sit.shape[0], int(flop_variant), out.data_ptr(), st))
-        return out
-    fn = lib.holdem_hp_batch_direct if direct else lib.holdem_hp_batch
-    _lib.check(fn(sit.data_ptr(), sit.shape[0], mode_id(mode), out.data_ptr(), st))
+    with _enter(sit) as (lib, st):
+        if variants is not None:
+            if mode_id(mode) != MODE_TREYS or direct or flop_variant is not None or turn_variant is not None:
+                raise ValueError("variants applies to mode='treys' alone")
+            f, t, r = (int(v) for v in variants)
+            _lib.check(lib.holdem_hp_batch_variant(sit.data_ptr(), sit.shape[0], f, t, r, out.data_ptr(), st))
+        elif turn_variant is not None:
+            if mode_id(mode) != MODE_TREYS or direct or flop_variant is not None:
+                raise ValueError("turn_variant applies to mode='treys' alone")
+            _lib.check(lib.holdem_hp_turn_variant(sit.data_ptr(), sit.shape[0], int(turn_variant), out.data_ptr(), st))
+        elif flop_variant is not None:
+            if mode_id(mode) != MODE_TREYS or direct:
+                raise ValueError("flop_variant applies to mode='treys' without direct=True")
+            _lib.check(lib.holdem_hp_flop_variant(sit.data_ptr(), sit.shape[0], int(flop_variant), out.data_ptr(), st))
+        else:
+            fn = lib.holdem_hp_batch_direct if direct else lib.holdem_hp_batch
+            _lib.check(fn(sit.data_ptr(), sit.shape[0], mode_id(mode), out.data_ptr(), st))
+    return out
+
+
+def table_hand_potential_counts(hole: torch.Tensor, board: torch.Tensor, n_board: int, mode="treys",
+                                binding: str = "ops") -> torch.Tensor:
+    """Whole tables (GameBoard.py:12, :204-229): hole uint8 [H,S,2], board uint8 [H,5] -> int32 [H,S,16], the HS+HP rows
+    of every seat on the first n_board (3/4/5) board cards."""
+    _require_cuda(hole, "hole", torch.uint8)
+    _require_cuda(board, "board", torch.uint8, 5)
+    if hole.dim() != 3 or hole.shape[2] != 2 or board.shape[0] != hole.shape[0] or board.device != hole.device:
+        raise ValueError("expected hole [H,S,2] and board [H,5] on one device")
+    ops = _ops_ns(binding)
+    if ops is not None:
+        return ops.table_hp(hole, board, int(n_board), mode_id(mode))
+    out = torch.empty((hole.shape[0], hole.shape[1], HP_ROW), dtype=torch.int32, device=hole.device)
+    with _enter(hole) as (lib, st):
+        _lib.check(lib.holdem_table_hp_batch(hole.data_ptr(), board.data_ptr(), hole.shape[0], hole.shape[1], int(n_board),
+                                             mode_id(mode), out.data_ptr(), st))
     return out
 
 
@@ -128,19 +188,64 @@ def flop_phase_cycles(sit: torch.Tensor):
     _require_cuda(sit, "sit", torch.uint8, 8)
     out = torch.empty((sit.shape[0], HP_ROW), dtype=torch.int32, device=sit.device)
     cyc = torch.zeros(4, dtype=torch.int64, device=sit.device)
-    lib, st = _enter(sit)
-    _lib.check(lib.holdem_hp_flop_phase_cycles(sit.data_ptr(), sit.shape[0], out.data_ptr(), cyc.data_ptr(), st))
+    with _enter(sit) as (lib, st):
+        _lib.check(lib.holdem_hp_flop_phase_cycles(sit.data_ptr(), sit.shape[0], out.data_ptr(), cyc.data_ptr(), st))
     return out, cyc
 
 
-def exhaustive7(device=None):
-    """All C(52,7) hands evaluated in-kernel -> (hist int64 [7463] indexed by rank, sums int64 [2] = sum r, sum r^2)."""
+def exhaustive7(device=None, variant: int = None):
+    """All C(52,7) hands evaluated in-kernel -> (hist int64 [7463] indexed by rank, sums int64 [2] = sum r, sum r^2).
+    variant: None / 0 = tuple kernel (production), 1 = chunk-per-thread kernel."""
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     hist = torch.empty(7463, dtype=torch.int64, device=dev)
     sums = torch.empty(2, dtype=torch.int64, device=dev)
-    lib, st = _enter(hist)
-    _lib.check(lib.holdem_exhaustive7(hist.data_ptr(), sums.data_ptr(), st))
+    with _enter(hist) as (lib, st):
+        if variant is None:
+            _lib.check(lib.holdem_exhaustive7(hist.data_ptr(), sums.data_ptr(), st))
+        else:
+            _lib.check(lib.holdem_exhaustive7_variant(int(variant), hist.data_ptr(), sums.data_ptr(), st))
     return hist, sums
+
+
+def rows_hash(rows: torch.Tensor, first_row: int = 0) -> int:
+    """64-bit content hash of a contiguous int32 [n, words] CUDA buffer (holdem_rows_hash): position-dependent through
+    first_row + row index, additive over shards (mod 2^64).  Synchronises (returns a Python int)."""
+    _require_cuda(rows, "rows", torch.int32)
+    if rows.dim() != 2:
+        raise ValueError("rows must be [n, words]")
+    out = torch.empty(1, dtype=torch.int64, device=rows.device)
+    with _enter(rows) as (lib, st):
+        _lib.check(lib.holdem_rows_hash(rows.data_ptr(), rows.shape[0], rows.shape[1], int(first_row), out.data_ptr(), st))
+    return int(out.item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def rows_hash_host(rows, first_row: int = 0) -> int:
+    """numpy twin of rows_hash (same value) for host-side checks of buffers that never were on a device."""
+    r = np.ascontiguousarray(rows).view(np.uint32).astype(np.uint64)
+    n = r.shape[0]
+    M = np.uint64
+
+    def mix(x):
+        x = x ^ (x >> M(30)); x = x * M(0xBF58476D1CE4E5B9)
+        x = x ^ (x >> M(27)); x = x * M(0x94D049BB133111EB)
+        return x ^ (x >> M(31))
+
+    with np.errstate(over="ignore"):
+        h = M(0xCBF29CE484222325) ^ mix(np.arange(first_row, first_row + n, dtype=np.uint64) + M(0x9E3779B97F4A7C15))
+        for w in range(r.shape[1]):
+            h = (h ^ r[:, w]) * M(0x100000001B3)
+        return int(mix(h).sum(dtype=np.uint64))
+
+
+def pack_rank_major(hole: torch.Tensor, board: torch.Tensor) -> torch.Tensor:
+    """utils.card_to_int wire ints (utils.py:82-85: rank * 4 + suit; int64 [N,2] and [N,3..5], CUDA) -> uint8 [N,8]
+    situation rows in the path encoding.  Values outside [0,52) become 0xFE, which the kernels report as malformed rows."""
+    return _ops.load().pack_rank_major(hole.contiguous(), board.contiguous())
+
+
+def kernel_launches() -> int:
+    """Kernels launched by the library in this process so far (every launch site counts itself)."""
+    return int(_lib.load().holdem_kernel_launches())
 
 
 # ---- floats from counts (the reference's formulas, same dtype and operation order) -----------------------------------------
@@ -191,10 +296,11 @@ def ehs_from_counts(rows: torch.Tensor) -> torch.Tensor:
 
 
 # ---- host entry points (numpy in / numpy out; copies happen inside the library) -----------------------------------------------
+@contextlib.contextmanager
 def _host_enter(device):
     dev = torch.cuda.current_device() if device is None else int(device)
-    torch.cuda.set_device(dev)
-    return _lib.init(dev)
+    with torch.cuda.device(dev):
+        yield _lib.load() if dev in _lib._inited else _lib.init(dev)
 
 
 def _np_u8(a, cols=None):
@@ -209,52 +315,54 @@ def evaluate_host(cards, n_cards: int, device=None) -> np.ndarray:
     if n_cards not in (5, 6, 7):
         raise KeyError(n_cards)
     out = np.empty(cards.shape[0], dtype=np.uint16)
-    lib = _host_enter(device)
-    _lib.check(lib.holdem_eval_batch_host(cards.ctypes.data, n_cards, cards.shape[0], out.ctypes.data))
+    with _host_enter(device) as lib:
+        _lib.check(lib.holdem_eval_batch_host(cards.ctypes.data, n_cards, cards.shape[0], out.ctypes.data))
     return out
 
 
 def category_host(cards, n_cards: int, device=None) -> np.ndarray:
     cards = _np_u8(cards)
     out = np.empty(cards.shape[0], dtype=np.uint8)
-    lib = _host_enter(device)
-    _lib.check(lib.holdem_category_batch_host(cards.ctypes.data, n_cards, cards.shape[1], cards.shape[0],
-                                              out.ctypes.data))
+    with _host_enter(device) as lib:
+        _lib.check(lib.holdem_category_batch_host(cards.ctypes.data, n_cards, cards.shape[1], cards.shape[0],
+                                                  out.ctypes.data))
     return out
 
 
 def hand_strength_counts_host(sit, mode="treys", device=None) -> np.ndarray:
     sit = _np_u8(sit, 8)
     out = np.empty((sit.shape[0], HS_ROW), dtype=np.uint32)
-    lib = _host_enter(device)
-    _lib.check(lib.holdem_hs_batch_host(sit.ctypes.data, sit.shape[0], mode_id(mode), out.ctypes.data))
+    with _host_enter(device) as lib:
+        _lib.check(lib.holdem_hs_batch_host(sit.ctypes.data, sit.shape[0], mode_id(mode), out.ctypes.data))
     return out
 
 
-def hand_potential_counts_host(sit, mode="treys", device=None, out=None) -> np.ndarray:
+def hand_potential_counts_host(sit, mode="treys", device=None, out=None, staged: bool = False) -> np.ndarray:
+    """staged=True: the chunked copy pipeline even for page-locked buffers (holdem_hp_batch_host_staged)."""
     sit = _np_u8(sit, 8)
     if out is None:
         out = np.empty((sit.shape[0], HP_ROW), dtype=np.uint32)
-    lib = _host_enter(device)
-    _lib.check(lib.holdem_hp_batch_host(sit.ctypes.data, sit.shape[0], mode_id(mode), out.ctypes.data))
+    with _host_enter(device) as lib:
+        fn = lib.holdem_hp_batch_host_staged if staged else lib.holdem_hp_batch_host
+        _lib.check(fn(sit.ctypes.data, sit.shape[0], mode_id(mode), out.ctypes.data))
     return out
 
 
 def smem_gather_microbench(table_bytes=131072, iters=2048, pattern=0, blocks_per_sm=1, threads=1024, device=None):
     """Measured shared-memory uint16 gather rate (lookups/s) -- the lookup roofline denominator."""
-    lib = _host_enter(device)
     ms = ctypes.c_float(0)
     lookups = ctypes.c_double(0)
-    _lib.check(lib.holdem_microbench_smem_gather(table_bytes, iters, pattern, blocks_per_sm, threads,
-                                                 ctypes.byref(ms), ctypes.byref(lookups), None))
+    with _host_enter(device) as lib:
+        _lib.check(lib.holdem_microbench_smem_gather(table_bytes, iters, pattern, blocks_per_sm, threads,
+                                                     ctypes.byref(ms), ctypes.byref(lookups), None))
     return lookups.value / (ms.value * 1e-3), ms.value
 
 
 def int_issue_microbench(mix=0, iters=4096, blocks_per_sm=1, threads=1024, device=None):
     """Measured integer instruction issue rate (warp instructions/s) -- the issue roofline denominator.
     mix 0: compare + predicated multiply-add pairs (ALU + FMA pipes), 1: FMA pipe only, 2: ALU pipe only."""
-    lib = _host_enter(device)
     ms = ctypes.c_float(0)
     n = ctypes.c_double(0)
-    _lib.check(lib.holdem_microbench_int_issue(iters, mix, blocks_per_sm, threads, ctypes.byref(ms), ctypes.byref(n), None))
+    with _host_enter(device) as lib:
+        _lib.check(lib.holdem_microbench_int_issue(iters, mix, blocks_per_sm, threads, ctypes.byref(ms), ctypes.byref(n), None))
     return n.value / (ms.value * 1e-3), ms.value

@@ -9,6 +9,7 @@
   two attributes pokerlib_to_treys.convert_to_treys reads.
 """
 import numpy as np
+import torch
 
 RANK_CHARS = "23456789TJQKA"
 SUIT_CHARS = "cdhs"
@@ -71,6 +72,10 @@ def pack_situations(our, board) -> np.ndarray:
     n = our.shape[0]
     if our.shape != (n, 2) or board.shape[0] != n or not 3 <= board.shape[1] <= 5:
         raise ValueError("expected our [N,2] and board [N,3..5]")
+    # validate BEFORE the uint8 cast: 256 would wrap to card 0, -1 to the 0xFF "absent" marker
+    for name, a in (("our", our), ("board", board)):
+        if a.size and (not np.issubdtype(a.dtype, np.integer) or a.min() < 0 or a.max() > 51):
+            raise ValueError(f"{name}: cards must be integers in 0..51")
     rows = np.full((n, 8), 0xFF, dtype=np.uint8)
     rows[:, 0:2] = our
     rows[:, 2:2 + board.shape[1]] = board
@@ -83,4 +88,60 @@ def random_situations(n: int, seed: int, n_board: int = 3) -> np.ndarray:
     cards = np.argsort(rng.random((n, 52)), axis=1)[:, :2 + n_board].astype(np.uint8)
     rows = np.full((n, 8), 0xFF, dtype=np.uint8)
     rows[:, :2 + n_board] = cards
+    return rows
+
+
+# ---- tensor-in / tensor-out converters (vectorised; any device, any integer dtype) ----------------------------------------
+def path_from_rank_major_t(v: torch.Tensor) -> torch.Tensor:
+    """utils.card_to_int ints (rank*4+suit, utils.py:82-85) -> path encoding (suit*13+rank), elementwise."""
+    return (v % 4) * 13 + torch.div(v, 4, rounding_mode="floor")
+
+
+def rank_major_from_path_t(c: torch.Tensor) -> torch.Tensor:
+    return (c % 13) * 4 + torch.div(c, 13, rounding_mode="floor")
+
+
+_PRIMES_T = torch.tensor(PRIMES, dtype=torch.int64)
+_TREYS_SUIT_BITS_T = torch.tensor([8, 4, 2, 1], dtype=torch.int64)      # path suits c d h s -> Treys suit bits
+
+
+def treys_from_path_t(c: torch.Tensor) -> torch.Tensor:
+    """path encoding -> Treys card ints (int64), elementwise: (1<<rank)<<16 | suit_bit<<12 | rank<<8 | prime[rank]."""
+    c = c.to(torch.int64)
+    r, s = c % 13, torch.div(c, 13, rounding_mode="floor")
+    return ((1 << r) << 16) | (_TREYS_SUIT_BITS_T.to(c.device)[s] << 12) | (r << 8) | _PRIMES_T.to(c.device)[r]
+
+
+def path_from_treys_t(t: torch.Tensor) -> torch.Tensor:
+    """Treys card ints -> path encoding (int64), elementwise; malformed ints raise ValueError."""
+    t = t.to(torch.int64)
+    r, bit = (t >> 8) & 0xF, (t >> 12) & 0xF
+    suit = torch.full_like(t, -1)
+    for b, s in _SUIT_FROM_BIT.items():
+        suit = torch.where(bit == b, torch.full_like(t, s), suit)
+    rc = r.clamp(max=12)
+    ok = (r <= 12) & (suit >= 0) & ((t >> 16) == (1 << rc)) & ((t & 0xFF) == _PRIMES_T.to(t.device)[rc])
+    if not bool(ok.all()):
+        raise ValueError("not a Treys card int")
+    return suit * 13 + r
+
+
+def situations_from_rank_major(hole: torch.Tensor, board: torch.Tensor) -> torch.Tensor:
+    """Wire-format ints as GameBoard / Player publish them (rank-major, utils.py:82-92): hole [N,2], board [N,3..5] ->
+    uint8 [N,8] situation rows.  CUDA tensors go through one fused kernel (holdem_pack_rank_major); values outside [0,52)
+    become 0xFE there and the HS/HP kernels report the row as malformed.  CPU tensors are packed with torch (and validated
+    here, raising ValueError)."""
+    hole = hole.to(torch.int64)
+    board = board.to(torch.int64)
+    if hole.dim() != 2 or hole.shape[1] != 2 or board.dim() != 2 or board.shape[0] != hole.shape[0] \
+            or not 3 <= board.shape[1] <= 5:
+        raise ValueError("expected hole [N,2] and board [N,3..5]")
+    if hole.is_cuda:
+        from .api import pack_rank_major
+        return pack_rank_major(hole, board)
+    both = torch.cat([hole, board], dim=1)
+    if both.numel() and (int(both.min()) < 0 or int(both.max()) > 51):
+        raise ValueError("cards must be integers in 0..51")
+    rows = torch.full((hole.shape[0], 8), 0xFF, dtype=torch.uint8)
+    rows[:, :both.shape[1]] = path_from_rank_major_t(both).to(torch.uint8)
     return rows

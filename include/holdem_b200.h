@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define HOLDEM_ABI_VERSION 1
+#define HOLDEM_ABI_VERSION 2
 
 #define HOLDEM_MODE_TREYS 0
 #define HOLDEM_MODE_REFERENCE 1
@@ -113,6 +113,9 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
  * sit: uint8[n,8]; out: uint32[n,HOLDEM_HP_ROW].  PPot/NPot are derived by the caller exactly as :221-224. */
 int holdem_hp_batch(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
 int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out);
+/* The same through the chunked copy pipeline (16,384-row chunks, library-side pinned staging, two streams) even when the
+ * caller's buffers are page-locked; holdem_hp_batch_host uses it for pageable buffers. */
+int holdem_hp_batch_host_staged(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_out);
 
 /* holdem_hp_batch that also stores every result row into up to 8 other GPUs' buffers (peer memory mapped into this process:
  * CUDA IPC / symmetric memory; NVLink stores issued by the kernels themselves, no separate collective).  peer_out is a HOST
@@ -121,6 +124,13 @@ int holdem_hp_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
  * overwritten and one after this call's stream work); HandCalculations' multi-GPU layer (holdem_b200/sharded.py) does. */
 int holdem_hp_batch_peers(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *const *peer_out, int n_peers,
                           void *stream);
+
+/* Whole tables: every seat of a hand shares the board (GameBoard.py:12 MAX_PLAYERS = 22; GameBoard.py:204-229 walks the
+ * seats one by one).  d_hole uint8[hands,seats,2], d_board uint8[hands,5] (the first n_board = 3, 4 or 5 cards are used),
+ * d_out uint32[hands,seats,HOLDEM_HP_ROW]: the rows holdem_hp_batch would return for situation (hole[h][s], board[h][:n_board]).
+ * The seats of one board are adjacent in the work order, so the per-board table rows are fetched once per board. */
+int holdem_table_hp_batch(const uint8_t *d_hole, const uint8_t *d_board, int64_t hands, int seats, int n_board, int mode,
+                          uint32_t *d_out, void *stream);
 
 /* Same results as holdem_hp_batch computed by the plain (non-deduplicating) enumeration kernel: one opponent
  * evaluation per (opponent holding, runout) pair.  Kept as the independent second implementation the parity
@@ -137,10 +147,46 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
  * Rows of other streets are left untouched. */
 int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
+/* Whole Treys-mode batches (all streets) through named implementations: flop 4 / 3 / 2 and turn 4 / 3 as above, river 0 =
+ * rank-pair HS kernel in its HP-row form (production), 1 = plain enumeration.  holdem_hp_batch == (4, 4, 0).  These entry
+ * points replace the HOLDEM_*_KERNEL environment switches of ABI version 1: production dispatch reads no environment. */
+int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, int turn_variant, int river_variant,
+                            uint32_t *d_out, void *stream);
+/* holdem_hs_batch through a named kernel: 0 = production (Treys mode: rank-pair kernel), 1 = one evaluation per holding. */
+int holdem_hs_batch_variant(const uint8_t *d_sit, int64_t n, int mode, int variant, uint32_t *d_out, void *stream);
+/* holdem_exhaustive7 through a named kernel: 0 = tuple kernel (production), 1 = chunk-per-thread kernel. */
+int holdem_exhaustive7_variant(int variant, uint64_t *d_hist, uint64_t *d_sums, void *stream);
+
 /* The production flop kernel with its phase clocks switched on: d_cycles uint64[4] receives the SM cycles each situation
  * group spent in (0) list + hash-table phase, (1) pair table + T expansion, (2) holding descriptors, (3) generic + flush
  * tasks, summed over all situations.  Profiling aid for bench.py / DESIGN.md; results in d_out are the normal rows. */
 int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out, uint64_t *d_cycles, void *stream);
+
+/* ---- callers and data formats either side of the path -------------------------------------------
+ * Position-dependent 64-bit content hash of a [n, words_per_row] uint32 buffer: sum over rows r of
+ * mix(fnv1a64(row r, seed first_row + r)).  Equal hashes across GPU counts / kernel variants mean equal rows (a plain sum
+ * of the counts is a structural constant).  d_hash: uint64[1], overwritten.  Shards combine by addition. */
+int holdem_rows_hash(const uint32_t *d_rows, int64_t n, int words_per_row, int64_t first_row, uint64_t *d_hash, void *stream);
+
+/* Batched Decision.decision_based_on_blind_position (Decision.py:4-48).  Positions: 0 'SB', 1 'BB', 2 'NONE' -- one per row
+ * (d_pos uint8[n]) or pos_all for the whole batch when d_pos is NULL (anything else: HOLDEM_ERR_BAD_ARG with the reference's
+ * message, Decision.py:8-9; a bad per-row code gives action -2).  d_action int8[n]: 0 fold, 1 check, 2 call, 3 raise,
+ * -1 where the reference falls through and returns None (hand_strength > 0.8 and npot >= 0.3). */
+int holdem_decide_batch(const double *d_hs, const double *d_ppot, const double *d_npot, const uint8_t *d_pos, int pos_all,
+                        int64_t n, int8_t *d_action, void *stream);
+/* The same straight from HS/HP result rows (uint32[n,16]): HS as HandCalculations.py:175 (double), PPot/NPot as :221-224 with
+ * each HP row divided by the runouts per opponent (probabilities; 0 where undefined), then the tree above -- one fused pass
+ * over the rows.  d_hs_ppot_npot: optional double[n,3] receiving the three inputs of the tree.  Malformed rows give -2. */
+int holdem_decide_from_counts(const uint32_t *d_rows, const uint8_t *d_pos, int pos_all, int64_t n, int8_t *d_action,
+                              double *d_hs_ppot_npot, void *stream);
+
+/* utils.card_to_int wire format (utils.py:82-85: rank * 4 + suit, what GameBoard / Player publish) -> situation rows in the
+ * path encoding (HandCalculations.py:53-54).  d_hole int64[n,2], d_board int64[n,n_board], n_board 3..5; d_sit uint8[n,8].
+ * A value outside [0,52) is written as 0xFE, which every kernel reports as a malformed row. */
+int holdem_pack_rank_major(const int64_t *d_hole, const int64_t *d_board, int n_board, int64_t n, uint8_t *d_sit, void *stream);
+
+/* Kernels launched by this library in this process so far (every launch site counts itself). */
+unsigned long long holdem_kernel_launches(void);
 
 /* ---- roofline micro-benchmarks (bench.py) ---------------------------------------------------------------
  * Issues `iters` dependent uniformly-random uint16 gathers per thread over a shared-memory table of

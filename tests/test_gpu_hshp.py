@@ -360,10 +360,15 @@ def test_hp_batch_peers_replicates_rows(hb, oracle):
         want = hb.hand_potential_counts(sub, mode)
         mine = torch.zeros((m, 16), dtype=torch.int32, device="cuda")
         peers = [torch.full((m + 2 * off, 16), 7, dtype=torch.int32, device="cuda") for _ in range(2)]
-        lib, st = _enter(sub)
-        arr = (ctypes.c_void_p * 2)(*[p.data_ptr() + off * 64 for p in peers])
-        _lib.check(lib.holdem_hp_batch_peers(sub.data_ptr(), m, hb.mode_id(mode), mine.data_ptr(), arr, 2, st))
+        with _enter(sub) as (lib, st):
+            arr = (ctypes.c_void_p * 2)(*[p.data_ptr() + off * 64 for p in peers])
+            _lib.check(lib.holdem_hp_batch_peers(sub.data_ptr(), m, hb.mode_id(mode), mine.data_ptr(), arr, 2, st))
         torch.cuda.synchronize()
+        # the torch op over the same entry point
+        mine2 = torch.zeros_like(mine)
+        peers2 = [torch.full((m + 2 * off, 16), 7, dtype=torch.int32, device="cuda") for _ in range(2)]
+        torch.ops.holdem.hp_peers(sub, hb.mode_id(mode), mine2, [p.data_ptr() + off * 64 for p in peers2])
+        assert torch.equal(mine2, want) and all(torch.equal(a, b) for a, b in zip(peers, peers2)), mode
         assert torch.equal(mine, want), mode
         for p in peers:
             assert torch.equal(p[off:off + m], want), mode

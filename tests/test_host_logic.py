@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.holdem_abi_version() == 1
+    assert lib.holdem_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_tables_selfcheck():
@@ -187,3 +187,52 @@ def test_table_helpers_cpu():
     assert table.winners(ranks, "reference").tolist() == [[False, False, True, False], [False, True, True, False]]
     active = torch.tensor([[True, True, True, False], [True, True, True, True]])
     assert table.winners(ranks, "best", active).tolist() == [[True, True, False, False], [False, False, False, True]]
+
+
+def test_torch_ops_library_loads_and_has_no_cpu_kernel():
+    """torch.ops.holdem.* (csrc/torch_ops.cpp) registers without a GPU; only CUDA implementations exist."""
+    from holdem_b200 import _ops
+    ops = _ops.load()
+    for name in ("eval", "category", "hs", "hp", "hp_out", "hp_peers", "hp_sharded", "table_hp", "decide",
+                 "decide_from_counts", "pack_rank_major", "rows_hash"):
+        assert hasattr(ops, name), name
+    with pytest.raises(Exception) as ei:
+        ops.hp(torch.zeros((1, 8), dtype=torch.uint8), 0)
+    assert "CPU" in str(ei.value)
+
+
+def test_rows_hash_host_properties():
+    rng = np.random.default_rng(0)
+    rows = rng.integers(0, 2 ** 31, size=(1000, 16), dtype=np.int64).astype(np.int32)
+    h = hb.rows_hash_host(rows)
+    assert h == (hb.rows_hash_host(rows[:400]) + hb.rows_hash_host(rows[400:], first_row=400)) % 2 ** 64
+    swapped = rows.copy(); swapped[[1, 2]] = swapped[[2, 1]]
+    assert hb.rows_hash_host(swapped) != h and hb.rows_hash_host(rows, first_row=1) != h
+    assert hb.rows_hash_host(rows[:0]) == 0
+
+
+def test_positions_and_tensor_converters_cpu():
+    from holdem_b200 import policy
+    assert [policy.position_from_player_position(p) for p in
+            ("NONE", "SMALL_BLIND", "BIG_BLIND", "DEALER", "DEALER_SMALL_BLIND")] == ["NONE", "SB", "BB", "NONE", "SB"]
+    assert [policy.position_from_player_position(v) for v in (1, 2, 3, 4, 5)] == ["NONE", "SB", "BB", "NONE", "SB"]
+
+    class P:            # duck-typed Enum member (utils.PlayerPosition needs the third-party `poker` import chain)
+        name = "BIG_BLIND"
+    assert policy.position_from_player_position(P()) == "BB"
+    with pytest.raises(ValueError):
+        policy.position_from_player_position("UTG")
+    assert policy.position_codes(["SB", "BIG_BLIND", "DEALER"]).tolist() == [0, 1, 2]
+    c = torch.arange(52)
+    assert hb.rank_major_from_path_t(c).tolist() == [hb.rank_major_from_path(int(x)) for x in c]
+    assert torch.equal(hb.path_from_rank_major_t(hb.rank_major_from_path_t(c)), c)
+    assert hb.treys_from_path_t(c).tolist() == [hb.treys_from_path(int(x)) for x in c]
+    assert torch.equal(hb.path_from_treys_t(hb.treys_from_path_t(c)), c)
+    with pytest.raises(ValueError):
+        hb.path_from_treys_t(torch.tensor([12345]))
+    rows = hb.situations_from_rank_major(torch.tensor([[0, 5]]), torch.tensor([[51, 50, 4]]))
+    assert rows.tolist() == [[0, 14, 51, 38, 1, 255, 255, 255]]
+    with pytest.raises(ValueError):
+        hb.pack_situations([[0, 300]], [[1, 2, 3]])
+    with pytest.raises(ValueError):
+        hb.pack_situations([[0, -1]], [[1, 2, 3]])
