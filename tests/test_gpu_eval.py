@@ -58,6 +58,8 @@ def test_eval_host_entry(hb, oracle):
 def test_exhaustive_seven_cards(hb):
     """BASELINE.json configs[1]: all 133,784,560 hands, published class frequencies and checksums."""
     hist, sums = hb.exhaustive7()
+    # the whole rank histogram equals the CPU oracle's, bin by bin (hash committed from tests/test_oracle_treys.py)
+    assert f"{hb.rows_hash(hist.view(torch.int32).reshape(-1, 2)):016x}" == load_golden("gpu_hashes.json")["exhaustive7_rank_histogram"]
     hist = hist.cpu().numpy()
     assert int(hist.sum()) == 133784560
     bounds = [0, 10, 166, 322, 1599, 1609, 2467, 3325, 6185, 7462]

@@ -74,3 +74,11 @@ def test_exhaustive_seven_card_histogram():
     assert int(hist[1]) == 4324 and int(hist[10]) == 4140 and int(hist[11]) == 4052 and int(hist[1600]) == 747980
     assert int(hist[7462]) == 0 and int((hist > 0).sum()) == 4824
     assert s == 547965983972 and s2 == 2665153084455708
+    # the whole 7463-bin histogram pinned by one hash: the GPU sweep (tests/test_gpu_eval.py) and any later table change must
+    # reproduce it -- the product's independent table builder and this restatement agree bin by bin
+    import json
+    import os
+    import numpy as np
+    import holdem_b200 as hb
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gpu_hashes.json")))["exhaustive7_rank_histogram"]
+    assert f"{hb.rows_hash_host(hist.astype(np.uint64).view(np.uint32).reshape(-1, 2)):016x}" == want
