@@ -58,6 +58,7 @@ struct DeviceState {
     bool slot_used[1024] = {};
     unsigned flag_next = 0;
     std::mutex flag_mu;
+    cudaMemPool_t pool = nullptr;   // stream-ordered scratch (whole-table entry point); keeps its memory between calls
 };
 constexpr unsigned kFlagRing = 1024;
 
@@ -273,6 +274,15 @@ int holdem_init(int device) {
     }
     CUDA_TRY(cudaMalloc(&S.flags, 4 * kFlagRing * sizeof(int)));     // 16-byte slots: flag word + work counters
     CUDA_TRY(cudaMemset(S.flags, 0, 4 * kFlagRing * sizeof(int)));
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CUDA_TRY(cudaMemPoolCreate(&S.pool, &props));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(S.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     S.sms = prop.multiProcessorCount;
     S.ready.store(true, std::memory_order_release);
     return HOLDEM_OK;
@@ -627,7 +637,7 @@ int holdem_table_hp_batch(const uint8_t *d_hole, const uint8_t *d_board, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = hands * seats;
     uint8_t *d_sit = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_sit, (size_t)n * 8, st));           // stream-ordered scratch: the expanded situation rows
+    CUDA_TRY(cudaMallocFromPoolAsync(&d_sit, (size_t)n * 8, S->pool, st));           // stream-ordered scratch: the expanded situation rows
     cudaError_t e = launch_table_rows(d_hole, d_board, hands, seats, n_board, d_sit, S->sms, st);
     if (e == cudaSuccess) e = hp_dispatch(*S, d_sit, n, mode, d_out, st);
     cudaFreeAsync(d_sit, st);
