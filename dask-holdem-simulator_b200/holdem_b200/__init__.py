@@ -13,3 +13,8 @@ from .encoding import (pack_situations, random_situations, path_from_str, str_fr
 from .sharded import shard_bounds, hand_potential_counts_sharded  # noqa: F401
 from .extensions import hand_strength_vs_n, preflop_hand_strength, monte_carlo_equity  # noqa: F401
 from . import policy, table, extensions  # noqa: F401,E402
+
+try:        # register torch.ops.holdem.* now when the extension is built; a missing build raises at first use instead
+    _ops.load()
+except RuntimeError:
+    pass
