@@ -419,6 +419,7 @@ struct HpImpl {
     int flop = 4;      // 4 rank-multiset kernel, 3 / 2 the 4-set kernels
     int turn = 4;      // 4 rank-multiset kernel, 3 the 3-set walk
     int river = 0;     // 0 rank-pair HS kernel in its HP-row form, 1 plain enumeration
+    int ref = 5;       // HOLDEM_MODE_REFERENCE: 5 rank-multiset kernel, 4 the earlier 4-set walk + arithmetic irregular runouts
 };
 
 // Treys mode: the flop kernel takes every 3-card-board row and flags what else it saw; turn rows go to the turn kernel, river
@@ -432,6 +433,12 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     cudaError_t e = slot.acquire(S, st);
     if (e != cudaSuccess) return e;
     int *flag = slot.ptr;
+    if (mode == HOLDEM_MODE_REFERENCE && impl.ref == 5) {
+        e = launch_hp_ref5(S.T, d_sit, n, d_out, S.sms, flag, peers, st);      // stores its rows into the peers itself
+        if (e != cudaSuccess) return e;
+        if (flag_out) *flag_out = flag;
+        return slot.release();
+    }
     if (mode == HOLDEM_MODE_REFERENCE) {
         e = cudaMemsetAsync(flag, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
@@ -599,6 +606,18 @@ int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, i
     HpImpl impl;
     impl.flop = flop_variant; impl.turn = turn_variant; impl.river = river_variant;
     CUDA_TRY(hp_dispatch(*S, d_sit, n, HOLDEM_MODE_TREYS, d_out, (cudaStream_t)stream, PeerOut{}, nullptr, impl));
+    return HOLDEM_OK;
+}
+
+int holdem_hp_ref_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
+    if (variant != 4 && variant != 5) return fail(HOLDEM_ERR_BAD_ARG, "unknown reference-mode kernel variant %d", variant);
+    HpImpl impl;
+    impl.ref = variant;
+    CUDA_TRY(hp_dispatch(*S, d_sit, n, HOLDEM_MODE_REFERENCE, d_out, (cudaStream_t)stream, PeerOut{}, nullptr, impl));
     return HOLDEM_OK;
 }
 

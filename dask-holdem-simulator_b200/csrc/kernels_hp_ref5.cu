@@ -1,0 +1,495 @@
+// kernels_hp_ref5.cu -- hand strength + hand potential in HOLDEM_MODE_REFERENCE, rank-multiset formulation ("v5"), and the
+// rank-pair hand-strength kernel of the same mode.  Flop / turn / river boards.  sm_100a only.
+//
+// What is counted -- the reference's loops exactly as written (HandCalculations.py:178-226 with the 9-category ranker of
+// :45-82, higher = better):
+//     HP[cls(P)][cmp(our(Q), opp(P,Q))] += 1   for EVERY opponent holding P (pairs of the m = 47/46/45 cards unseen by us,
+//                                               :148-150) and EVERY runout Q (pairs of deck \ board, :152-154: 1176/1128/1081,
+//                                               they may repeat our hole cards or the opponent's own cards)
+// with our(Q) = category of the card MULTISET hole + board + Q, opp(P,Q) = category of board + Q + P, cls(P) from the
+// categories on the current board.  Unlike the canonical enumeration (kernels_hp_flop4.cu) P and Q are independent: the
+// sum runs over the full Cartesian product, which is what makes this formulation short.
+//
+// How (bit-identical counts; the identity is restated on the CPU in scripts/proto_ref_multiset.py and checked against the
+// literal oracle by tests/test_multiset_identity.py; on the GPU this kernel is compared with the plain enumeration, with the
+// earlier 4-set kernel and with the golden vectors of the unmodified reference):
+//   The literal category of a multiset is  NF = the category its RANK counts alone give (no flush tests)  unless a suit holds
+//   five or more of its cards (repeats counted), in which case it is 8 when that suit's cards are pairwise distinct and contain
+//   a cyclic five-run (:24-37, :61-65), else NF if NF is 7, 6 or 4 (quads / full house / straight are tested before the flush,
+//   :68-72), else 5.  So
+//     sum over (P,Q)  =  GENERIC part: sum over (rank pair q of Q, our category o) of  M(q,o) x  sum over rank pairs pp of
+//                            N(pp) [clsr(pp)] x cmp(o, T[q][pp])
+//                        with T[q][pp] = NF(board + q + pp), N(pp) = number of holdings with those ranks (a product of
+//                        per-rank counts, independent of Q), M(q,o) = number of runouts with rank pair q on which we hold
+//                        category o: ~150 (q,o) entries x 91 compare steps per situation;
+//                     +  FLUSH part: for every suit s with b board cards and every (P,Q) with b + |Q in s| + |P in s| >= 5
+//                        (a card shared by P and Q counts twice, as in the reference's Counter):
+//                            + [cls(P)]  x cmp(our(Q), 8 if no shared card of s and cyclic run in s, else keep(T[q][pp]))
+//                            - [clsr(pp)] x cmp(our(Q), T[q][pp] nf)                               (undo the generic term)
+//                        ~7 K items on a rainbow flop, ~45 K two-tone, ~240 K monotone instead of 1.27 M evaluations.
+//
+// One CTA of 256 threads per situation (claimed from a global counter: suited boards cost far more than rainbow ones).  Per
+// situation: the unseen cards in (rank, suit) order and per-suit position lists; T[91][91] computed on the fly from the board's
+// rank counts (two nibbles per entry: NF and keep(NF)); our category on every runout and the class of every holding by the
+// arithmetic ranker of device_common.cuh (multiset-exact); then the generic entries and a dynamic queue of flush tasks
+// (32 runouts of one (suit, cards-in-suit) class x a segment of the suit's holding descriptors; a step is one broadcast
+// descriptor load, one table byte, a bit test and four compare / predicated multiply-add pairs on packed 10-bit class counters).
+#include "device_common.cuh"
+#include "launch.h"
+#include "multiset_common.cuh"
+
+namespace holdem {
+
+namespace {
+
+using namespace ms;
+
+constexpr int kR5Threads = 256;
+constexpr int kR5Warps = kR5Threads / 32;
+constexpr int kTPitch5 = 92;          // bytes per row of T
+constexpr int kPP5 = 91;
+constexpr int kMaxQ5 = 1176;          // C(49,2)
+constexpr int kMaxP5 = 1081;          // C(47,2)
+constexpr int kPDCap5 = 2304;         // holding descriptors of all suits (a 5-card board can need 1081 + 2 x ~450, see below)
+constexpr int kSeg5 = 192;            // steps per flush task (packed 10-bit counters hold 1023)
+constexpr int kMaxTaskGroups = 12;    // (suit, cards of Q in suit) classes
+
+struct Ref5Smem {
+    uint4 PD[kPDCap5];                 // x = rank bits of the holding's cards in s | pp << 16, y = 1 << 10 cls(P), z = 1 << 10 clsr(pp)
+    unsigned long long Wt[96];         // per rank pair: N(pp) << 20 clsr(pp)
+    uint32_t M[kPP5 * 9 + 1];          // runouts by (rank pair, our category)
+    uint32_t elist[kPP5 * 9 + 1];      // nonzero entries of M, compacted
+    uint32_t cyc[256];                 // bit m: the 13-bit rank mask m holds a cyclic five-run (static)
+    uint32_t cnt[12];                  // behind[3], ahead[3] (by class), class totals[3]
+    uint32_t bmask[4];                 // board rank mask per suit
+    uint32_t g_first[kMaxTaskGroups + 1];
+    uint32_t g_nq[kMaxTaskGroups], g_np[kMaxTaskGroups], g_nseg[kMaxTaskGroups], g_pdbase[kMaxTaskGroups], g_sq[kMaxTaskGroups];
+    uint32_t pd_base[4], pd_len[4];
+    uint32_t n_groups, n_entries, next_task, claim;
+    uint16_t pairs[kMaxQ5 + 8];        // colex pairs i | j << 8 (static)
+    uint8_t T[kPP5 * kTPitch5 + 4];    // [q][pp]: NF | keep(NF) << 4
+    uint8_t ourQ[kMaxQ5 + 8];          // our category on runout (i,j), colex index over the positions of D
+    uint8_t clsP[kMaxP5 + 7];          // class of holding (i,j), colex index over the positions of U
+    uint8_t clsR[96];                  // per rank pair: class from ranks alone
+    uint8_t ppxy[96];                  // rank pair -> x | y << 4 (static)
+    uint8_t code[56];                  // D = deck \ board: positions 0..m-1 the unseen cards (rank*4+suit ascending), m, m+1 our hole cards
+    uint8_t Ls[4][20];                 // positions of D with suit s: unseen cards first, then our hole cards of that suit
+    uint8_t Lns[4][52];                // positions of D with another suit, same order
+    uint8_t nsu[4], nsd[4];            // cards of suit s among the unseen cards / among D
+    uint8_t u[16];                     // unseen cards per rank
+};
+
+__device__ __forceinline__ LitHand one_card5(uint32_t c) {
+    LitHand h = {0, 0, 0, 0, 0};
+    lit_add_card(h, c);
+    return h;
+}
+
+__device__ __forceinline__ void cmp_add64(unsigned long long &gt, unsigned long long &lt, uint32_t a, uint32_t b,
+                                          unsigned long long w) {
+    if (a > b) gt += w;
+    if (a < b) lt += w;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kR5Threads)
+hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T, uint32_t one,
+               int *__restrict__ bad_flag, unsigned int *__restrict__ work_counter, PeerOut peers) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Ref5Smem &S = *reinterpret_cast<Ref5Smem *>(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- static tables ---------------------------------------------------------------------------------------------------------
+    for (uint32_t i = tid; i < (uint32_t)kMaxQ5; i += kR5Threads) S.pairs[i] = __ldg(T.pairs + i);
+    {
+        uint32_t word = 0;
+        for (uint32_t b = 0; b < 32; ++b) word |= (uint32_t)cyclic_run5(tid * 32 + b) << b;
+        S.cyc[tid] = word;
+    }
+    if (tid < 96) {
+        uint32_t y = 0;
+        while (tri(y + 1) <= tid) ++y;
+        S.ppxy[tid] = tid < kPP5 ? (uint8_t)((tid - tri(y)) | (y << 4)) : (uint8_t)0xFF;
+    }
+    const uint32_t t_s = (uint32_t)__cvta_generic_to_shared(S.T);
+    const uint32_t cyc_s = (uint32_t)__cvta_generic_to_shared(S.cyc);
+
+    for (;;) {
+        __syncthreads();                                                                            // previous situation consumed
+        if (tid == 0) S.claim = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const int64_t idx = S.claim;
+        if (idx >= n) break;
+        // ---- parse -----------------------------------------------------------------------------------------------------------------
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
+        uint32_t cb[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cb[k] = (w.x >> (8 * k)) & 0xFFu; cb[4 + k] = (w.y >> (8 * k)) & 0xFFu; }
+        int nb = 0;
+        bool ok = cb[0] < 52u && cb[1] < 52u, ended = false;
+        uint64_t known = card_bit(cb[0] < 52u ? cb[0] : 63u) | card_bit(cb[1] < 52u ? cb[1] : 63u), bset = 0;
+        LitHand lb = {0, 0, 0, 0, 0};
+        uint32_t bsuit = 0;                      // board cards per suit, 4 bits each
+#pragma unroll
+        for (int k = 2; k < 7; ++k) {
+            const uint32_t c = cb[k];
+            if (c == 0xFFu) ended = true;
+            else {
+                ok = ok && !ended && c < 52u;
+                const uint32_t cc = c < 52u ? c : 0u;
+                nb += 1;
+                bset |= card_bit(cc);
+                lit_add_card(lb, cc);
+                bsuit += 1u << (4 * card_suit(cc));
+            }
+        }
+        known |= bset;
+        ok = ok && nb >= 3 && __popcll(known) == nb + 2;
+        if (!ok) {
+            if (tid == 0 && bad_flag != nullptr) atomicOr(bad_flag, 4);   // bit 2: a malformed row was marked
+            if (tid < 16) {
+                out[idx * 16 + tid] = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (k < peers.n) peers.p[k][idx * 16 + tid] = 0xFFFFFFFFu;
+            }
+            continue;
+        }
+        const uint32_t m = 50u - (uint32_t)nb;          // unseen cards
+        const uint32_t md = m + 2u;                     // cards of D = deck \ board
+        const uint32_t n_p = m * (m - 1) / 2, n_q = md * (md - 1) / 2;
+        const LitHand lours = lit_merge(lb, lit_merge(one_card5(cb[0]), one_card5(cb[1])));
+        const uint32_t ours_now = lit_category(lours);                                           // :190
+        if (tid < 12) S.cnt[tid] = 0;
+        if (tid < 4) S.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
+        for (uint32_t i = tid; i < (uint32_t)(kPP5 * 9); i += kR5Threads) S.M[i] = 0;
+        if (warp == 0) {
+            // ---- D in (rank, suit) order, our hole cards last; per-suit position lists ----------------------------------------------
+            const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
+            const bool in0 = !((known >> p0) & 1ull);
+            const bool in1 = (lane + 32 < 52) && !((known >> p1) & 1ull);
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
+            const uint32_t ltm = (1u << lane) - 1u;
+            if (in0) S.code[__popc(m0 & ltm)] = (uint8_t)lane;
+            if (in1) S.code[__popc(m0) + __popc(m1 & ltm)] = (uint8_t)(lane + 32);
+            if (lane < 2) {
+                const uint32_t h = cb[lane];
+                S.code[m + lane] = (uint8_t)(card_rank(h) * 4 + card_suit(h));
+            }
+            if (lane < 13) {
+                const uint32_t c4 = 4 * lane;
+                S.u[lane] = (uint8_t)(c4 < 32 ? __popc((m0 >> c4) & 15u) : __popc((m1 >> (c4 - 32)) & 15u));
+            }
+            __syncwarp();
+            const uint32_t cd0 = S.code[lane], cd1 = lane + 32 < md ? S.code[lane + 32] : 0u;
+            const bool v1 = lane + 32 < md;
+#pragma unroll
+            for (uint32_t s = 0; s < 4; ++s) {
+                const bool a0 = (cd0 & 3u) == s, a1 = v1 && (cd1 & 3u) == s;
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, a0), b1 = __ballot_sync(0xFFFFFFFFu, a1);
+                const uint32_t vb1 = __ballot_sync(0xFFFFFFFFu, v1);
+                const uint32_t n0 = __popc(b0);
+                if (a0) S.Ls[s][__popc(b0 & ltm)] = (uint8_t)lane;
+                else S.Lns[s][lane - __popc(b0 & ltm)] = (uint8_t)lane;
+                if (v1) {
+                    if (a1) S.Ls[s][n0 + __popc(b1 & ltm)] = (uint8_t)(lane + 32);
+                    else S.Lns[s][(32 - n0) + __popc(vb1 & ~b1 & ltm)] = (uint8_t)(lane + 32);
+                }
+                if (lane == 0) {
+                    const uint32_t nd = n0 + __popc(b1);
+                    const uint32_t hole_s = (uint32_t)((S.code[m] & 3u) == s) + (uint32_t)((S.code[m + 1] & 3u) == s);
+                    S.nsd[s] = (uint8_t)nd;
+                    S.nsu[s] = (uint8_t)(nd - hole_s);     // positions ascend, the hole cards sit last: unseen cards come first
+                }
+            }
+        }
+        // ---- T[q][pp]: category from the rank counts of board + two rank pairs, plain (low nibble) and as it reads when a flush
+        //      that is no straight flush is present (high nibble: quads / full house / straight survive, :68-72, else 5) ---------------
+        for (uint32_t e = tid; e < (uint32_t)(kPP5 * kPP5); e += kR5Threads) {
+            const uint32_t q = e / kPP5, p = e - q * kPP5;
+            if (p < q) continue;
+            const uint32_t qxy = S.ppxy[q], pxy = S.ppxy[p];
+            LitHand h = lb;
+            h.sc = 0; h.cards = 0; h.dup = 0;
+            const uint32_t r4[4] = {qxy & 15u, qxy >> 4, pxy & 15u, pxy >> 4};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { h.rc += 1ull << (4 * r4[k]); h.rmask |= 1u << r4[k]; }
+            const uint32_t nf = lit_category(h);
+            const uint8_t v = (uint8_t)(nf | (((nf == 4u || nf >= 6u) ? nf : 5u) << 4));
+            S.T[q * kTPitch5 + p] = v;
+            S.T[p * kTPitch5 + q] = v;
+        }
+        __syncthreads();                                                                            // (A) lists, u[] ready
+        // ---- per rank pair: class from ranks alone and the number of holdings ---------------------------------------------------------
+        if (tid < 96) {
+            uint32_t clsr = 3;
+            unsigned long long wt = 0;
+            if (tid < (uint32_t)kPP5) {
+                const uint32_t xy = S.ppxy[tid], x = xy & 15u, y = xy >> 4;
+                LitHand h = lb;
+                h.sc = 0; h.cards = 0; h.dup = 0;
+                h.rc += (1ull << (4 * x)) + (1ull << (4 * y));
+                h.rmask |= (1u << x) | (1u << y);
+                const uint32_t nf5 = lit_category(h);
+                clsr = ours_now > nf5 ? 0u : (ours_now == nf5 ? 1u : 2u);
+                const uint32_t ux = S.u[x], uy = S.u[y];
+                const uint32_t cntp = x != y ? ux * uy : (ux ? ux * (ux - 1) / 2 : 0u);
+                wt = (unsigned long long)cntp << (20 * clsr);
+            }
+            S.clsR[tid] = (uint8_t)clsr;
+            S.Wt[tid] = wt;
+        }
+        // ---- class of every holding (:194-203), multiset-exact ---------------------------------------------------------------------
+        {
+            uint32_t c0 = 0, c1 = 0, c2 = 0;
+            for (uint32_t p = tid; p < n_p; p += kR5Threads) {
+                const uint32_t pr = S.pairs[p];
+                LitHand lp = one_card5(path_of_code4(S.code[pr & 0xFFu]));
+                lit_add_card(lp, path_of_code4(S.code[pr >> 8]));
+                const uint32_t opp = lit_category(lit_merge(lb, lp));
+                const uint32_t cls = ours_now > opp ? 0u : (ours_now == opp ? 1u : 2u);
+                S.clsP[p] = (uint8_t)cls;
+                c0 += cls == 0; c1 += cls == 1; c2 += cls == 2;
+            }
+            c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+            c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+            c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
+            if (lane == 0) { atomicAdd(&S.cnt[6], c0); atomicAdd(&S.cnt[7], c1); atomicAdd(&S.cnt[8], c2); }
+        }
+        // ---- our category on every runout (:207-210; a runout may repeat our hole cards) ---------------------------------------------
+        for (uint32_t q = tid; q < n_q; q += kR5Threads) {
+            const uint32_t pr = S.pairs[q];
+            const uint32_t ci = S.code[pr & 0xFFu], cj = S.code[pr >> 8];
+            LitHand lq = one_card5(path_of_code4(ci));
+            lit_add_card(lq, path_of_code4(cj));
+            const uint32_t o = lit_category(lit_merge(lours, lq));
+            S.ourQ[q] = (uint8_t)o;
+            const uint32_t ri = ci >> 2, rj = cj >> 2;
+            atomicAdd(&S.M[(tri(max(ri, rj)) + min(ri, rj)) * 9 + o], 1u);
+        }
+        if (warp == 0) {
+            // ---- flush task groups and descriptor sections: lane = 3 * suit + (2 - qtype) ------------------------------------------------
+            const uint32_t ltm = (1u << lane) - 1u;
+            const uint32_t s = min(lane / 3u, 3u), qtype = 2u - (lane - 3u * (lane / 3u));
+            const uint32_t bs = (bsuit >> (4 * s)) & 15u;
+            const uint32_t nu = S.nsu[s], nnu = m - nu, nd = S.nsd[s], nnd = md - nd;
+            // holdings of the suit by their cards in s: [two | one | none]
+            const uint32_t len2 = choose2u(nu), len1 = len2 + nu * nnu, len0 = n_p;
+            // longest prefix any runout class needs: cards of s the holding must bring when the runout brings two
+            const int need2 = 5 - (int)bs - 2;
+            const uint32_t len = bs == 0 ? 0u : (need2 >= 3 ? 0u : (need2 == 2 ? len2 : (need2 == 1 ? len1 : len0)));
+            uint32_t pdo = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < 3; ++q) {
+                const uint32_t lq = __shfl_sync(0xFFFFFFFFu, len, 3 * q);
+                if (q < s) pdo += lq;
+            }
+            const int need = 5 - (int)bs - (int)qtype;                 // cards of s the holding must bring for this runout class
+            const uint32_t nq = qtype == 2 ? choose2u(nd) : (qtype == 1 ? nd * nnd : choose2u(nnd));
+            const uint32_t np = need >= 3 ? 0u : (need == 2 ? len2 : (need == 1 ? len1 : len0));
+            const bool live = lane < 12 && bs != 0 && nq != 0 && np != 0;
+            const uint32_t nseg = (np + kSeg5 - 1) / kSeg5;
+            const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
+            const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
+            const uint32_t gi = __popc(livem & ltm);
+            uint32_t first = ntask;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, first, d);
+                if ((int)lane >= d) first += v;
+            }
+            if (live) {
+                S.g_first[gi] = first - ntask;
+                S.g_nq[gi] = nq; S.g_np[gi] = np; S.g_nseg[gi] = nseg; S.g_pdbase[gi] = pdo;
+                S.g_sq[gi] = s | (qtype << 2);
+            }
+            if (lane < 12 && qtype == 2) { S.pd_base[s] = pdo; S.pd_len[s] = len; }
+            if (lane == 11) {
+                S.g_first[__popc(livem)] = first;
+                S.n_groups = __popc(livem);
+                S.next_task = 0;
+                S.n_entries = 0;
+            }
+        }
+        __syncthreads();                                                                            // (B)
+        // ---- compact the (rank pair, our category) entries that occur ---------------------------------------------------------------
+        for (uint32_t e = tid; e < (uint32_t)(kPP5 * 9 + kR5Threads - 1) / kR5Threads * kR5Threads; e += kR5Threads) {
+            const bool nz = e < (uint32_t)(kPP5 * 9) && S.M[e] != 0;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, nz);
+            uint32_t base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&S.n_entries, __popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (nz) S.elist[base + __popc(bal & ((1u << lane) - 1u))] = e;
+        }
+        // ---- holding descriptors of the flush part --------------------------------------------------------------------------------------
+        {
+            const uint32_t total = S.pd_base[3] + S.pd_len[3];
+            for (uint32_t e = tid; e < total; e += kR5Threads) {
+                uint32_t s = 0;
+#pragma unroll
+                for (uint32_t q = 1; q < 4; ++q)
+                    if (S.pd_len[q] && e >= S.pd_base[q]) s = q;
+                const uint32_t t = e - S.pd_base[s];
+                const uint32_t nu = S.nsu[s], nnu = m - nu, nboth = choose2u(nu);
+                uint32_t pa, pb;                                   // positions in D (both < m)
+                if (t < nboth) {
+                    const uint32_t pr = S.pairs[t];
+                    pa = S.Ls[s][pr & 0xFFu]; pb = S.Ls[s][pr >> 8];
+                } else if (t < nboth + nu * nnu) {
+                    const uint32_t t2 = t - nboth, a = t2 / nnu, z = t2 - a * nnu;
+                    pa = S.Ls[s][a]; pb = S.Lns[s][z];
+                } else {
+                    const uint32_t pr = S.pairs[t - nboth - nu * nnu];
+                    pa = S.Lns[s][pr & 0xFFu]; pb = S.Lns[s][pr >> 8];
+                }
+                const uint32_t lo = min(pa, pb), hi = max(pa, pb);
+                const uint32_t ca = S.code[pa], cb2 = S.code[pb];
+                const uint32_t ra = ca >> 2, rb = cb2 >> 2;
+                const uint32_t bits = ((ca & 3u) == s ? 1u << ra : 0u) | ((cb2 & 3u) == s ? 1u << rb : 0u);
+                const uint32_t pp = tri(max(ra, rb)) + min(ra, rb);
+                S.PD[e] = make_uint4(bits | (pp << 16), 1u << (10 * S.clsP[hi * (hi - 1) / 2 + lo]), 1u << (10 * S.clsR[pp]), 0u);
+            }
+        }
+        __syncthreads();                                                                            // (C)
+
+        uint32_t accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};     // per class: our > opp (ahead) / our < opp (behind), net, mod 2^32
+        // ---- generic part -----------------------------------------------------------------------------------------------------------------
+        {
+            const uint32_t n_entries = S.n_entries;
+            for (uint32_t k = tid; k < n_entries; k += kR5Threads) {
+                const uint32_t e = S.elist[k], q = e / 9u, o = e - 9u * q, mult = S.M[e];
+                const uint8_t *row = S.T + q * kTPitch5;
+                unsigned long long gt = 0, lt = 0;
+#pragma unroll 7
+                for (uint32_t pp = 0; pp < (uint32_t)kPP5; ++pp) cmp_add64(gt, lt, o, (uint32_t)row[pp] & 15u, S.Wt[pp]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    accA[c] += (uint32_t)((gt >> (20 * c)) & 0xFFFFFu) * mult;
+                    accB[c] += (uint32_t)((lt >> (20 * c)) & 0xFFFFFu) * mult;
+                }
+            }
+        }
+        // ---- flush part: dynamic task queue ----------------------------------------------------------------------------------------------------
+        {
+            const uint32_t n_groups = S.n_groups;
+            const uint32_t n_tasks = S.g_first[n_groups];
+            for (;;) {
+                uint32_t task = 0;
+                if (lane == 0) task = atomicAdd(&S.next_task, 1u);
+                task = __shfl_sync(0xFFFFFFFFu, task, 0);
+                if (task >= n_tasks) break;
+                uint32_t g = 0;
+                while (g + 1 < n_groups && task >= S.g_first[g + 1]) ++g;
+                const uint32_t local = task - S.g_first[g];
+                const uint32_t nseg = S.g_nseg[g], np = S.g_np[g], nq = S.g_nq[g];
+                const uint32_t chunk = local / nseg, seg = local - chunk * nseg;
+                const uint32_t s = S.g_sq[g] & 3u, qtype = S.g_sq[g] >> 2;
+                const uint32_t p0 = seg * kSeg5, p1 = min(np, p0 + kSeg5);
+                const uint32_t qi = chunk * 32 + lane;
+                const uint32_t nd = S.nsd[s], nnd = md - nd;
+                uint32_t our = 0, qbits = 0, trow = 0;
+                const bool valid = qi < nq;
+                if (valid) {
+                    uint32_t x, y;                                 // positions in D
+                    if (qtype == 2) {
+                        const uint32_t pr = S.pairs[qi];
+                        x = S.Ls[s][pr & 0xFFu]; y = S.Ls[s][pr >> 8];
+                    } else if (qtype == 1) {
+                        const uint32_t a = qi / nnd, z = qi - a * nnd;
+                        x = S.Ls[s][a]; y = S.Lns[s][z];
+                    } else {
+                        const uint32_t pr = S.pairs[qi];
+                        x = S.Lns[s][pr & 0xFFu]; y = S.Lns[s][pr >> 8];
+                    }
+                    const uint32_t lo = min(x, y), hi = max(x, y);
+                    const uint32_t cx = S.code[x], cy = S.code[y];
+                    const uint32_t rx = cx >> 2, ry = cy >> 2;
+                    our = S.ourQ[hi * (hi - 1) / 2 + lo];
+                    qbits = ((cx & 3u) == s ? 1u << rx : 0u) | ((cy & 3u) == s ? 1u << ry : 0u);
+                    trow = (tri(max(rx, ry)) + min(rx, ry)) * kTPitch5;
+                }
+                const uint32_t base_mask = S.bmask[s] | qbits;
+                const uint32_t tq_s = t_s + trow;
+                const uint4 *pd = S.PD + S.g_pdbase[g] + p0;
+                uint32_t aG = 0, aL = 0, sG = 0, sL = 0;
+#pragma unroll 2
+                for (uint32_t t = p0; t < p1; ++t, ++pd) {
+                    const uint4 d = *pd;
+                    const uint32_t pbits = d.x & 0xFFFFu;
+                    uint32_t e8;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e8) : "r"(tq_s + (d.x >> 16)));
+                    const uint32_t mask = base_mask | pbits;
+                    uint32_t cw;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(cyc_s + ((mask >> 5) << 2)));
+                    const bool sf = ((cw >> (mask & 31u)) & 1u) != 0 && (qbits & pbits) == 0;   // no shared card of s, cyclic run
+                    const uint32_t catf = sf ? 8u : (e8 >> 4), catn = e8 & 15u;
+                    // if (our > catf) aG += wa; if (our < catf) aL += wa; if (our > catn) sG += ws; if (our < catn) sL += ws
+                    asm("{\n\t.reg .pred p;\n\t"
+                        "setp.gt.u32 p, %4, %5;\n\t@p mad.lo.u32 %0, %7, %9, %0;\n\t"
+                        "setp.lt.u32 p, %4, %5;\n\t@p mad.lo.u32 %1, %7, %9, %1;\n\t"
+                        "setp.gt.u32 p, %4, %6;\n\t@p mad.lo.u32 %2, %8, %9, %2;\n\t"
+                        "setp.lt.u32 p, %4, %6;\n\t@p mad.lo.u32 %3, %8, %9, %3;\n\t}"
+                        : "+r"(aG), "+r"(aL), "+r"(sG), "+r"(sL)
+                        : "r"(our), "r"(catf), "r"(catn), "r"(d.y), "r"(d.z), "r"(one));
+                }
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        accA[c] += ((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu);
+                        accB[c] += ((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu);
+                    }
+                }
+            }
+        }
+        // ---- reduce over the warp, then into the CTA's counters ------------------------------------------------------------------------------
+#pragma unroll
+        for (uint32_t c = 0; c < 3; ++c) {
+            const uint32_t a = __reduce_add_sync(0xFFFFFFFFu, accA[c]);
+            const uint32_t b = __reduce_add_sync(0xFFFFFFFFu, accB[c]);
+            if (lane == 0) {
+                if (a) atomicAdd(&S.cnt[3 + c], a);
+                if (b) atomicAdd(&S.cnt[c], b);
+            }
+        }
+        __syncthreads();                                                                            // (D)
+        if (tid < 16) {
+            uint32_t v;
+            if (tid < 3) v = S.cnt[6 + tid];
+            else if (tid < 12) {
+                const uint32_t cls = (tid - 3) / 3, o = (tid - 3) % 3;
+                const uint32_t behind = S.cnt[cls], ahead = S.cnt[3 + cls], all = n_q * S.cnt[6 + cls];
+                v = o == 0 ? ahead : (o == 2 ? behind : all - ahead - behind);   // HP[class][ahead|tied|behind] (:213-218)
+            } else if (tid < 15) v = S.cnt[6 + tid - 12];
+            else v = (uint32_t)nb;
+            out[idx * 16 + tid] = v;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)          // other GPUs' result buffers (NVLink stores)
+                if (k < peers.n) peers.p[k][idx * 16 + tid] = v;
+        }
+    }
+}
+
+cudaError_t launch_hp_ref5(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *flag_slot,
+                           const PeerOut &peers, cudaStream_t st) {
+    // flag_slot points at the call's 16-byte slot: [0] flag word (bit 2 = malformed row marked), [1] this kernel's work counter
+    if (n == 0) return cudaSuccess;
+    if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
+    const size_t smem = sizeof(Ref5Smem);
+    cudaError_t e = cudaFuncSetAttribute(hp_ref5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    static int bps = 0;
+    if (bps == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, hp_ref5_kernel, kR5Threads, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) bps = 1;
+    }
+    int64_t blocks = (int64_t)sms * bps;
+    if (blocks > n) blocks = n;
+    e = cudaMemsetAsync(flag_slot, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    count_launch(); hp_ref5_kernel<<<(int)blocks, kR5Threads, smem, st>>>(sit, n, out, T, 1u, flag_slot,
+                                                                          reinterpret_cast<unsigned int *>(flag_slot) + 1, peers);
+    return cudaGetLastError();
+}
+
+}  // namespace holdem

@@ -73,6 +73,11 @@ cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *
 cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *bad_flag,
                           cudaStream_t st);
 
+// HOLDEM_MODE_REFERENCE, all streets, rank-multiset formulation (kernels_hp_ref5.cu): the default.  flag_slot = the call's 16-byte
+// slot ([0] flag word, bit 2 = malformed row marked; [1] work counter, zeroed here); rows go to the peers as well.
+cudaError_t launch_hp_ref5(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *flag_slot,
+                           const PeerOut &peers, cudaStream_t st);
+
 // kernels_aux.cu: content hash of result rows, the Decision.py threshold tree, rank-major wire ints -> situation rows.
 cudaError_t launch_rows_hash(const uint32_t *rows, int64_t n, int words, int64_t first_row, uint64_t *out, int sms,
                              cudaStream_t st);

@@ -46,6 +46,7 @@ SYMBOLS = {
     "holdem_hp_batch_host": (_i, [_vp, _i64, _i, _vp]),
     "holdem_hp_batch_host_staged": (_i, [_vp, _i64, _i, _vp]),
     "holdem_hp_batch_variant": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "holdem_hp_ref_variant": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hs_batch_variant": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "holdem_exhaustive7_variant": (_i, [_i, _vp, _vp, _vp]),
     "holdem_rows_hash": (_i, [_vp, _i64, _i, _i64, _vp, _vp]),

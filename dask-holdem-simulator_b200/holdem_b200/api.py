@@ -122,16 +122,17 @@ def hand_strength_counts(sit: torch.Tensor, mode="treys", variant: int = None, b
 
 def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = None,
                           direct: bool = False, flop_variant: int = None, turn_variant: int = None,
-                          variants=None, binding: str = "ops") -> torch.Tensor:
+                          variants=None, ref_variant: int = None, binding: str = "ops") -> torch.Tensor:
     """HS + HP counts per situation: int32 [N,16] = ahead tied behind | HP[3][3] | HPTotal[3] | n_board.
     `out` may be a [N,16] int32 view into a larger buffer (e.g. this rank's slice of an all-gather buffer).
     direct=True forces the plain-enumeration kernel (the independent second implementation).  flop_variant (treys mode,
     flop rows only; 4 = rank-multiset kernel, 3 / 2 = the 4-set kernels) runs one named implementation of the flop kernel
     for A/B measurements; rows of other streets are then left as they are in `out`.  turn_variant (4 = rank-multiset
     kernel, 3 = 3-set walk) does the same for turn rows.  variants=(flop, turn, river) runs a whole mixed-street treys batch
-    through named kernels (holdem_hp_batch_variant)."""
+    through named kernels (holdem_hp_batch_variant).  ref_variant (mode='reference': 5 = rank-multiset kernel, 4 = the
+    earlier 4-set kernel) does the same for the reference's literal mode."""
     _require_cuda(sit, "sit", torch.uint8, 8)
-    plain = not direct and flop_variant is None and turn_variant is None and variants is None
+    plain = not direct and flop_variant is None and turn_variant is None and variants is None and ref_variant is None
     ops = _ops_ns(binding)
     if ops is not None and plain and out is None:
         return ops.hp(sit, mode_id(mode))
@@ -145,7 +146,11 @@ def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = N
         ops.hp_out(sit, mode_id(mode), out)
         return out
     with _enter(sit) as (lib, st):
-        if variants is not None:
+        if ref_variant is not None:
+            if mode_id(mode) != MODE_REFERENCE or direct:
+                raise ValueError("ref_variant applies to mode='reference' without direct=True")
+            _lib.check(lib.holdem_hp_ref_variant(sit.data_ptr(), sit.shape[0], int(ref_variant), out.data_ptr(), st))
+        elif variants is not None:
             if mode_id(mode) != MODE_TREYS or direct or flop_variant is not None or turn_variant is not None:
                 raise ValueError("variants applies to mode='treys' alone")
             f, t, r = (int(v) for v in variants)

@@ -152,6 +152,9 @@ int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
  * points replace the HOLDEM_*_KERNEL environment switches of ABI version 1: production dispatch reads no environment. */
 int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, int turn_variant, int river_variant,
                             uint32_t *d_out, void *stream);
+/* HOLDEM_MODE_REFERENCE batches (all streets) through a named kernel: 5 = rank-multiset kernel (what holdem_hp_batch runs),
+ * 4 = the earlier 4-set walk with arithmetic ranking of the irregular runouts.  Same counts. */
+int holdem_hp_ref_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 /* holdem_hs_batch through a named kernel: 0 = production (Treys mode: rank-pair kernel), 1 = one evaluation per holding. */
 int holdem_hs_batch_variant(const uint8_t *d_sit, int64_t n, int mode, int variant, uint32_t *d_out, void *stream);
 /* holdem_exhaustive7 through a named kernel: 0 = tuple kernel (production), 1 = chunk-per-thread kernel. */

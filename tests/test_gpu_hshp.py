@@ -118,6 +118,38 @@ def test_hp_full_size_properties(hb):
     assert torch.equal(rows[sl], direct)
 
 
+def test_hp_reference_v5_kernel_full_size(hb, oracle):
+    """mode=reference (HandCalculations.py:178-226 as written): the rank-multiset kernel (kernels_hp_ref5.cu) against the plain
+    enumeration kernel -- one literal category evaluation per (holding, runout) pair -- on 65,536 flop + 65,536 turn + 16,384
+    river situations, against the earlier 4-set kernel, and against the C oracle on board textures that stress the flush part
+    (monotone / four- and five-suited boards, paired boards, our own flush draws)."""
+    textures = [([14, 1], [31, 32, 33]), ([0, 1], [2, 3, 4]), ([13, 26], [2, 3, 4]), ([5, 7], [1, 3, 9]), ([5, 20], [1, 3, 30]),
+                ([12, 25], [0, 14, 28]), ([12, 25], [11, 24, 37]), ([0, 13], [26, 39, 1]), ([24, 48], [26, 2, 16]),
+                ([0, 1], [2, 3, 4, 5]), ([13, 26], [2, 3, 4, 5]), ([12, 11], [2, 3, 4, 18]), ([39, 1], [41, 42, 43, 44]),
+                ([0, 12], [13, 26, 39, 1]), ([21, 47], [8, 34, 9, 35]),
+                ([0, 1], [2, 3, 4, 5, 6]), ([13, 26], [2, 3, 4, 5, 7]), ([12, 25], [0, 2, 4, 6, 8]), ([11, 13], [0, 2, 4, 6, 21]),
+                ([0, 13], [26, 27, 28, 29, 30]), ([5, 18], [31, 44, 6, 19, 32]), ([50, 51], [49, 48, 47, 46, 45])]
+    for nb in (3, 4, 5):
+        sub = [c for c in textures if len(c[1]) == nb]
+        sit = hb.pack_situations([c[0] for c in sub], [c[1] for c in sub])
+        want = oracle.hp_batch(sit, "reference")
+        d = torch.from_numpy(sit).cuda()
+        for variant in (5, 4):
+            got = _u32(hb.hand_potential_counts(d, "reference", ref_variant=variant))
+            bad = np.nonzero((got != want).any(axis=1))[0]
+            assert bad.size == 0, (nb, variant, bad, sit[bad[:3]], got[bad[:3]], want[bad[:3]])
+    for nb, n in ((3, 65536), (4, 65536), (5, 16384)):
+        d = torch.from_numpy(hb.random_situations(n, seed=700 + nb, n_board=nb)).cuda()
+        v5 = hb.hand_potential_counts(d, "reference")
+        direct = hb.hand_potential_counts(d, "reference", direct=True)
+        bad = torch.nonzero((v5 != direct).any(dim=1)).flatten()
+        assert bad.numel() == 0, (nb, bad[:5].tolist(), d[bad[:2]].tolist(), v5[bad[:2]].tolist(), direct[bad[:2]].tolist())
+        sl = slice(0, 4096)
+        assert torch.equal(hb.hand_potential_counts(d[sl].contiguous(), "reference", ref_variant=4), v5[sl])
+        hs = hb.hand_strength_counts(d, "reference")
+        assert torch.equal(hs, v5[:, 0:3])
+
+
 def test_hp_treys_all_65536_vs_oracle(hb, oracle):
     """EVERY row of the headline workload (BASELINE.json configs[2]: 65,536 random flop situations, seed 20251019)
     against the C oracle -- made affordable by the oracle's 4-set cache (oracle/ehs_oracle.c:
