@@ -272,6 +272,13 @@ int holdem_init(int device) {
         S.T.disp_entries[i] = (uint32_t)t.nf[i].disp.size();
         S.T.val_entries[i] = (uint32_t)t.nf[i].val.size();
     }
+    for (int k = 3; k <= 5; ++k) {          // reference-mode category tables: built on the device (71 MB in all, ~1 ms)
+        uint8_t *tab = nullptr;
+        CUDA_TRY(cudaMalloc(&tab, ref_t_table_bytes(k)));
+        CUDA_TRY(launch_ref_t_table(tab, k, prop.multiProcessorCount, nullptr));
+        S.T.ref_t[k - 3] = tab;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMalloc(&S.flags, 4 * kFlagRing * sizeof(int)));     // 16-byte slots: flag word + work counters
     CUDA_TRY(cudaMemset(S.flags, 0, 4 * kFlagRing * sizeof(int)));
     {

@@ -47,6 +47,7 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint16_t *board4_opp6;      // [1820][96]
     const uint16_t *own6_our7;        // [18564][16]
     const uint16_t *own6_rank6;       // [18564]
+    const uint8_t *ref_t[3];          // HOLDEM_MODE_REFERENCE: [455 | 1820 | 6188][8384] category tables (kernels_hp_ref5.cu), device-built
 };
 
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,

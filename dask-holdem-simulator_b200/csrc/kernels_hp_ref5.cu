@@ -29,8 +29,9 @@
 //                        ~7 K items on a rainbow flop, ~45 K two-tone, ~240 K monotone instead of 1.27 M evaluations.
 //
 // One CTA of 256 threads per situation (claimed from a global counter: suited boards cost far more than rainbow ones).  Per
-// situation: the unseen cards in (rank, suit) order and per-suit position lists; T[91][91] computed on the fly from the board's
-// rank counts (two nibbles per entry: NF and keep(NF)); our category on every runout and the class of every holding by the
+// situation: the unseen cards in (rank, suit) order and per-suit position lists; T[91][91] (two nibbles per entry: NF and keep(NF))
+// = the board's 8,384-byte row of a device-resident table built at holdem_init, fetched with cp.async.bulk onto an mbarrier
+// under the set-up phases; our category on every runout and the class of every holding by the
 // arithmetic ranker of device_common.cuh (multiset-exact); then the generic entries and a dynamic queue of flush tasks
 // (32 runouts of one (suit, cards-in-suit) class x a segment of the suit's holding descriptors; a step is one broadcast
 // descriptor load, one table byte, a bit test and four compare / predicated multiply-add pairs on packed 10-bit class counters).
@@ -50,15 +51,17 @@ constexpr int kTPitch5 = 92;          // bytes per row of T
 constexpr int kPP5 = 91;
 constexpr int kMaxQ5 = 1176;          // C(49,2)
 constexpr int kMaxP5 = 1081;          // C(47,2)
-constexpr int kPDCap5 = 2304;         // holding descriptors of all suits (a 5-card board can need 1081 + 2 x ~450, see below)
-constexpr int kSeg5 = 192;            // steps per flush task (packed 10-bit counters hold 1023)
+constexpr int kPDCap5 = 1024;         // holding descriptors of all suits: at most C(n,2) + 13 n + 91 per suit, n <= 11 cards of the suit unseen
+constexpr int kSeg5 = 96;             // steps per flush task: a step adds at most 9 to a packed 10-bit counter (1023)
+constexpr int kTRow5 = 8384;          // bytes per board of the global T tables (91 x 92 rounded up to a multiple of 16)
 constexpr int kMaxTaskGroups = 12;    // (suit, cards of Q in suit) classes
 
 struct Ref5Smem {
-    uint4 PD[kPDCap5];                 // x = rank bits of the holding's cards in s | pp << 16, y = 1 << 10 cls(P), z = 1 << 10 clsr(pp)
+    uint4 PD[kPDCap5];                 // x = rank bits of the holding's cards in s, y = 1 << 10 cls(P), z = 1 << 10 clsr(pp), w = pp
     unsigned long long Wt[96];         // per rank pair: N(pp) << 20 clsr(pp)
+    unsigned long long bar;            // mbarrier of the T row copy
     uint32_t M[kPP5 * 9 + 1];          // runouts by (rank pair, our category)
-    uint32_t elist[kPP5 * 9 + 1];      // nonzero entries of M, compacted
+    uint16_t elist[kPP5 * 9 + 1];      // nonzero entries of M, compacted
     uint32_t cyc[256];                 // bit m: the 13-bit rank mask m holds a cyclic five-run (static)
     uint32_t cnt[12];                  // behind[3], ahead[3] (by class), class totals[3]
     uint32_t bmask[4];                 // board rank mask per suit
@@ -67,7 +70,7 @@ struct Ref5Smem {
     uint32_t pd_base[4], pd_len[4];
     uint32_t n_groups, n_entries, next_task, claim;
     uint16_t pairs[kMaxQ5 + 8];        // colex pairs i | j << 8 (static)
-    uint8_t T[kPP5 * kTPitch5 + 4];    // [q][pp]: NF | keep(NF) << 4
+    alignas(16) uint8_t T[kTRow5];     // [q][pp]: NF | keep(NF) << 4 -- one row of the global table of this board size
     uint8_t ourQ[kMaxQ5 + 8];          // our category on runout (i,j), colex index over the positions of D
     uint8_t clsP[kMaxP5 + 7];          // class of holding (i,j), colex index over the positions of U
     uint8_t clsR[96];                  // per rank pair: class from ranks alone
@@ -77,6 +80,8 @@ struct Ref5Smem {
     uint8_t Lns[4][52];                // positions of D with another suit, same order
     uint8_t nsu[4], nsd[4];            // cards of suit s among the unseen cards / among D
     uint8_t u[16];                     // unseen cards per rank
+    uint8_t rstart[16];                // first position of each rank among the unseen cards
+    uint32_t smask[4];                 // rank mask of the unseen cards per suit
 };
 
 __device__ __forceinline__ LitHand one_card5(uint32_t c) {
@@ -91,7 +96,76 @@ __device__ __forceinline__ void cmp_add64(unsigned long long &gt, unsigned long 
     if (a < b) lt += w;
 }
 
+// index of a sorted rank multiset r0 <= r1 <= ... in the combinatorial number system: sum of C(r_i + i, i + 1)
+__device__ __forceinline__ uint32_t multiset_index(const uint32_t *r, int k) {
+    uint32_t idx = 0;
+    for (int i = 0; i < k; ++i) {
+        uint32_t c = 1;                       // C(r_i + i, i + 1)
+        for (int j = 0; j <= i; ++j) c = c * (r[i] + i - j) / (j + 1);
+        idx += c;
+    }
+    return idx;
+}
+
 }  // namespace
+
+// T tables of HOLDEM_MODE_REFERENCE, one row of kTRow5 bytes per board rank multiset (k = 3, 4, 5 board cards: 455 / 1820 / 6188
+// rows): entry [q][pp] = category from the rank counts of board + rank pair q + rank pair pp (low nibble) and the value it takes
+// when a flush that is no straight flush is present (high nibble).  Built on the device at holdem_init by the same arithmetic
+// ranker the batched category kernel uses (pinned to the unmodified reference by tests/golden/literal_category.json).
+__global__ void __launch_bounds__(256)
+ref_t_table_kernel(uint8_t *__restrict__ table, int k, uint32_t n_boards) {
+    __shared__ uint32_t ranks[5];
+    __shared__ uint8_t ppxy[96];
+    for (uint32_t b = blockIdx.x; b < n_boards; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) {               // unrank b: largest r with C(r + i, i + 1) <= rest, from the top position down
+            uint32_t rest = b;
+            for (int i = k - 1; i >= 0; --i) {
+                uint32_t r = 0;
+                for (;;) {
+                    uint32_t c = 1;
+                    for (int j = 0; j <= i; ++j) c = c * (r + 1 + i - j) / (j + 1);     // C(r + 1 + i, i + 1)
+                    if (c > rest) break;
+                    ++r;
+                }
+                uint32_t c = 1;
+                for (int j = 0; j <= i; ++j) c = c * (r + i - j) / (j + 1);
+                rest -= c;
+                ranks[i] = r;
+            }
+        }
+        if (threadIdx.x < 96) {
+            uint32_t y = 0;
+            while (tri(y + 1) <= threadIdx.x) ++y;
+            ppxy[threadIdx.x] = threadIdx.x < (uint32_t)kPP5 ? (uint8_t)((threadIdx.x - tri(y)) | (y << 4)) : (uint8_t)0xFF;
+        }
+        __syncthreads();
+        LitHand lb = {0, 0, 0, 0, 0};
+        for (int i = 0; i < k; ++i) { lb.rc += 1ull << (4 * ranks[i]); lb.rmask |= 1u << ranks[i]; }
+        uint8_t *row = table + (size_t)b * kTRow5;
+        for (uint32_t e = threadIdx.x; e < (uint32_t)(kPP5 * kPP5); e += blockDim.x) {
+            const uint32_t q = e / kPP5, p = e - q * kPP5;
+            const uint32_t qxy = ppxy[q], pxy = ppxy[p];
+            LitHand h = lb;
+            const uint32_t r4[4] = {qxy & 15u, qxy >> 4, pxy & 15u, pxy >> 4};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { h.rc += 1ull << (4 * r4[t]); h.rmask |= 1u << r4[t]; }
+            const uint32_t nf = lit_category(h);
+            row[q * kTPitch5 + p] = (uint8_t)(nf | (((nf == 4u || nf >= 6u) ? nf : 5u) << 4));
+        }
+        for (uint32_t e = threadIdx.x; e < (uint32_t)kTRow5; e += blockDim.x)
+            if (e >= (uint32_t)(kPP5 * kTPitch5) || e % kTPitch5 == (uint32_t)kPP5) row[e] = 0;     // padding bytes
+    }
+}
+
+size_t ref_t_table_bytes(int k) { return (size_t)(k == 3 ? 455 : (k == 4 ? 1820 : 6188)) * kTRow5; }
+
+cudaError_t launch_ref_t_table(uint8_t *table, int k, int sms, cudaStream_t st) {
+    const uint32_t n_boards = k == 3 ? 455u : (k == 4 ? 1820u : 6188u);
+    count_launch(); ref_t_table_kernel<<<sms * 4, 256, 0, st>>>(table, k, n_boards);
+    return cudaGetLastError();
+}
 
 __global__ void __launch_bounds__(kR5Threads)
 hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T, uint32_t one,
@@ -113,6 +187,12 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
     }
     const uint32_t t_s = (uint32_t)__cvta_generic_to_shared(S.T);
     const uint32_t cyc_s = (uint32_t)__cvta_generic_to_shared(S.cyc);
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&S.bar);
+    if (tid == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t parity = 0;
 
     for (;;) {
         __syncthreads();                                                                            // previous situation consumed
@@ -179,6 +259,7 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             if (lane < 13) {
                 const uint32_t c4 = 4 * lane;
                 S.u[lane] = (uint8_t)(c4 < 32 ? __popc((m0 >> c4) & 15u) : __popc((m1 >> (c4 - 32)) & 15u));
+                S.rstart[lane] = (uint8_t)(c4 < 32 ? __popc(m0 & ((1u << c4) - 1u)) : __popc(m0) + __popc(m1 & ((1u << (c4 - 32)) - 1u)));
             }
             __syncwarp();
             const uint32_t cd0 = S.code[lane], cd1 = lane + 32 < md ? S.code[lane + 32] : 0u;
@@ -195,7 +276,10 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                     if (a1) S.Ls[s][n0 + __popc(b1 & ltm)] = (uint8_t)(lane + 32);
                     else S.Lns[s][(32 - n0) + __popc(vb1 & ~b1 & ltm)] = (uint8_t)(lane + 32);
                 }
+                const bool un1 = lane + 32 < m;                       // unseen (not one of our hole cards)
+                const uint32_t rm = __reduce_or_sync(0xFFFFFFFFu, (a0 ? 1u << (cd0 >> 2) : 0u) | ((a1 && un1) ? 1u << (cd1 >> 2) : 0u));
                 if (lane == 0) {
+                    S.smask[s] = rm;
                     const uint32_t nd = n0 + __popc(b1);
                     const uint32_t hole_s = (uint32_t)((S.code[m] & 3u) == s) + (uint32_t)((S.code[m + 1] & 3u) == s);
                     S.nsd[s] = (uint8_t)nd;
@@ -203,21 +287,19 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 }
             }
         }
-        // ---- T[q][pp]: category from the rank counts of board + two rank pairs, plain (low nibble) and as it reads when a flush
-        //      that is no straight flush is present (high nibble: quads / full house / straight survive, :68-72, else 5) ---------------
-        for (uint32_t e = tid; e < (uint32_t)(kPP5 * kPP5); e += kR5Threads) {
-            const uint32_t q = e / kPP5, p = e - q * kPP5;
-            if (p < q) continue;
-            const uint32_t qxy = S.ppxy[q], pxy = S.ppxy[p];
-            LitHand h = lb;
-            h.sc = 0; h.cards = 0; h.dup = 0;
-            const uint32_t r4[4] = {qxy & 15u, qxy >> 4, pxy & 15u, pxy >> 4};
+        if (tid == 32) {
+            // ---- T = the board's row of the global table (8,384 bytes), fetched by the TMA engine under the set-up phases -------------
+            uint32_t br[5];
+            int k = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { h.rc += 1ull << (4 * r4[k]); h.rmask |= 1u << r4[k]; }
-            const uint32_t nf = lit_category(h);
-            const uint8_t v = (uint8_t)(nf | (((nf == 4u || nf >= 6u) ? nf : 5u) << 4));
-            S.T[q * kTPitch5 + p] = v;
-            S.T[p * kTPitch5 + q] = v;
+            for (int j = 2; j < 7; ++j)
+                if (j - 2 < nb) br[k++] = card_rank(cb[j]);
+            for (int i = 1; i < nb; ++i)                               // insertion sort, <= 5 ranks
+                for (int j = i; j > 0 && br[j - 1] > br[j]; --j) { const uint32_t t = br[j]; br[j] = br[j - 1]; br[j - 1] = t; }
+            const uint32_t bi = multiset_index(br, nb);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of T precede the refill
+            mbar_expect_tx(bar_s, kTRow5);
+            bulk_g2s(t_s, T.ref_t[nb - 3] + (size_t)bi * kTRow5, kTRow5, bar_s);
         }
         __syncthreads();                                                                            // (A) lists, u[] ready
         // ---- per rank pair: class from ranks alone and the number of holdings ---------------------------------------------------------
@@ -273,8 +355,10 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             const uint32_t s = min(lane / 3u, 3u), qtype = 2u - (lane - 3u * (lane / 3u));
             const uint32_t bs = (bsuit >> (4 * s)) & 15u;
             const uint32_t nu = S.nsu[s], nnu = m - nu, nd = S.nsd[s], nnd = md - nd;
-            // holdings of the suit by their cards in s: [two | one | none]
-            const uint32_t len2 = choose2u(nu), len1 = len2 + nu * nnu, len0 = n_p;
+            // holdings of the suit by their cards in s: [two, card by card | one: (card a in s, rank of the other card) |
+            // none: rank pairs] -- cards outside s matter through their rank only, so those holdings are merged into weighted steps
+            const uint32_t len2 = choose2u(nu), len1 = len2 + 13u * nu, len0 = len1 + (uint32_t)kPP5;
+            (void)nnu;
             // longest prefix any runout class needs: cards of s the holding must bring when the runout brings two
             const int need2 = 5 - (int)bs - 2;
             const uint32_t len = bs == 0 ? 0u : (need2 >= 3 ? 0u : (need2 == 2 ? len2 : (need2 == 1 ? len1 : len0)));
@@ -319,7 +403,7 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             uint32_t base = 0;
             if (lane == 0 && bal) base = atomicAdd(&S.n_entries, __popc(bal));
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (nz) S.elist[base + __popc(bal & ((1u << lane) - 1u))] = e;
+            if (nz) S.elist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
         }
         // ---- holding descriptors of the flush part --------------------------------------------------------------------------------------
         {
@@ -330,42 +414,73 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 for (uint32_t q = 1; q < 4; ++q)
                     if (S.pd_len[q] && e >= S.pd_base[q]) s = q;
                 const uint32_t t = e - S.pd_base[s];
-                const uint32_t nu = S.nsu[s], nnu = m - nu, nboth = choose2u(nu);
-                uint32_t pa, pb;                                   // positions in D (both < m)
-                if (t < nboth) {
+                const uint32_t nu = S.nsu[s], nboth = choose2u(nu), sm = S.smask[s];
+                // first / second unseen card of rank r outside s (positions; the unseen cards are sorted by rank, then suit)
+                auto rep = [&](uint32_t r, uint32_t skip) -> uint32_t {
+                    uint32_t pos = S.rstart[r];
+                    for (uint32_t k = 0; k < 4u; ++k) {
+                        const uint32_t ps = pos + k;
+                        if ((S.code[ps] & 3u) != s) { if (skip == 0) return ps; --skip; }
+                    }
+                    return pos;
+                };
+                uint32_t bits, pp, wgt, pa, pb;                    // pa, pb: a representative holding (positions in D, both < m)
+                if (t < nboth) {                                   // both cards in s: card by card
                     const uint32_t pr = S.pairs[t];
                     pa = S.Ls[s][pr & 0xFFu]; pb = S.Ls[s][pr >> 8];
-                } else if (t < nboth + nu * nnu) {
-                    const uint32_t t2 = t - nboth, a = t2 / nnu, z = t2 - a * nnu;
-                    pa = S.Ls[s][a]; pb = S.Lns[s][z];
-                } else {
-                    const uint32_t pr = S.pairs[t - nboth - nu * nnu];
-                    pa = S.Lns[s][pr & 0xFFu]; pb = S.Lns[s][pr >> 8];
+                    const uint32_t ra = S.code[pa] >> 2, rb = S.code[pb] >> 2;
+                    bits = (1u << ra) | (1u << rb);
+                    pp = tri(max(ra, rb)) + min(ra, rb);
+                    wgt = 1;
+                } else if (t < nboth + 13u * nu) {                 // card a in s, any unseen card of rank y outside s
+                    const uint32_t t2 = t - nboth, ai = t2 / 13u, y = t2 - 13u * ai;
+                    pa = S.Ls[s][ai];
+                    const uint32_t ra = S.code[pa] >> 2;
+                    bits = 1u << ra;
+                    pp = tri(max(ra, y)) + min(ra, y);
+                    wgt = S.u[y] - ((sm >> y) & 1u);
+                    pb = wgt ? rep(y, 0) : pa;
+                } else {                                           // a rank pair, neither card in s
+                    pp = t - nboth - 13u * nu;
+                    const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
+                    const uint32_t wx = S.u[x] - ((sm >> x) & 1u), wy = S.u[y] - ((sm >> y) & 1u);
+                    bits = 0;
+                    wgt = x != y ? wx * wy : (wx ? wx * (wx - 1) / 2 : 0u);
+                    pa = wgt ? rep(x, 0) : 0u;
+                    pb = wgt ? (x != y ? rep(y, 0) : rep(x, 1)) : 1u;
                 }
                 const uint32_t lo = min(pa, pb), hi = max(pa, pb);
-                const uint32_t ca = S.code[pa], cb2 = S.code[pb];
-                const uint32_t ra = ca >> 2, rb = cb2 >> 2;
-                const uint32_t bits = ((ca & 3u) == s ? 1u << ra : 0u) | ((cb2 & 3u) == s ? 1u << rb : 0u);
-                const uint32_t pp = tri(max(ra, rb)) + min(ra, rb);
-                S.PD[e] = make_uint4(bits | (pp << 16), 1u << (10 * S.clsP[hi * (hi - 1) / 2 + lo]), 1u << (10 * S.clsR[pp]), 0u);
+                const uint32_t cls = wgt && lo != hi ? (uint32_t)S.clsP[hi * (hi - 1) / 2 + lo] : 0u;
+                S.PD[e] = make_uint4(bits, wgt << (10 * cls), wgt << (10 * S.clsR[pp]), pp);
             }
         }
         __syncthreads();                                                                            // (C)
 
         uint32_t accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};     // per class: our > opp (ahead) / our < opp (behind), net, mod 2^32
-        // ---- generic part -----------------------------------------------------------------------------------------------------------------
+        mbar_wait(bar_s, parity);                                      // T has landed
+        parity ^= 1u;
+        // ---- generic part: eight lanes share one (rank pair, our category) entry, each takes every eighth rank pair -------------------------
         {
             const uint32_t n_entries = S.n_entries;
-            for (uint32_t k = tid; k < n_entries; k += kR5Threads) {
-                const uint32_t e = S.elist[k], q = e / 9u, o = e - 9u * q, mult = S.M[e];
+            const uint32_t sub = lane & 7u;
+            for (uint32_t k0 = tid >> 3; k0 < ((n_entries + 3u) & ~3u); k0 += kR5Threads / 8) {   // warp-uniform trip count
+                const bool act = k0 < n_entries;
+                const uint32_t e = act ? (uint32_t)S.elist[k0] : 0u, q = e / 9u, o = e - 9u * q;
                 const uint8_t *row = S.T + q * kTPitch5;
                 unsigned long long gt = 0, lt = 0;
-#pragma unroll 7
-                for (uint32_t pp = 0; pp < (uint32_t)kPP5; ++pp) cmp_add64(gt, lt, o, (uint32_t)row[pp] & 15u, S.Wt[pp]);
+                for (uint32_t pp = sub; pp < (uint32_t)kPP5; pp += 8) cmp_add64(gt, lt, o, (uint32_t)row[pp] & 15u, S.Wt[pp]);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    accA[c] += (uint32_t)((gt >> (20 * c)) & 0xFFFFFu) * mult;
-                    accB[c] += (uint32_t)((lt >> (20 * c)) & 0xFFFFFu) * mult;
+                for (int d = 1; d < 8; d <<= 1) {
+                    gt += __shfl_xor_sync(0xFFFFFFFFu, gt, d);
+                    lt += __shfl_xor_sync(0xFFFFFFFFu, lt, d);
+                }
+                if (act && sub == 0) {
+                    const uint32_t mult = S.M[e];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        accA[c] += (uint32_t)((gt >> (20 * c)) & 0xFFFFFu) * mult;
+                        accB[c] += (uint32_t)((lt >> (20 * c)) & 0xFFFFFu) * mult;
+                    }
                 }
             }
         }
@@ -412,12 +527,12 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 const uint32_t tq_s = t_s + trow;
                 const uint4 *pd = S.PD + S.g_pdbase[g] + p0;
                 uint32_t aG = 0, aL = 0, sG = 0, sL = 0;
-#pragma unroll 2
+#pragma unroll 4
                 for (uint32_t t = p0; t < p1; ++t, ++pd) {
                     const uint4 d = *pd;
-                    const uint32_t pbits = d.x & 0xFFFFu;
+                    const uint32_t pbits = d.x;
                     uint32_t e8;
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e8) : "r"(tq_s + (d.x >> 16)));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e8) : "r"(tq_s + d.w));
                     const uint32_t mask = base_mask | pbits;
                     uint32_t cw;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(cyc_s + ((mask >> 5) << 2)));

@@ -78,6 +78,10 @@ cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uin
 cudaError_t launch_hp_ref5(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *flag_slot,
                            const PeerOut &peers, cudaStream_t st);
 
+// Device-side construction of the reference-mode category tables (k = 3, 4, 5 board cards); called once per device by holdem_init.
+size_t ref_t_table_bytes(int k);
+cudaError_t launch_ref_t_table(uint8_t *table, int k, int sms, cudaStream_t st);
+
 // kernels_aux.cu: content hash of result rows, the Decision.py threshold tree, rank-major wire ints -> situation rows.
 cudaError_t launch_rows_hash(const uint32_t *rows, int64_t n, int words, int64_t first_row, uint64_t *out, int sms,
                              cudaStream_t st);
