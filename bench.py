@@ -211,8 +211,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG is left as the driver set it (its log is how the driver counts ranks); the JSON line is printed last,
-        # after the process group is gone, so it stays one intact line.
+        # NCCL_DEBUG is left as the driver set it (its log is how the driver counts ranks) but the log is routed to stderr, so
+        # that stdout holds exactly one line: the JSON (NCCL still prints a line at process exit, after anything we could print).
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     hb._lib.init(local_rank)
     golden = load_json("tests", "golden", "gpu_hashes.json")

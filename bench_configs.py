@@ -63,7 +63,8 @@ def config5(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"      # keep stdout to the JSON line, the log stays visible
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.situations
     sit = torch.from_numpy(hb.random_situations(n, seed=20251021)).cuda()
@@ -85,12 +86,12 @@ def config5(args):
     r = full.cpu().numpy().astype(np.int64)
     ok = bool((r[:, 12:15].sum(axis=1) == 1081).all()
               and (r[:, 3:12].reshape(-1, 3, 3).sum(axis=2) == 990 * r[:, 12:15]).all())
-    checksum = int(r[:, :15].sum())
+    content_hash = f"{hb.rows_hash(full.contiguous()):016x}"
     if rank == 0:
         print(json.dumps({"config": "configs[4]: 1M random flop situations HS+HP sharded over the GPUs, every rank receives all rows (kernels store into all ranks' symmetric-memory buffers over NVLink; NCCL all-gather as fallback)",
                           "n_gpus": world, "situations": n, "ms": float(ms.item()),
                           "situations_per_sec": n / (float(ms.item()) * 1e-3), "scaling": "strong",
-                          "properties_ok": ok, "checksum_of_counts": checksum}), flush=True)
+                          "properties_ok": ok, "content_hash": content_hash}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -223,7 +224,7 @@ def main():
             ok = bool((rows[:, 12:15].sum(axis=1) == m * (m - 1) // 2).all()
                       and (rows[:, 3:12].reshape(-1, 3, 3).sum(axis=2) == runouts * rows[:, 12:15]).all())
         c4[name] = {"ms": ms, "situations_per_sec": sit.shape[0] / (ms * 1e-3), "properties_ok": ok,
-                    "checksum_of_counts": int(rows.sum())}
+                    "content_hash": f"{hb.rows_hash(fn().to(torch.int32).contiguous()):016x}"}
     c4["total_ms"] = total_ms
     c4["hands_per_sec"] = args.hands / (total_ms * 1e-3)
     res["config4_22_seat_table"] = c4

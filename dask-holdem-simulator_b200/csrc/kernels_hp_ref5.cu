@@ -607,4 +607,139 @@ cudaError_t launch_hp_ref5(const DevTables &T, const uint8_t *sit, int64_t n, ui
     return cudaGetLastError();
 }
 
+// =====================================================================================================================================
+// Hand strength in HOLDEM_MODE_REFERENCE from rank pairs (HandCalculations.py:157-176 with the literal ranker): one warp per
+// situation, no shared memory, no tables.
+//   ahead / tied / behind over the C(m,2) opponent holdings.  A holding whose five / six / seven cards with the board hold no
+//   five of a suit is ranked by its rank pair alone:  sum over the 91 rank pairs of n(pp) x cmp(ours, NF(board + pp)), three
+//   rank pairs per lane, NF from the arithmetic ranker on rank counts.  Holdings that do make a flush with the board (the suit
+//   with >= 3 board cards: both cards in it; with >= 4: one card in it, merged by the rank of the other; with 5: every holding,
+//   merged by rank pair) move from the class of NF to the class of  8 if the suit's ranks hold a cyclic five-run, else NF when it
+//   is 7, 6 or 4, else 5.
+__global__ void __launch_bounds__(256)
+hs_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    // the lane's three rank pairs x <= y (of 91) and its three pairs of distinct ranks x < y (of 78), packed x | y << 4
+    uint32_t ppk[3], sqk[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const uint32_t pp = lane + 32u * p;
+        uint32_t y = 0;
+        while (tri(y + 1) <= pp) ++y;
+        ppk[p] = pp < (uint32_t)kPP5 ? ((pp - tri(y)) | (y << 4)) : 0xFFu;
+        y = 1;
+        while (y * (y + 1) / 2 <= pp) ++y;
+        sqk[p] = pp < 78u ? ((pp - y * (y - 1) / 2) | (y << 4)) : 0xFFu;
+    }
+    for (int64_t idx = (int64_t)blockIdx.x * 8 + warp; idx < n; idx += n_warps) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
+        uint32_t cb[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cb[k] = (w.x >> (8 * k)) & 0xFFu; cb[4 + k] = (w.y >> (8 * k)) & 0xFFu; }
+        const uint32_t nb = cb[5] == 0xFFu ? 3u : (cb[6] == 0xFFu ? 4u : 5u);
+        bool ok = true;
+        uint64_t known = 0, bset = 0;
+        uint32_t bsuit = 0;
+        LitHand lb = {0, 0, 0, 0, 0}, lh = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const uint32_t c = cb[k];
+            const bool used = (uint32_t)k < nb + 2;
+            ok = ok && (used ? c < 52u : c == 0xFFu);
+            const uint32_t cc = (used && c < 52u) ? c : 0u;
+            if (used) {
+                known |= card_bit(cc);
+                if (k >= 2) { bset |= card_bit(cc); bsuit += 1u << (4 * card_suit(cc)); lit_add_card(lb, cc); }
+                else lit_add_card(lh, cc);
+            }
+        }
+        ok = ok && (uint32_t)__popcll(known) == nb + 2;
+        if (!ok) {
+            if (lane < 3) out[idx * 3 + lane] = 0xFFFFFFFFu;
+            continue;
+        }
+        const uint32_t ours_now = lit_category(lit_merge(lb, lh));                                 // :163
+        LitHand rb = lb;                                    // the board's rank counts alone
+        rb.sc = 0; rb.cards = 0; rb.dup = 0;
+        // unseen cards per rank: four minus the known ones (bit 13 s + r of the card set); per suit: the complement of the suit's ranks
+        auto unseen = [&](uint32_t r) { return 4u - (uint32_t)__popcll((known >> r) & 0x0000008004002001ull); };
+        auto nf_of = [&](uint32_t x, uint32_t y) {
+            LitHand h = rb;
+            h.rc += (1ull << (4 * x)) + (1ull << (4 * y));
+            h.rmask |= (1u << x) | (1u << y);
+            return lit_category(h);
+        };
+        auto cls_of = [&](uint32_t theirs) { return ours_now > theirs ? 0u : (ours_now == theirs ? 1u : 2u); };   // :168-173
+        int acc0 = 0, acc1 = 0, acc2 = 0;
+        auto add = [&](uint32_t cls, int v) { acc0 += cls == 0 ? v : 0; acc1 += cls == 1 ? v : 0; acc2 += cls == 2 ? v : 0; };
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if (ppk[p] != 0xFFu) {
+                const uint32_t x = ppk[p] & 15u, y = ppk[p] >> 4;
+                const uint32_t ux = unseen(x), uy = unseen(y);
+                const uint32_t cnt = x != y ? ux * uy : (ux * (ux - 1)) / 2;
+                if (cnt) add(cls_of(nf_of(x, y)), (int)cnt);
+            }
+        }
+        // ---- holdings that make a flush with the board ---------------------------------------------------------------------------------
+        const uint32_t f3 = (bsuit + 0x5555u) & 0x8888u;                 // the suit with >= 3 board cards (at most one)
+        if (f3) {
+            const uint32_t s = (uint32_t)(__ffs(f3) - 1) >> 2, bs = (bsuit >> (4 * s)) & 15u;
+            const uint32_t bmask = (uint32_t)(bset >> (13 * s)) & 0x1FFFu;
+            const uint32_t smask = ~(uint32_t)(known >> (13 * s)) & 0x1FFFu;          // unseen ranks of the suit
+            auto flush_cat = [&](uint32_t mask, uint32_t nf) { return cyclic_run5(mask) ? 8u : ((nf == 4u || nf >= 6u) ? nf : 5u); };
+            auto unseen_ns = [&](uint32_t r) { return unseen(r) - ((smask >> r) & 1u); };
+            // both cards in s: pairs of distinct ranks x < y of the suit
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const uint32_t x = sqk[p] & 15u, y = sqk[p] >> 4;
+                if (sqk[p] != 0xFFu && ((smask >> x) & (smask >> y) & 1u) != 0) {
+                    const uint32_t nf = nf_of(x, y);
+                    add(cls_of(flush_cat(bmask | (1u << x) | (1u << y), nf)), 1);
+                    add(cls_of(nf), -1);
+                }
+            }
+            if (bs >= 4) {      // one card a in s, the other outside: merged by the other card's rank
+                for (uint32_t t = lane; t < 169u; t += 32) {
+                    const uint32_t a = t / 13u, y = t - 13u * a;
+                    const uint32_t wgt = ((smask >> a) & 1u) ? unseen_ns(y) : 0u;
+                    if (wgt) {
+                        const uint32_t nf = nf_of(a, y);
+                        add(cls_of(flush_cat(bmask | (1u << a), nf)), (int)wgt);
+                        add(cls_of(nf), -(int)wgt);
+                    }
+                }
+            }
+            if (bs == 5) {      // the board itself is the flush: holdings without a card of s, merged by rank pair
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    if (ppk[p] != 0xFFu) {
+                        const uint32_t x = ppk[p] & 15u, y = ppk[p] >> 4;
+                        const uint32_t wx = unseen_ns(x), wy = unseen_ns(y);
+                        const uint32_t wgt = x != y ? wx * wy : (wx * (wx - 1)) / 2;
+                        if (wgt) {
+                            const uint32_t nf = nf_of(x, y);
+                            add(cls_of(flush_cat(bmask, nf)), (int)wgt);
+                            add(cls_of(nf), -(int)wgt);
+                        }
+                    }
+                }
+            }
+        }
+        const int a0 = __reduce_add_sync(0xFFFFFFFFu, acc0);
+        const int a1 = __reduce_add_sync(0xFFFFFFFFu, acc1);
+        const int a2 = __reduce_add_sync(0xFFFFFFFFu, acc2);
+        if (lane < 3) out[idx * 3 + lane] = (uint32_t)(lane == 0 ? a0 : (lane == 1 ? a1 : a2));
+    }
+}
+
+cudaError_t launch_hs_ref5(const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    count_launch(); hs_ref5_kernel<<<(int)blocks, 256, 0, st>>>(sit, n, out);
+    return cudaGetLastError();
+}
+
 }  // namespace holdem

@@ -157,6 +157,7 @@ hs_kernel(const uint8_t *__restrict__ sit, int64_t n, int mode, uint32_t *__rest
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                             cudaStream_t st, int variant) {
     if (n == 0) return cudaSuccess;
+    if (mode != kModeTreys && variant == 0) return launch_hs_ref5(sit, n, out, sms, st);
     if (mode == kModeTreys && variant == 0) return launch_hs_treys_v4(T, sit, n, out, sms, st);
     int64_t blocks = (n + kHsWarps - 1) / kHsWarps;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;

@@ -34,7 +34,7 @@ cudaError_t launch_smem_gather(int table_bytes, int iters, int pattern, int bloc
 // 16 warp instructions per thread per iteration; mix 0 = compare + predicated multiply-add, 1 = FMA pipe only, 2 = ALU pipe only
 cudaError_t launch_int_issue(int iters, int mix, int blocks, int threads, cudaStream_t st);
 
-// variant 0 = production (treys: rank-pair kernel; reference: per-holding kernel), 1 = the per-holding kernel for both modes.
+// variant 0 = production (rank-pair kernels of both modes), 1 = the per-holding kernel for both modes.
 cudaError_t launch_hs_batch(const DevTables &T, const uint8_t *sit, int64_t n, int mode, uint32_t *out, int sms,
                             cudaStream_t st, int variant = 0);
 // Treys-mode hand strength from rank pairs (kernels_hs4.cu): same results, what launch_hs_batch runs for HOLDEM_MODE_TREYS
@@ -77,6 +77,9 @@ cudaError_t launch_hp_ref(const DevTables &T, const uint8_t *sit, int64_t n, uin
 // slot ([0] flag word, bit 2 = malformed row marked; [1] work counter, zeroed here); rows go to the peers as well.
 cudaError_t launch_hp_ref5(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms, int *flag_slot,
                            const PeerOut &peers, cudaStream_t st);
+
+// Reference-mode hand strength from rank pairs (kernels_hp_ref5.cu): what launch_hs_batch runs for HOLDEM_MODE_REFERENCE.
+cudaError_t launch_hs_ref5(const uint8_t *sit, int64_t n, uint32_t *out, int sms, cudaStream_t st);
 
 // Device-side construction of the reference-mode category tables (k = 3, 4, 5 board cards); called once per device by holdem_init.
 size_t ref_t_table_bytes(int k);
