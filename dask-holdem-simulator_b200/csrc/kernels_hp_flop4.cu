@@ -50,8 +50,15 @@ namespace holdem {
 
 namespace {
 
-constexpr int kGroupThreads = 160;
-constexpr int kGroups = 6;
+// Group shape (threads per situation group, groups per CTA).  Measured on B200, 65,536 random flops: 6 x 160 -> 39.0 M
+// situations/s, 7 x 128 (one more situation in flight per SM) -> 38.8 M: the kernel is bound by instruction issue and
+// shared-memory wavefronts inside the task phase, not by the latency of the per-situation set-up phases.
+#ifndef HOLDEM_F4_GT
+#define HOLDEM_F4_GT 160
+#define HOLDEM_F4_G 6
+#endif
+constexpr int kGroupThreads = HOLDEM_F4_GT;
+constexpr int kGroups = HOLDEM_F4_G;
 constexpr int kThreads4 = kGroupThreads * kGroups;
 constexpr int kU = 47;
 constexpr int kPairs4 = 1081;
@@ -81,6 +88,7 @@ struct Flop4Group {                    // one situation in flight
     uint32_t g_first[kMaxGroups + 1];  // first task id of each flush group; [n_groups] = total
     uint32_t g_nq[kMaxGroups], g_np[kMaxGroups], g_nseg[kMaxGroups], g_seglen[kMaxGroups], g_pdbase[kMaxGroups];
     uint32_t g_sq[kMaxGroups];         // suit | qtype << 2 | rank-level lanes << 4
+    uint32_t g_inv[kMaxGroups];        // ceil(2^16 / cards outside the suit): lane index / that count by multiplication
     uint32_t pd_base[4], pd_len[4];    // PD section per suit
     uint32_t smask[4];                 // rank mask of the unseen cards per suit
     uint32_t hist_none[4];             // holdings without a card of the board's suit, by flop class (monotone boards)
@@ -199,7 +207,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         if (tid < 12) G.cnt[tid] = 0;
         if (tid < 4) { G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu; G.hist_none[tid] = 0; }
-        if (tid >= 64 && tid < 160) G.qflush[tid - 64] = 0;
+        if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
         if (warp == 0) {
             // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
             const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
@@ -275,6 +283,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     G.g_nq[gi] = nq; G.g_np[gi] = np; G.g_nseg[gi] = nseg; G.g_seglen[gi] = seglen;
                     G.g_pdbase[gi] = pdo;
                     G.g_sq[gi] = s | (qtype << 2) | ((uint32_t)rank_lanes << 4);
+                    G.g_inv[gi] = 65535u / max(nns, 1u) + 1u;          // exact for indices < 2^16 / nns (here < 600)
                 }
                 if (lane < 12 && qtype == 2) { G.pd_base[s] = pdo; G.pd_len[s] = len; }
                 if (lane == 11) {
@@ -486,7 +495,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     } else {
                         uint32_t i, j;
                         if (qtype == 1) {
-                            const uint32_t a = qi / nns, z = qi - a * nns;
+                            const uint32_t a = (qi * G.g_inv[g]) >> 16, z = qi - a * nns;      // qi / nns
                             const uint32_t x = G.Ls[s][a], y = G.Lns[s][z];
                             i = min(x, y); j = max(x, y);
                             zpos = y;
