@@ -7,9 +7,13 @@ the Treys evaluation behind evaluate_best_hand (:229-240) run in hand-written CU
 C ABI of include/holdem_b200.h.  There is no CPU fallback: importing works anywhere, calling needs a B200.
 
 Rank semantics: environment variable HOLDEM_MODE, or set_mode():
-  "treys"     (default) canonical Effective-Hand-Strength enumeration on Treys ranks -- what BASELINE.json grades.
-  "reference" the reference's code exactly as written (9-category ranker, 1176 runouts, quirks) -- bit-identical to
-              the original module, e.g. HandPotential([14,1],[31,32,33]) -> [135.2782, 327.2654].
+  "reference" (default) the reference's code exactly as written (9-category ranker, 1176 runouts, quirks) -- this module is
+              a drop-in, so by default every function returns what the original module returns, bit for bit, e.g.
+              HandStrength([0,13],[26..30]) -> 0.5 and HandPotential([14,1],[31,32,33]) -> [135.2782, 327.2654].
+  "treys"     opt-in: the canonical Effective-Hand-Strength enumeration on Treys ranks (what BASELINE.json grades and the
+              batched API / bench.py use explicitly).  In this mode PPot/NPot are still the reference's unnormalised formula
+              (:221-224); use HandPotentialCounts / EffectiveHandStrength or holdem_b200.normalised_potentials for
+              probabilities.
 The float formulas are the reference's own in both modes (:175 in Python floats, :221-224 in float32 tensors).
 """
 import itertools
@@ -32,7 +36,7 @@ from pokerlib_to_treys import convert_to_treys, Evaluator, Card  # noqa: F401
 # Pre-flight check exactly like the reference (HandCalculations.py:22)
 device = 'cuda' if torch.cuda.is_available() else 'cpu'
 
-_MODE = os.environ.get("HOLDEM_MODE", "treys")
+_MODE = os.environ.get("HOLDEM_MODE", "reference")
 if _MODE not in ("treys", "reference"):
     raise ValueError(f"HOLDEM_MODE must be 'treys' or 'reference', got {_MODE!r}")
 
@@ -157,12 +161,16 @@ def HandPotential(ourcards, boardcards):
 def HandPotentialCounts(ourcards, boardcards):
     """Extension: the integer HP[3][3] matrix and HPTotal[3] the floats above are derived from."""
     row = _api.hand_potential_counts(_situation_tensor(ourcards, boardcards), _MODE)[0].tolist()
+    if row[15] < 0:
+        raise ValueError("malformed situation (cards must be distinct and in 0..51)")
     return [row[3:6], row[6:9], row[9:12]], row[12:15]
 
 
 def EffectiveHandStrength(ourcards, boardcards):
     """Extension: HS*(1-NPot) + (1-HS)*PPot on the normalised potentials (parity unpinned, see api.ehs_from_counts)."""
     rows = _api.hand_potential_counts(_situation_tensor(ourcards, boardcards), _MODE)
+    if int(rows[0, 15].item()) < 0:
+        raise ValueError("malformed situation (cards must be distinct and in 0..51)")
     return float(_api.ehs_from_counts(rows)[0].item())
 
 

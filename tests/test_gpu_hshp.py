@@ -166,7 +166,7 @@ def test_dropin_handcalculations(hb):
     import HandCalculations as HC
     our_hs, board_hs = torch.tensor([0, 13]), torch.tensor([26, 27, 28, 29, 30])     # testing/ExampleHS.py:4-5
     our_hp, board_hp = torch.tensor([14, 1]), torch.tensor([31, 32, 33])            # testing/ExampleHS.py:11-12
-    HC.set_mode("reference")
+    assert HC.get_mode() == "reference"            # the drop-in's default: what the original module returns
     try:
         hs = HC.HandStrength(our_hs, board_hs)
         assert isinstance(hs, float) and hs == 0.5
@@ -177,13 +177,18 @@ def test_dropin_handcalculations(hb):
         s = HC.HandStrength(torch.tensor([0, 1]), torch.tensor([2, 3, 4]))             # test_HandCalculations.py:49-52
         assert s == 0.9995374653098983 and 0 <= s <= 1
         assert our_hs.tolist() == [0, 13]                                              # inputs are not mutated
-    finally:
+        with pytest.raises(ValueError):
+            HC.HandPotentialCounts(torch.tensor([0, 0]), board_hp)                     # malformed rows raise everywhere
+        with pytest.raises(ValueError):
+            HC.EffectiveHandStrength(torch.tensor([0, 31]), board_hp)
         HC.set_mode("treys")
-    assert HC.HandStrength(our_hs, board_hs) == (0 + 946 / 2) / 990
-    hp = HC.HandPotential(our_hp, board_hp)
-    assert [float(x) for x in hp] == [87.47679138183594, 467.04071044921875]
-    assert HC.HandPotentialCounts(our_hp, board_hp)[1] == [564, 1, 516]
-    assert 0.0 <= HC.EffectiveHandStrength(our_hp, board_hp) <= 1.0
+        assert HC.HandStrength(our_hs, board_hs) == (0 + 946 / 2) / 990
+        hp = HC.HandPotential(our_hp, board_hp)
+        assert [float(x) for x in hp] == [87.47679138183594, 467.04071044921875]
+        assert HC.HandPotentialCounts(our_hp, board_hp)[1] == [564, 1, 516]
+        assert 0.0 <= HC.EffectiveHandStrength(our_hp, board_hp) <= 1.0
+    finally:
+        HC.set_mode("reference")
     assert HC.CalculateHandRankValue(torch.tensor([0, 1]), torch.tensor([10, 11, 12, 13, 14])) == 8
     assert HC.CalculateHandRankValue([0, 1], [10, 11, 12, 13, 14]) == 8                # test_HandCalculations.py:17-18
 

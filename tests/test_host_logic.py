@@ -137,9 +137,10 @@ def test_dropin_surface():
     ev = P2T.Evaluator()
     assert ev.get_rank_class(1) == 1 and ev.get_rank_class(1600) == 5 and ev.get_rank_class(7462) == 9
     assert ev.class_to_string(5) == "Straight"
-    HC.set_mode("reference")
-    assert HC.get_mode() == "reference"
+    assert HC.get_mode() == os.environ.get("HOLDEM_MODE", "reference")    # drop-in default: the reference's own semantics
     HC.set_mode("treys")
+    assert HC.get_mode() == "treys"
+    HC.set_mode("reference")
     with pytest.raises(ValueError):
         HC.set_mode("bogus")
 
