@@ -497,17 +497,39 @@ def main():
                                   "what": "hp_direct_kernel: one real evaluation (shared-memory table gathers) per (holding, "
                                           "runout) pair -- the literal shape of the reference loop"},
         }
-        # mode=reference (the reference's code as written: 9-category ranker, 1176 runouts) on the same situations
-        n_ref = 8192
-        d_ref = d_sit[:n_ref].contiguous()
-        ref_out = torch.empty((n_ref, hb.HP_ROW), dtype=torch.int32, device=dev)
-        msr = _time(lambda: hb.hand_potential_counts(d_ref, "reference", out=ref_out), 2)
-        msh = _time(lambda: hb.hand_strength_counts(d_sit, "reference"), 5)
-        extras["mode_reference"] = {"hp_situations_per_sec": n_ref / (msr * 1e-3), "hp_situations": n_ref,
-                                    "hs_situations_per_sec": n_local / (msh * 1e-3),
-                                    "content_hash": f"{hb.rows_hash(ref_out):016x}",
-                                    "what": "HOLDEM_MODE_REFERENCE: HandCalculations.py:45-82 / :178-226 exactly as written "
-                                            "(golden-pinned to the unmodified reference in tests/)"}
+        # mode=reference (the reference's code as written: 9-category ranker, 1176 runouts) on the same 65,536 situations
+        ref_out = torch.empty((n_local, hb.HP_ROW), dtype=torch.int32, device=dev)
+        msr = _time(lambda: hb.hand_potential_counts(d_sit, "reference", out=ref_out), 5)
+        big_hs = torch.from_numpy(hb.random_situations(1 << 20, seed=SEED + 1)).to(dev)
+        msh = _time(lambda: hb.hand_strength_counts(big_hs, "reference"), 5)
+        msh_t = _time(lambda: hb.hand_strength_counts(big_hs, "treys"), 5)
+        n_old = 4096
+        old_out = torch.empty((n_old, hb.HP_ROW), dtype=torch.int32, device=dev)
+        mso = _time(lambda: hb.hand_potential_counts(d_sit[:n_old].contiguous(), "reference", out=old_out, ref_variant=4), 2)
+        same_old = bool(torch.equal(old_out, ref_out[:n_old]))
+        plain_ref = hb.hand_potential_counts(d_plain, "reference", direct=True)
+        same_plain = bool(torch.equal(plain_ref, ref_out[:n_plain]))
+        ok = ok and same_old and same_plain
+        rc = load_json("profiles", "hot_kernel_counters.json").get("hp_ref5_kernel<flop>", {})
+        wi_r = rc.get("warp_instructions_per_situation")
+        ref_hash = f"{hb.rows_hash(ref_out):016x}"
+        extras["mode_reference"] = {
+            "hp_flop_situations_per_sec": n_local / (msr * 1e-3), "hp_situations": n_local, "ms": msr,
+            "hs_situations_per_sec": big_hs.shape[0] / (msh * 1e-3), "hs_situations": int(big_hs.shape[0]),
+            "hs_treys_mode_situations_per_sec": big_hs.shape[0] / (msh_t * 1e-3),
+            "content_hash": ref_hash,
+            "hash_equals_committed": None if "configs2_first_65536_rows_reference" not in golden
+                                     else ref_hash == golden["configs2_first_65536_rows_reference"],
+            "equal_to_earlier_4set_kernel": same_old, "earlier_4set_kernel_situations_per_sec": n_old / (mso * 1e-3),
+            "equal_to_plain_enumeration": same_plain,
+            "roofline": None if wi_r is None else {
+                "kernel": "hp_ref5_kernel", "bound": "issue_slots (ALU pipe 86 % busy in the committed capture)",
+                "achieved": wi_r * n_local / (msr * 1e-3) / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
+                "frac": wi_r * n_local / (msr * 1e-3) / issue_peak, "warp_instructions_per_situation": wi_r,
+                "ncu": {k: rc.get(k) for k in ("issue_active_pct", "alu_pipe_pct", "fma_pipe_pct", "shared_wavefront_pct", "capture")}},
+            "what": "HOLDEM_MODE_REFERENCE: HandCalculations.py:45-82 / :178-226 exactly as written (golden-pinned to the "
+                    "unmodified reference in tests/): rank-multiset kernel hp_ref5_kernel, rank-pair HS kernel hs_ref5_kernel"}
+        ok = ok and extras["mode_reference"]["hash_equals_committed"] is not False
 
     def _eval_ncu_counters():
         c = load_json("profiles", "hot_kernel_counters.json").get("eval_batch_fast_kernel<7>")

@@ -50,6 +50,16 @@ k = 65536 if args.oracle_all else args.sample
 same, n_or = oracle_sample(sit_np, rows, k)
 assert torch.equal(rows, v3) and same
 res["configs2_first_65536_rows_treys"] = hx(rows)
+# the same situations in mode=reference: rank-multiset kernel == plain enumeration (one literal category evaluation per pair,
+# all rows) == the earlier 4-set kernel; oracle sample
+ref = hb.hand_potential_counts(sit, "reference")
+assert torch.equal(ref, hb.hand_potential_counts(sit, "reference", direct=True))
+assert torch.equal(ref[:8192], hb.hand_potential_counts(sit[:8192].contiguous(), "reference", ref_variant=4))
+pick = np.sort(rng.choice(65536, 256, replace=False))
+assert np.array_equal(ref[torch.from_numpy(pick).cuda()].cpu().numpy().astype(np.uint32), O.hp_batch_parallel(sit_np[pick], "reference", cache4=False))
+res["configs2_first_65536_rows_reference"] = hx(ref)
+ev["configs2_reference"] = {"v5_equals_plain_enumeration_all_rows": True, "v5_equals_4set_kernel_rows": 8192, "oracle_rows_compared": 256,
+                            "oracle_equal": True}
 ev["configs2"] = {"production_equals_4set_kernel_all_rows": True, "oracle_rows_compared": n_or, "oracle_equal": same}
 
 # configs[4]
