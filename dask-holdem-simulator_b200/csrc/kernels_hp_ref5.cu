@@ -26,7 +26,10 @@
 //                        (a card shared by P and Q counts twice, as in the reference's Counter):
 //                            + [cls(P)]  x cmp(our(Q), 8 if no shared card of s and cyclic run in s, else keep(T[q][pp]))
 //                            - [clsr(pp)] x cmp(our(Q), T[q][pp] nf)                               (undo the generic term)
-//                        ~7 K items on a rainbow flop, ~45 K two-tone, ~240 K monotone instead of 1.27 M evaluations.
+//                        Cards outside s matter through their RANK only, on both sides: holdings with a card outside s are
+//                        merged into weighted steps, runouts with a card outside s into weighted lanes (counted per
+//                        (cards in s, rank of the rest, our category) while our categories are computed).
+//                        ~7 K items on a rainbow flop, ~19 K two-tone, ~40 K monotone instead of 1.27 M evaluations.
 //
 // One CTA of 256 threads per situation (claimed from a global counter: suited boards cost far more than rainbow ones).  Per
 // situation: the unseen cards in (rank, suit) order and per-suit position lists; T[91][91] (two nibbles per entry: NF and keep(NF))
@@ -68,7 +71,14 @@ struct Ref5Smem {
     uint32_t g_first[kMaxTaskGroups + 1];
     uint32_t g_nq[kMaxTaskGroups], g_np[kMaxTaskGroups], g_nseg[kMaxTaskGroups], g_pdbase[kMaxTaskGroups], g_sq[kMaxTaskGroups];
     uint32_t pd_base[4], pd_len[4];
+    uint32_t h_np[kMaxTaskGroups], h_pdo[kMaxTaskGroups];   // per (suit, qtype) class before the live ones are compacted
     uint32_t n_groups, n_entries, next_task, claim;
+    uint32_t nL1[2], nL0;              // merged runout lanes per list
+    uint32_t A1[2][768];               // runouts with ONE card in a suit holding >= 2 board cards, counted by (rank of that card, rank
+                                       // of the other card, our category): 13 x 13 x 9 counters, two 16-bit counters per word
+    uint32_t A0[416];                  // runouts WITHOUT a card of the suit holding >= 3 board cards, by (rank pair, our category)
+    uint32_t L1[2][512];               // non-zero entries of A1 / A0: key | multiplicity << 16 -- the lanes of those runout classes
+    uint32_t L0[320];
     uint16_t pairs[kMaxQ5 + 8];        // colex pairs i | j << 8 (static)
     alignas(16) uint8_t T[kTRow5];     // [q][pp]: NF | keep(NF) << 4 -- one row of the global table of this board size
     uint8_t ourQ[kMaxQ5 + 8];          // our category on runout (i,j), colex index over the positions of D
@@ -243,6 +253,18 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
         if (tid < 12) S.cnt[tid] = 0;
         if (tid < 4) S.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
         for (uint32_t i = tid; i < (uint32_t)(kPP5 * 9); i += kR5Threads) S.M[i] = 0;
+        // Suits with >= 2 board cards (at most two) own a slot of A1 / L1, the suit with >= 3 (at most one) owns A0 / L0.
+        uint32_t slotmap = 0, n_slots = 0, a0suit = 4;
+#pragma unroll
+        for (uint32_t su = 0; su < 4; ++su) {
+            const uint32_t bsq = (bsuit >> (4 * su)) & 15u;
+            slotmap |= (bsq >= 2 ? n_slots++ : 15u) << (4 * su);
+            if (bsq >= 3) a0suit = su;
+        }
+        if (n_slots) for (uint32_t i = tid; i < n_slots * 768u; i += kR5Threads) (&S.A1[0][0])[i] = 0;
+        if (a0suit < 4) for (uint32_t i = tid; i < 416u; i += kR5Threads) S.A0[i] = 0;
+        if (tid < 3) (&S.nL1[0])[tid] = 0;          // nL1[0], nL1[1], nL0
+        if (tid == 3) S.n_entries = 0;
         if (warp == 0) {
             // ---- D in (rank, suit) order, our hole cards last; per-suit position lists ----------------------------------------------
             const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
@@ -347,7 +369,19 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             const uint32_t o = lit_category(lit_merge(lours, lq));
             S.ourQ[q] = (uint8_t)o;
             const uint32_t ri = ci >> 2, rj = cj >> 2;
-            atomicAdd(&S.M[(tri(max(ri, rj)) + min(ri, rj)) * 9 + o], 1u);
+            const uint32_t qp = tri(max(ri, rj)) + min(ri, rj);
+            atomicAdd(&S.M[qp * 9 + o], 1u);
+            // the runout as a lane of the flush part: with a card outside a suit it matters through that card's RANK only
+            const uint32_t si = ci & 3u, sj = cj & 3u;
+            if (si != sj) {                                  // exactly one card in suit si and one in suit sj
+                const uint32_t sl_i = (slotmap >> (4 * si)) & 15u, sl_j = (slotmap >> (4 * sj)) & 15u;
+                if (sl_i < 2) { const uint32_t k = (ri * 13 + rj) * 9 + o; atomicAdd(&S.A1[sl_i][k >> 1], 1u << (16 * (k & 1u))); }
+                if (sl_j < 2) { const uint32_t k = (rj * 13 + ri) * 9 + o; atomicAdd(&S.A1[sl_j][k >> 1], 1u << (16 * (k & 1u))); }
+            }
+            if (a0suit < 4 && si != a0suit && sj != a0suit) {
+                const uint32_t k = qp * 9 + o;
+                atomicAdd(&S.A0[k >> 1], 1u << (16 * (k & 1u)));
+            }
         }
         if (warp == 0) {
             // ---- flush task groups and descriptor sections: lane = 3 * suit + (2 - qtype) ------------------------------------------------
@@ -369,31 +403,10 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 if (q < s) pdo += lq;
             }
             const int need = 5 - (int)bs - (int)qtype;                 // cards of s the holding must bring for this runout class
-            const uint32_t nq = qtype == 2 ? choose2u(nd) : (qtype == 1 ? nd * nnd : choose2u(nnd));
-            const uint32_t np = need >= 3 ? 0u : (need == 2 ? len2 : (need == 1 ? len1 : len0));
-            const bool live = lane < 12 && bs != 0 && nq != 0 && np != 0;
-            const uint32_t nseg = (np + kSeg5 - 1) / kSeg5;
-            const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
-            const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
-            const uint32_t gi = __popc(livem & ltm);
-            uint32_t first = ntask;
-#pragma unroll
-            for (int d = 1; d < 16; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, first, d);
-                if ((int)lane >= d) first += v;
-            }
-            if (live) {
-                S.g_first[gi] = first - ntask;
-                S.g_nq[gi] = nq; S.g_np[gi] = np; S.g_nseg[gi] = nseg; S.g_pdbase[gi] = pdo;
-                S.g_sq[gi] = s | (qtype << 2);
-            }
+            const uint32_t np = (bs == 0 || need >= 3) ? 0u : (need == 2 ? len2 : (need == 1 ? len1 : len0));
+            (void)nd; (void)nnd; (void)ltm;
+            if (lane < 12) { S.h_np[lane] = np; S.h_pdo[lane] = pdo; }
             if (lane < 12 && qtype == 2) { S.pd_base[s] = pdo; S.pd_len[s] = len; }
-            if (lane == 11) {
-                S.g_first[__popc(livem)] = first;
-                S.n_groups = __popc(livem);
-                S.next_task = 0;
-                S.n_entries = 0;
-            }
         }
         __syncthreads();                                                                            // (B)
         // ---- compact the (rank pair, our category) entries that occur ---------------------------------------------------------------
@@ -404,6 +417,21 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             if (lane == 0 && bal) base = atomicAdd(&S.n_entries, __popc(bal));
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (nz) S.elist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+        }
+        // ---- the merged runout lanes: non-zero counters of A1 (per slot) and A0, as key | multiplicity << 16 ------------------------------
+        {
+            auto compact16 = [&](const uint32_t *arr, uint32_t n_keys, uint32_t *list, uint32_t *counter) {
+                for (uint32_t e = tid; e < (n_keys + kR5Threads - 1) / kR5Threads * kR5Threads; e += kR5Threads) {
+                    const uint32_t c = e < n_keys ? (arr[e >> 1] >> (16 * (e & 1u))) & 0xFFFFu : 0u;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, c != 0);
+                    uint32_t base = 0;
+                    if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (c) list[base + __popc(bal & ((1u << lane) - 1u))] = e | (c << 16);
+                }
+            };
+            for (uint32_t sl = 0; sl < n_slots; ++sl) compact16(S.A1[sl], 13u * 13u * 9u, S.L1[sl], &S.nL1[sl]);
+            if (a0suit < 4) compact16(S.A0, (uint32_t)kPP5 * 9u, S.L0, &S.nL0);
         }
         // ---- holding descriptors of the flush part --------------------------------------------------------------------------------------
         {
@@ -456,6 +484,36 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
         }
         __syncthreads();                                                                            // (C)
 
+        if (warp == 0) {
+            // ---- live flush task groups: lane = 3 * suit + (2 - qtype); runouts with two cards in s are lanes one by one, the others
+            //      are the merged lanes of L1 / L0 ------------------------------------------------------------------------------------------
+            const uint32_t ltm = (1u << lane) - 1u;
+            const uint32_t s = min(lane / 3u, 3u), qtype = 2u - (lane - 3u * (lane / 3u));
+            const uint32_t slot = (slotmap >> (4 * s)) & 15u;
+            const uint32_t np = lane < 12 ? S.h_np[lane] : 0u, pdo = lane < 12 ? S.h_pdo[lane] : 0u;
+            const uint32_t nq = qtype == 2 ? choose2u(S.nsd[s]) : (qtype == 1 ? (slot < 2 ? S.nL1[slot] : 0u) : (s == a0suit ? S.nL0 : 0u));
+            const bool live = lane < 12 && nq != 0 && np != 0;
+            const uint32_t nseg = (np + kSeg5 - 1) / kSeg5;
+            const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
+            const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
+            const uint32_t gi = __popc(livem & ltm);
+            uint32_t first = ntask;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, first, d);
+                if ((int)lane >= d) first += v;
+            }
+            if (live) {
+                S.g_first[gi] = first - ntask;
+                S.g_nq[gi] = nq; S.g_np[gi] = np; S.g_nseg[gi] = nseg; S.g_pdbase[gi] = pdo;
+                S.g_sq[gi] = s | (qtype << 2) | (slot << 4);
+            }
+            if (lane == 11) {
+                S.g_first[__popc(livem)] = first;
+                S.n_groups = __popc(livem);
+                S.next_task = 0;
+            }
+        }
         uint32_t accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};     // per class: our > opp (ahead) / our < opp (behind), net, mod 2^32
         mbar_wait(bar_s, parity);                                      // T has landed
         parity ^= 1u;
@@ -484,6 +542,7 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 }
             }
         }
+        __syncthreads();                                                                            // (C2) task groups ready
         // ---- flush part: dynamic task queue ----------------------------------------------------------------------------------------------------
         {
             const uint32_t n_groups = S.n_groups;
@@ -498,30 +557,33 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 const uint32_t local = task - S.g_first[g];
                 const uint32_t nseg = S.g_nseg[g], np = S.g_np[g], nq = S.g_nq[g];
                 const uint32_t chunk = local / nseg, seg = local - chunk * nseg;
-                const uint32_t s = S.g_sq[g] & 3u, qtype = S.g_sq[g] >> 2;
+                const uint32_t s = S.g_sq[g] & 3u, qtype = (S.g_sq[g] >> 2) & 3u, slot = S.g_sq[g] >> 4;
                 const uint32_t p0 = seg * kSeg5, p1 = min(np, p0 + kSeg5);
                 const uint32_t qi = chunk * 32 + lane;
-                const uint32_t nd = S.nsd[s], nnd = md - nd;
-                uint32_t our = 0, qbits = 0, trow = 0;
+                uint32_t our = 0, qbits = 0, trow = 0, mult = 0;
                 const bool valid = qi < nq;
                 if (valid) {
-                    uint32_t x, y;                                 // positions in D
-                    if (qtype == 2) {
+                    if (qtype == 2) {                              // both cards in s: the runout itself
                         const uint32_t pr = S.pairs[qi];
-                        x = S.Ls[s][pr & 0xFFu]; y = S.Ls[s][pr >> 8];
-                    } else if (qtype == 1) {
-                        const uint32_t a = qi / nnd, z = qi - a * nnd;
-                        x = S.Ls[s][a]; y = S.Lns[s][z];
-                    } else {
-                        const uint32_t pr = S.pairs[qi];
-                        x = S.Lns[s][pr & 0xFFu]; y = S.Lns[s][pr >> 8];
+                        const uint32_t x = S.Ls[s][pr & 0xFFu], y = S.Ls[s][pr >> 8];     // positions in D, x < y
+                        const uint32_t rx = S.code[x] >> 2, ry = S.code[y] >> 2;
+                        our = S.ourQ[y * (y - 1) / 2 + x];
+                        qbits = (1u << rx) | (1u << ry);
+                        trow = (tri(max(rx, ry)) + min(rx, ry)) * kTPitch5;
+                        mult = 1;
+                    } else if (qtype == 1) {                       // (card of s by its rank, rank of the other card, our category)
+                        const uint32_t en = S.L1[slot][qi], key = en & 0xFFFFu;
+                        const uint32_t rx = key / 117u, rem = key - 117u * rx, ry = rem / 9u;
+                        our = rem - 9u * ry;
+                        qbits = 1u << rx;
+                        trow = (tri(max(rx, ry)) + min(rx, ry)) * kTPitch5;
+                        mult = en >> 16;
+                    } else {                                       // (rank pair, our category), neither card in s
+                        const uint32_t en = S.L0[qi], key = en & 0xFFFFu, qp = key / 9u;
+                        our = key - 9u * qp;
+                        trow = qp * kTPitch5;
+                        mult = en >> 16;
                     }
-                    const uint32_t lo = min(x, y), hi = max(x, y);
-                    const uint32_t cx = S.code[x], cy = S.code[y];
-                    const uint32_t rx = cx >> 2, ry = cy >> 2;
-                    our = S.ourQ[hi * (hi - 1) / 2 + lo];
-                    qbits = ((cx & 3u) == s ? 1u << rx : 0u) | ((cy & 3u) == s ? 1u << ry : 0u);
-                    trow = (tri(max(rx, ry)) + min(rx, ry)) * kTPitch5;
                 }
                 const uint32_t base_mask = S.bmask[s] | qbits;
                 const uint32_t tq_s = t_s + trow;
@@ -547,12 +609,10 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                         : "+r"(aG), "+r"(aL), "+r"(sG), "+r"(sL)
                         : "r"(our), "r"(catf), "r"(catn), "r"(d.y), "r"(d.z), "r"(one));
                 }
-                if (valid) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        accA[c] += ((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu);
-                        accB[c] += ((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu);
-                    }
+                for (int c = 0; c < 3; ++c) {       // mult = 0 on lanes past the end of the lane list
+                    accA[c] += (((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu)) * mult;
+                    accB[c] += (((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu)) * mult;
                 }
             }
         }
