@@ -84,6 +84,7 @@ struct Ref5Smem {
     uint8_t ourQ[kMaxQ5 + 8];          // our category on runout (i,j), colex index over the positions of D
     uint8_t clsP[kMaxP5 + 7];          // class of holding (i,j), colex index over the positions of U
     uint8_t clsR[96];                  // per rank pair: class from ranks alone
+    uint8_t nf5[96];                   // per rank pair: NF(board + pair) | keep(NF) << 4
     uint8_t ppxy[96];                  // rank pair -> x | y << 4 (static)
     uint8_t code[56];                  // D = deck \ board: positions 0..m-1 the unseen cards (rank*4+suit ascending), m, m+1 our hole cards
     uint8_t Ls[4][20];                 // positions of D with suit s: unseen cards first, then our hole cards of that suit
@@ -250,6 +251,10 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
         const uint32_t n_p = m * (m - 1) / 2, n_q = md * (md - 1) / 2;
         const LitHand lours = lit_merge(lb, lit_merge(one_card5(cb[0]), one_card5(cb[1])));
         const uint32_t ours_now = lit_category(lours);                                           // :190
+        const uint32_t hr0 = card_rank(cb[0]), hr1 = card_rank(cb[1]);
+        const uint32_t hole_pp = tri(max(hr0, hr1)) + min(hr0, hr1);
+        const uint32_t hsuit = bsuit + (1u << (4 * card_suit(cb[0]))) + (1u << (4 * card_suit(cb[1])));   // hole + board per suit
+        const uint32_t h5 = (hsuit + 0x3333u) & 0x8888u;                                         // we already hold five of a suit
         if (tid < 12) S.cnt[tid] = 0;
         if (tid < 4) S.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu;
         for (uint32_t i = tid; i < (uint32_t)(kPP5 * 9); i += kR5Threads) S.M[i] = 0;
@@ -323,35 +328,56 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             mbar_expect_tx(bar_s, kTRow5);
             bulk_g2s(t_s, T.ref_t[nb - 3] + (size_t)bi * kTRow5, kTRow5, bar_s);
         }
-        __syncthreads();                                                                            // (A) lists, u[] ready
-        // ---- per rank pair: class from ranks alone and the number of holdings ---------------------------------------------------------
-        if (tid < 96) {
-            uint32_t clsr = 3;
-            unsigned long long wt = 0;
-            if (tid < (uint32_t)kPP5) {
-                const uint32_t xy = S.ppxy[tid], x = xy & 15u, y = xy >> 4;
+        if (tid >= 64 && tid < 160) {
+            // ---- per rank pair: the category board + pair takes from its ranks alone, and its class against ours -----------------------------
+            const uint32_t pp = tid - 64;
+            uint32_t clsr = 3, e8 = 0;
+            if (pp < (uint32_t)kPP5) {
+                const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
                 LitHand h = lb;
                 h.sc = 0; h.cards = 0; h.dup = 0;
                 h.rc += (1ull << (4 * x)) + (1ull << (4 * y));
                 h.rmask |= (1u << x) | (1u << y);
-                const uint32_t nf5 = lit_category(h);
-                clsr = ours_now > nf5 ? 0u : (ours_now == nf5 ? 1u : 2u);
+                const uint32_t nf = lit_category(h);
+                clsr = ours_now > nf ? 0u : (ours_now == nf ? 1u : 2u);
+                e8 = nf | (((nf == 4u || nf >= 6u) ? nf : 5u) << 4);
+            }
+            S.clsR[pp] = (uint8_t)clsr;
+            S.nf5[pp] = (uint8_t)e8;
+        }
+        __syncthreads();                                                                            // (A) lists, u[], clsR, nf5 ready
+        if (tid < 96) {                 // holdings per rank pair, packed by class
+            unsigned long long wt = 0;
+            if (tid < (uint32_t)kPP5) {
+                const uint32_t xy = S.ppxy[tid], x = xy & 15u, y = xy >> 4;
                 const uint32_t ux = S.u[x], uy = S.u[y];
                 const uint32_t cntp = x != y ? ux * uy : (ux ? ux * (ux - 1) / 2 : 0u);
-                wt = (unsigned long long)cntp << (20 * clsr);
+                wt = (unsigned long long)cntp << (20 * S.clsR[tid]);
             }
-            S.clsR[tid] = (uint8_t)clsr;
             S.Wt[tid] = wt;
         }
-        // ---- class of every holding (:194-203), multiset-exact ---------------------------------------------------------------------
+        // ---- class of every holding (:194-203): the class of its rank pair unless board + holding hold five of a suit -------------------
         {
             uint32_t c0 = 0, c1 = 0, c2 = 0;
             for (uint32_t p = tid; p < n_p; p += kR5Threads) {
                 const uint32_t pr = S.pairs[p];
-                LitHand lp = one_card5(path_of_code4(S.code[pr & 0xFFu]));
-                lit_add_card(lp, path_of_code4(S.code[pr >> 8]));
-                const uint32_t opp = lit_category(lit_merge(lb, lp));
-                const uint32_t cls = ours_now > opp ? 0u : (ours_now == opp ? 1u : 2u);
+                const uint32_t ca = S.code[pr & 0xFFu], cb2 = S.code[pr >> 8];
+                const uint32_t ra = ca >> 2, rb = cb2 >> 2, sa = ca & 3u, sb = cb2 & 3u;
+                const uint32_t pp = tri(max(ra, rb)) + min(ra, rb);
+                uint32_t cls = S.clsR[pp];
+                // suit counts of board + holding (distinct cards): a flush needs 5 - (board cards of the suit) cards of it in the holding
+                const uint32_t na = ((bsuit >> (4 * sa)) & 15u) + 1u + (uint32_t)(sb == sa), nbs = ((bsuit >> (4 * sb)) & 15u) + 1u;
+                const uint32_t f5 = (bsuit + 0x3333u) & 0x8888u;                    // a suit with five board cards
+                uint32_t fs = 4;
+                if (na >= 5) fs = sa;
+                else if (nbs >= 5) fs = sb;
+                else if (f5) fs = (uint32_t)(__ffs(f5) - 1) >> 2;
+                if (fs < 4) {
+                    const uint32_t mask = S.bmask[fs] | (sa == fs ? 1u << ra : 0u) | (sb == fs ? 1u << rb : 0u);
+                    const uint32_t e8 = S.nf5[pp];
+                    const uint32_t opp = ((S.cyc[mask >> 5] >> (mask & 31u)) & 1u) ? 8u : (e8 >> 4);
+                    cls = ours_now > opp ? 0u : (ours_now == opp ? 1u : 2u);
+                }
                 S.clsP[p] = (uint8_t)cls;
                 c0 += cls == 0; c1 += cls == 1; c2 += cls == 2;
             }
@@ -360,19 +386,32 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
             if (lane == 0) { atomicAdd(&S.cnt[6], c0); atomicAdd(&S.cnt[7], c1); atomicAdd(&S.cnt[8], c2); }
         }
+        mbar_wait(bar_s, parity);                                      // T has landed
+        parity ^= 1u;
         // ---- our category on every runout (:207-210; a runout may repeat our hole cards) ---------------------------------------------
         for (uint32_t q = tid; q < n_q; q += kR5Threads) {
             const uint32_t pr = S.pairs[q];
-            const uint32_t ci = S.code[pr & 0xFFu], cj = S.code[pr >> 8];
-            LitHand lq = one_card5(path_of_code4(ci));
-            lit_add_card(lq, path_of_code4(cj));
-            const uint32_t o = lit_category(lit_merge(lours, lq));
-            S.ourQ[q] = (uint8_t)o;
-            const uint32_t ri = ci >> 2, rj = cj >> 2;
+            const uint32_t pi = pr & 0xFFu, pj = pr >> 8;
+            const uint32_t ci = S.code[pi], cj = S.code[pj];
+            const uint32_t ri = ci >> 2, rj = cj >> 2, si = ci & 3u, sj = cj & 3u;
             const uint32_t qp = tri(max(ri, rj)) + min(ri, rj);
+            // hole + board + runout: the category of its rank counts is T[rank pair of our hole cards][rank pair of the runout];
+            // a flush needs five of a suit counted WITH repeats (a runout card that is one of our hole cards counts twice, :56)
+            const uint32_t e8 = S.T[hole_pp * kTPitch5 + qp];
+            uint32_t o = e8 & 15u;
+            const uint32_t ni = ((hsuit >> (4 * si)) & 15u) + 1u + (uint32_t)(sj == si), nj = ((hsuit >> (4 * sj)) & 15u) + 1u;
+            uint32_t fs = 4;
+            if (ni >= 5) fs = si;
+            else if (nj >= 5) fs = sj;
+            else if (h5) fs = (uint32_t)(__ffs(h5) - 1) >> 2;
+            if (fs < 4) {
+                const uint32_t mask = ((uint32_t)(known >> (13 * fs)) & 0x1FFFu) | (si == fs ? 1u << ri : 0u) | (sj == fs ? 1u << rj : 0u);
+                const bool repeated = (si == fs && pi >= m) || (sj == fs && pj >= m);     // one of our hole cards again: no straight flush
+                o = (!repeated && ((S.cyc[mask >> 5] >> (mask & 31u)) & 1u)) ? 8u : (e8 >> 4);
+            }
+            S.ourQ[q] = (uint8_t)o;
             atomicAdd(&S.M[qp * 9 + o], 1u);
             // the runout as a lane of the flush part: with a card outside a suit it matters through that card's RANK only
-            const uint32_t si = ci & 3u, sj = cj & 3u;
             if (si != sj) {                                  // exactly one card in suit si and one in suit sj
                 const uint32_t sl_i = (slotmap >> (4 * si)) & 15u, sl_j = (slotmap >> (4 * sj)) & 15u;
                 if (sl_i < 2) { const uint32_t k = (ri * 13 + rj) * 9 + o; atomicAdd(&S.A1[sl_i][k >> 1], 1u << (16 * (k & 1u))); }
@@ -515,8 +554,6 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             }
         }
         uint32_t accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};     // per class: our > opp (ahead) / our < opp (behind), net, mod 2^32
-        mbar_wait(bar_s, parity);                                      // T has landed
-        parity ^= 1u;
         // ---- generic part: eight lanes share one (rank pair, our category) entry, each takes every eighth rank pair -------------------------
         {
             const uint32_t n_entries = S.n_entries;
