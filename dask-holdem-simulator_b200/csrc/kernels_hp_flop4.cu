@@ -53,6 +53,9 @@ namespace {
 // Group shape (threads per situation group, groups per CTA).  Measured on B200, 65,536 random flops: 6 x 160 -> 39.0 M
 // situations/s, 7 x 128 (one more situation in flight per SM) -> 38.8 M: the kernel is bound by instruction issue and
 // shared-memory wavefronts inside the task phase, not by the latency of the per-situation set-up phases.
+#ifndef HOLDEM_F4_UNROLL
+#define HOLDEM_F4_UNROLL 2
+#endif
 #ifndef HOLDEM_F4_GT
 #define HOLDEM_F4_GT 160
 #define HOLDEM_F4_G 6
@@ -524,7 +527,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // steps [0, nboth + n_s) have an add part (holdings with both cards in s, or one card a in s); the ones behind them
                 // are rank-level undo steps: no suited-table gather, half the compares
                 const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
-#pragma unroll 2
+#pragma unroll HOLDEM_F4_UNROLL
                 for (uint32_t t = p0; t < split; ++t, ++pd) {
                     const uint4 d = *pd;
                     // fold() is XOR-linear and the step's cards of s are disjoint from board + runout when the step is valid

@@ -49,7 +49,6 @@ namespace {
 using namespace ms;
 
 constexpr int kR5Threads = 256;
-constexpr int kR5Warps = kR5Threads / 32;
 constexpr int kTPitch5 = 92;          // bytes per row of T
 constexpr int kPP5 = 91;
 constexpr int kMaxQ5 = 1176;          // C(49,2)
@@ -61,7 +60,7 @@ constexpr int kMaxTaskGroups = 12;    // (suit, cards of Q in suit) classes
 
 struct Ref5Smem {
     uint4 PD[kPDCap5];                 // x = rank bits of the holding's cards in s, y = 1 << 10 cls(P), z = 1 << 10 clsr(pp), w = pp
-    unsigned long long Wt[96];         // per rank pair: N(pp) << 20 clsr(pp)
+    uint32_t Wt32[96];                 // per rank pair: N(pp) << 10 clsr(pp)  (N <= 16)
     unsigned long long bar;            // mbarrier of the T row copy
     uint32_t M[kPP5 * 9 + 1];          // runouts by (rank pair, our category)
     uint16_t elist[kPP5 * 9 + 1];      // nonzero entries of M, compacted
@@ -99,12 +98,6 @@ __device__ __forceinline__ LitHand one_card5(uint32_t c) {
     LitHand h = {0, 0, 0, 0, 0};
     lit_add_card(h, c);
     return h;
-}
-
-__device__ __forceinline__ void cmp_add64(unsigned long long &gt, unsigned long long &lt, uint32_t a, uint32_t b,
-                                          unsigned long long w) {
-    if (a > b) gt += w;
-    if (a < b) lt += w;
 }
 
 // index of a sorted rank multiset r0 <= r1 <= ... in the combinatorial number system: sum of C(r_i + i, i + 1)
@@ -347,14 +340,14 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
         }
         __syncthreads();                                                                            // (A) lists, u[], clsR, nf5 ready
         if (tid < 96) {                 // holdings per rank pair, packed by class
-            unsigned long long wt = 0;
+            uint32_t wt = 0;
             if (tid < (uint32_t)kPP5) {
                 const uint32_t xy = S.ppxy[tid], x = xy & 15u, y = xy >> 4;
                 const uint32_t ux = S.u[x], uy = S.u[y];
                 const uint32_t cntp = x != y ? ux * uy : (ux ? ux * (ux - 1) / 2 : 0u);
-                wt = (unsigned long long)cntp << (20 * S.clsR[tid]);
+                wt = cntp << (10 * S.clsR[tid]);
             }
-            S.Wt[tid] = wt;
+            S.Wt32[tid] = wt;
         }
         // ---- class of every holding (:194-203): the class of its rank pair unless board + holding hold five of a suit -------------------
         {
@@ -554,7 +547,8 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             }
         }
         uint32_t accA[3] = {0, 0, 0}, accB[3] = {0, 0, 0};     // per class: our > opp (ahead) / our < opp (behind), net, mod 2^32
-        // ---- generic part: eight lanes share one (rank pair, our category) entry, each takes every eighth rank pair -------------------------
+        // ---- generic part: eight lanes share one (rank pair, our category) entry, each takes every eighth rank pair (<= 12 of them:
+        //      a packed 10-bit field holds at most 12 x 16 holdings); the fields are spread to 16 bits before the lanes are summed ----------
         {
             const uint32_t n_entries = S.n_entries;
             const uint32_t sub = lane & 7u;
@@ -562,20 +556,23 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 const bool act = k0 < n_entries;
                 const uint32_t e = act ? (uint32_t)S.elist[k0] : 0u, q = e / 9u, o = e - 9u * q;
                 const uint8_t *row = S.T + q * kTPitch5;
-                unsigned long long gt = 0, lt = 0;
-                for (uint32_t pp = sub; pp < (uint32_t)kPP5; pp += 8) cmp_add64(gt, lt, o, (uint32_t)row[pp] & 15u, S.Wt[pp]);
+                uint32_t gt = 0, lt = 0;
+                for (uint32_t pp = sub; pp < (uint32_t)kPP5; pp += 8) {
+                    const uint32_t nf = (uint32_t)row[pp] & 15u, w = S.Wt32[pp];
+                    if (o > nf) gt += w;
+                    if (o < nf) lt += w;
+                }
+                uint32_t g01 = (gt & 0x3FFu) | (((gt >> 10) & 0x3FFu) << 16), g2 = gt >> 20;
+                uint32_t l01 = (lt & 0x3FFu) | (((lt >> 10) & 0x3FFu) << 16), l2 = lt >> 20;
 #pragma unroll
                 for (int d = 1; d < 8; d <<= 1) {
-                    gt += __shfl_xor_sync(0xFFFFFFFFu, gt, d);
-                    lt += __shfl_xor_sync(0xFFFFFFFFu, lt, d);
+                    g01 += __shfl_xor_sync(0xFFFFFFFFu, g01, d); g2 += __shfl_xor_sync(0xFFFFFFFFu, g2, d);
+                    l01 += __shfl_xor_sync(0xFFFFFFFFu, l01, d); l2 += __shfl_xor_sync(0xFFFFFFFFu, l2, d);
                 }
                 if (act && sub == 0) {
                     const uint32_t mult = S.M[e];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        accA[c] += (uint32_t)((gt >> (20 * c)) & 0xFFFFFu) * mult;
-                        accB[c] += (uint32_t)((lt >> (20 * c)) & 0xFFFFFu) * mult;
-                    }
+                    accA[0] += (g01 & 0xFFFFu) * mult; accA[1] += (g01 >> 16) * mult; accA[2] += g2 * mult;
+                    accB[0] += (l01 & 0xFFFFu) * mult; accB[1] += (l01 >> 16) * mult; accB[2] += l2 * mult;
                 }
             }
         }
