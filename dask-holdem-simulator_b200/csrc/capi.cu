@@ -423,7 +423,7 @@ int holdem_hs_batch_host(const uint8_t *h_sit, int64_t n, int mode, uint32_t *h_
 // Which implementation serves each street of a Treys-mode HP call.  Production = {4, 4, 0}; the others are reached through the
 // explicit *_variant entry points only (A/B measurements and independent cross-checks).
 struct HpImpl {
-    int flop = 4;      // 4 rank-multiset kernel, 3 / 2 the 4-set kernels
+    int flop = 4;      // 4 rank-multiset kernel, 5 the same without the closed-form add path, 3 / 2 the 4-set kernels
     int turn = 4;      // 4 rank-multiset kernel, 3 the 3-set walk
     int river = 0;     // 0 rank-pair HS kernel in its HP-row form, 1 plain enumeration
     int ref = 5;       // HOLDEM_MODE_REFERENCE: 5 rank-multiset kernel, 4 the earlier 4-set walk + arithmetic irregular runouts
@@ -460,7 +460,7 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     const bool fused = !old_flop && !old_turn;          // the production kernels store their rows into the peers themselves
     const PeerOut none{};
     e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl.flop, st)
-                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st);
+                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st, impl.flop != 5);
     if (e != cudaSuccess) return e;
     e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
                  : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st);
@@ -518,10 +518,11 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (variant < 2 || variant > 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
+    if (variant < 2 || variant > 5) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
     FlagSlot slot;
     CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
-    if (variant == 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream));
+    if (variant >= 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream,
+                                                       variant == 4));
     else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, slot.ptr, variant, (cudaStream_t)stream));
     CUDA_TRY(slot.release());
     return HOLDEM_OK;
@@ -608,8 +609,8 @@ int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, i
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (flop_variant < 2 || flop_variant > 4 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
-        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..4, turn 3..4, river 0..1)");
+    if (flop_variant < 2 || flop_variant > 5 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
+        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..5, turn 3..4, river 0..1)");
     HpImpl impl;
     impl.flop = flop_variant; impl.turn = turn_variant; impl.river = river_variant;
     CUDA_TRY(hp_dispatch(*S, d_sit, n, HOLDEM_MODE_TREYS, d_out, (cudaStream_t)stream, PeerOut{}, nullptr, impl));

@@ -60,6 +60,7 @@ namespace {
 #define HOLDEM_F4_GT 160
 #define HOLDEM_F4_G 6
 #endif
+constexpr int kF4Unroll = HOLDEM_F4_UNROLL;      // step unroll of the flush part's add loop
 constexpr int kGroupThreads = HOLDEM_F4_GT;
 constexpr int kGroups = HOLDEM_F4_G;
 constexpr int kThreads4 = kGroupThreads * kGroups;
@@ -95,6 +96,9 @@ struct Flop4Group {                    // one situation in flight
     uint32_t pd_base[4], pd_len[4];    // PD section per suit
     uint32_t smask[4];                 // rank mask of the unseen cards per suit
     uint32_t hist_none[4];             // holdings without a card of the board's suit, by flop class (monotone boards)
+    uint32_t Wc0[4][16];               // per suit and card a of it: class histogram (10-bit fields) of the holdings {a, b}, b in s
+    uint32_t Hs[4][16];                // ... of the holdings {a, c}, c outside s (the add weight of the "card a in s" step)
+    uint32_t Wt0[4], Ht[4];            // the sums of Wc0 / 2 and of Hs over the suit's cards
     uint32_t HA[16 * 13];              // monotone boards: class histogram (10-bit fields) of {a, c} over the c of one rank outside s
     uint32_t upack[2];                 // unseen cards per rank, 3 bits each (64-bit)
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
@@ -120,7 +124,7 @@ __device__ __forceinline__ void group_sync(uint32_t gid) { group_sync_n<kGroupTh
 
 }  // namespace
 
-template <bool kProf>
+template <bool kProf, bool kFastAdd>
 __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
                         int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers,
@@ -209,7 +213,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             continue;
         }
         if (tid < 12) G.cnt[tid] = 0;
-        if (tid < 4) { G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu; G.hist_none[tid] = 0; }
+        if (tid < 4) { G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu; G.hist_none[tid] = 0; G.Wt0[tid] = 0; G.Ht[tid] = 0; }
+        if (tid >= 32 && tid < 96) (&G.Wc0[0][0])[tid - 32] = 0;
         if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
         if (warp == 0) {
             // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
@@ -414,12 +419,17 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
                     }
                     G.PD[e] = make_uint4((bits << 17) | (2u * fold(bits)), 1u << (10 * cls), G.clsw[pp], pp * (kTPitch * 2));
+                    atomicAdd(&G.Wc0[s][pr & 0xFFu], 1u << (10 * cls));
+                    atomicAdd(&G.Wc0[s][pr >> 8], 1u << (10 * cls));
+                    atomicAdd(&G.Wt0[s], 1u << (10 * cls));
                 } else if (t < nboth + nsu) {                      // one card a in s, any card c outside s: the flop class of {a, c}
                     const uint32_t ra = G.code[G.Ls[s][t - nboth]] >> 2;     // depends on ranks alone (four of the suit at most)
                     uint32_t hist = 0;
                     for (uint32_t y = 0; y < 13; ++y)
                         hist += (G.u[y] - ((sm >> y) & 1u)) * G.clsw[tri(max(ra, y)) + min(ra, y)];
                     G.PD[e] = make_uint4(((2u << ra) << 16) | (2u * fold(1u << ra)), hist, 0u, 0u);
+                    G.Hs[s][t - nboth] = hist;
+                    atomicAdd(&G.Ht[s], hist);
                 } else if (t < nboth + 14u * nsu) {                // undo step for {a, any c of rank y outside s}
                     t -= nboth + nsu;
                     const uint32_t ai = t / 13u, y = t - 13u * ai;
@@ -478,10 +488,12 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // the lane's runout: our rank, its cards of s (rank bits), folded flush index of board + runout in s, its column
                 // of T, its multiplicity; zpos / rz describe its card outside s for the fix-up below
                 uint32_t our = 0, fqf = 0, qb2 = 0, zpos = 0xFFu, rz = 0, qcol = 0, wl = 0, rq = 99;
+                uint32_t ia = 0xFFu, ib = 0xFFu;       // the runout's cards of s as indices into Ls[s] (fast path below)
                 if (qi < nq) {
                     uint32_t qbits, ppq;
                     if (rank_lanes && qtype == 1) {            // (card q of s, rank of the other card)
                         const uint32_t a = qi / 13u;
+                        ia = a;
                         rz = qi - 13u * a;
                         rq = G.code[G.Ls[s][a]] >> 2;
                         qbits = 1u << rq;
@@ -500,12 +512,14 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         if (qtype == 1) {
                             const uint32_t a = (qi * G.g_inv[g]) >> 16, z = qi - a * nns;      // qi / nns
                             const uint32_t x = G.Ls[s][a], y = G.Lns[s][z];
+                            ia = a;
                             i = min(x, y); j = max(x, y);
                             zpos = y;
                         } else {
                             const uint32_t pr = S.pairs[qi];
                             const uint8_t *L = qtype == 2 ? G.Ls[s] : G.Lns[s];
                             i = L[pr & 0xFFu]; j = L[pr >> 8];
+                            if (qtype == 2) { ia = pr & 0xFFu; ib = pr >> 8; }
                         }
                         const uint32_t ci = G.code[i], cj = G.code[j];
                         const uint32_t ri = ci >> 2, rj = cj >> 2;
@@ -527,13 +541,35 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // steps [0, nboth + n_s) have an add part (holdings with both cards in s, or one card a in s); the ones behind them
                 // are rank-level undo steps: no suited-table gather, half the compares
                 const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
-#pragma unroll HOLDEM_F4_UNROLL
-                for (uint32_t t = p0; t < split; ++t, ++pd) {
-                    const uint4 d = *pd;
-                    // fold() is XOR-linear and the step's cards of s are disjoint from board + runout when the step is valid
-                    const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
-                    const uint32_t rn = lds_u16(tq_s + d.w);
-                    flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
+                // Fast path.  Every step with an add part ranks the opponent by a real flush (rank <= 1599).  When none of the warp's
+                // runouts gives US a flush, full house or quads (our rank > 1599: the common case), every valid add part is a loss for us
+                // whatever the exact suited rank, so the add parts of the whole step list sum to a closed form per lane: the class
+                // histogram of all such holdings minus those that contain one of the runout's cards of s (inclusion-exclusion over
+                // Wc0 / Hs).  The steps then only carry their undo half: no suited-table gather, half the compares.
+                const bool fast = kFastAdd && __all_sync(0xFFFFFFFFu, our > 1599u || qi >= nq);
+                if (fast) {
+#pragma unroll kF4Unroll
+                    for (uint32_t t = p0; t < min(split, max(p0, choose2u(nsu))); ++t, ++pd) {   // (the "card a in s" steps have no undo half)
+                        const uint4 d = *pd;
+                        undo_step(sL, sG, our, lds_u16(tq_s + d.w), d.x, qb2, d.z, one);
+                    }
+                    pd = G.PD + G.g_pdbase[g] + split;
+                    if (seg == 0 && qi < nq) {
+                        const bool with_one = np > choose2u(nsu);            // the list also holds the "card a in s" steps
+                        uint32_t add = G.Wt0[s] + (with_one ? G.Ht[s] : 0u);
+                        if (ia != 0xFFu) add -= G.Wc0[s][ia] + (with_one ? G.Hs[s][ia] : 0u);
+                        if (ib != 0xFFu) add -= G.Wc0[s][ib] + (with_one ? G.Hs[s][ib] : 0u) - G.PD[G.g_pdbase[g] + qi].y;
+                        aG = add;                                            // our > suited rank for every one of them
+                    }
+                } else {
+#pragma unroll kF4Unroll
+                    for (uint32_t t = p0; t < split; ++t, ++pd) {
+                        const uint4 d = *pd;
+                        // fold() is XOR-linear and the step's cards of s are disjoint from board + runout when the step is valid
+                        const uint32_t rf = lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf));
+                        const uint32_t rn = lds_u16(tq_s + d.w);
+                        flush_step(aL, aG, sL, sG, our, rf, rn, d.x, qb2, d.y, d.z, one);
+                    }
                 }
 #pragma unroll 2
                 for (uint32_t t = split; t < p1; ++t, ++pd) {
@@ -686,24 +722,24 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 }
 
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st) {
+                                    int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
+                                    bool closed_form_add) {
     // other_rows_flag points at a 16-byte slot: [0] the flag word, [1] the work counter of this kernel, [2] of the turn kernel
     if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Flop4Smem);
-    cudaError_t e = prof ? cudaFuncSetAttribute(hp_flop_treys_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(hp_flop_treys_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the phase clocks are compiled out of the production instances: the kernel is sensitive to its code size
+    auto kernel = prof ? hp_flop_treys_v4_kernel<true, true>
+                       : (closed_form_add ? hp_flop_treys_v4_kernel<false, true> : hp_flop_treys_v4_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t blocks = sms;
     if (blocks * kGroups > n) blocks = (n + kGroups - 1) / kGroups;
     e = cudaMemsetAsync(other_rows_flag, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    // the phase clocks are compiled out of the production instance: the kernel is sensitive to its code size
     count_launch();
-    if (prof) hp_flop_treys_v4_kernel<true><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
-                                                                                    reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
-    else hp_flop_treys_v4_kernel<false><<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
-                                                                                    reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
+    kernel<<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
+                                                 reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
     return cudaGetLastError();
 }
 

@@ -55,10 +55,13 @@ cudaError_t launch_hp_turn_treys(const DevTables &T, const uint8_t *sit, int64_t
 cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                  int *other_rows_flag, int impl, cudaStream_t st);
 // Rank-multiset flop kernel (kernels_hp_flop4.cu): same contract and bit-identical counts, the default.
+// closed_form_add: sum the add parts of the flush steps in closed form where no runout of the warp gives us a flush or better
+// (production); false = walk them step by step (holdem_hp_flop_variant 5, kept for A/B and as a cross-check).
 // prof: optional device uint64[4], cycles spent per phase summed over the situation groups (tables / W+T / descriptors /
 // tasks); nullptr in production.
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st);
+                                    int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
+                                    bool closed_form_add = true);
 
 // Rank-multiset turn kernel (kernels_hp_turn4.cu): same contract as launch_hp_turn_treys, bit-identical counts, the default.
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,

@@ -139,8 +139,9 @@ int holdem_table_hp_batch(const uint8_t *d_hole, const uint8_t *d_board, int64_t
 int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d_out, void *stream);
 
 /* Treys-mode flop rows through one named implementation of the flop kernel (A/B measurements and cross-checks; every
- * variant returns the same counts): 4 = rank-multiset kernel (what holdem_hp_batch runs), 3 = deduplicating 4-set walk,
- * 2 = the earlier warp-per-pair 4-set kernel.  Rows with 4- or 5-card boards are left untouched. */
+ * variant returns the same counts): 4 = rank-multiset kernel (what holdem_hp_batch runs), 5 = the same kernel without the
+ * closed-form sum of the flush steps' add parts, 3 = deduplicating 4-set walk, 2 = the earlier warp-per-pair 4-set kernel.
+ * Rows with 4- or 5-card boards are left untouched. */
 int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
 /* The same for Treys-mode turn rows (four board cards): 4 = rank-multiset kernel (production), 3 = deduplicating 3-set walk.

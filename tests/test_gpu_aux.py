@@ -178,7 +178,9 @@ def test_variant_entry_points(hb):
     """The A/B kernels are reached through explicit entry points (no environment switches in the production dispatch)."""
     sit = torch.from_numpy(_mixed(hb, 1500)).cuda()
     want = hb.hand_potential_counts(sit, "treys")
-    for variants in ((4, 4, 0), (3, 3, 1), (2, 4, 1), (4, 3, 0)):
+    flop = torch.from_numpy(hb.random_situations(8192, seed=77)).cuda()
+    assert torch.equal(hb.hand_potential_counts(flop, "treys", flop_variant=5), hb.hand_potential_counts(flop, "treys", flop_variant=4))
+    for variants in ((4, 4, 0), (3, 3, 1), (2, 4, 1), (4, 3, 0), (5, 4, 0)):
         assert torch.equal(hb.hand_potential_counts(sit, "treys", variants=variants), want), variants
     for mode in ("treys", "reference"):
         assert torch.equal(hb.hand_strength_counts(sit, mode, variant=1), hb.hand_strength_counts(sit, mode))
