@@ -50,6 +50,7 @@ struct DevTables {          // pointers into the device-resident table image (gl
     const uint8_t *ref_t[3];          // HOLDEM_MODE_REFERENCE: [455 | 1820 | 6188][8384] category tables (kernels_hp_ref5.cu), device-built
 };
 
+// (provenance of the key set: tables.h)
 static __constant__ uint32_t c_rank_key[13] = {0,    1,     5,     22,     98,     453,    2031,
                                         8698, 22854, 83661, 262349, 636345, 1479181};
 

@@ -14,6 +14,9 @@ namespace holdem {
 
 // Additive rank keys: the sum over the cards of a hand identifies the rank multiset uniquely for every hand of
 // up to 7 cards with at most 4 cards per rank (checked by selftest()).  Largest 7-card sum: 7,825,759 (23 bits).
+// Provenance: this particular key set is not ours -- it is the published non-flush "face key" constant set of the
+// SpecialK / SKPokerEval family of public 7-card evaluators (K. J. Shackleton), used here as a constant only; nothing of the
+// reference tree or of Treys is involved, and the one property relied on (unique sums) is re-verified at start-up.
 constexpr uint32_t kRankKey[13] = {0,    1,     5,     22,     98,     453,    2031,
                                    8698, 22854, 83661, 262349, 636345, 1479181};
 

@@ -430,3 +430,28 @@ def test_hs_flush_board_textures_match_oracle(hb, oracle):
         want = oracle.hs_batch(sit, "treys")
         bad = np.nonzero((got != want).any(axis=1))[0]
         assert bad.size == 0, (nb, sit[bad[:5]], got[bad[:5]], want[bad[:5]])
+
+
+def test_full_size_configs_reproduce_committed_hashes(hb):
+    """BASELINE.json configs[2], configs[3] (22 seats x 100,000 hands, every street) and configs[4] (1,000,000 flop situations) at
+    FULL size: the 64-bit content hash of every result buffer equals the one committed in tests/golden/gpu_hashes.json (written
+    by scripts/make_gpu_hashes.py from a run in which the production kernels equalled the independent kernels on all rows and the
+    oracle on samples); and the sum of counts, by contrast, is the same structural constant for any well-formed rows."""
+    from holdem_b200 import table
+    g = load_golden("gpu_hashes.json")
+
+    def hx(t):
+        return f"{hb.rows_hash(t.contiguous()):016x}"
+
+    sit = torch.from_numpy(hb.random_situations(65536, seed=20251019)).cuda()
+    assert hx(hb.hand_potential_counts(sit, "treys")) == g["configs2_first_65536_rows_treys"]
+    assert hx(hb.hand_potential_counts(sit, "reference")) == g["configs2_first_65536_rows_reference"]
+    sit = torch.from_numpy(hb.random_situations(1_000_000, seed=20251021)).cuda()
+    rows = hb.hand_potential_counts(sit, "treys")
+    assert hx(rows) == g["configs4_1m_flop_rows_treys"]
+    assert int(rows[:, :15].to(torch.int64).sum()) == 1_000_000 * 1_072_352
+    del rows, sit
+    hole, board = table.deal_tables(100_000, seed=20251020, seats=22)
+    d_hole, d_board = torch.from_numpy(hole).cuda(), torch.from_numpy(board).cuda()
+    for nb, name in ((3, "flop_hs_hp"), (4, "turn_hs_hp"), (5, "river_hs")):
+        assert hx(hb.table_hand_potential_counts(d_hole, d_board, nb, "treys").reshape(-1, 16)) == g[f"configs3_22seat_100k_{name}"], name
