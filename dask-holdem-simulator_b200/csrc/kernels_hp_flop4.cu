@@ -53,6 +53,9 @@ namespace {
 // Group shape (threads per situation group, groups per CTA).  Measured on B200, 65,536 random flops: 6 x 160 -> 39.0 M
 // situations/s, 7 x 128 (one more situation in flight per SM) -> 38.8 M: the kernel is bound by instruction issue and
 // shared-memory wavefronts inside the task phase, not by the latency of the per-situation set-up phases.
+#ifndef HOLDEM_F4_CLAIM
+#define HOLDEM_F4_CLAIM 2
+#endif
 #ifndef HOLDEM_F4_UNROLL
 #define HOLDEM_F4_UNROLL 2
 #endif
@@ -73,7 +76,7 @@ constexpr int kSeg = 64;           // longest step segment of a flush task (pack
 constexpr int kPD = 320;           // step descriptors per situation: at most 3 x 66 (rainbow) or 45 + 14 x 11 + 91 + 66
 constexpr int kMaxGroups = 12;
 constexpr int kProfSlots = 8;
-constexpr int kClaim = 4;           // situations a group claims from the global work counter at a time
+constexpr int kClaim = HOLDEM_F4_CLAIM;           // situations a group claims from the global work counter at a time
 
 struct Flop4Group {                    // one situation in flight
     uint4 PD[kPD];                     // x = 2 * (rank bits of the step's cards in s) << 16 | 2 * fold(those bits),
