@@ -104,6 +104,8 @@ def main():
     ap.add_argument("--situations", type=int, default=1000000)
     ap.add_argument("--config5", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--oracle-fraction", type=float, default=0.0,
+                    help="config 4: fraction of the rows of every street compared with the C oracle (0.01 = 1 %%, ~2 min of CPU)")
     ap.add_argument("--python-baseline", action="store_true", help="also time the reference-shaped pure-Python path (config 1)")
     ap.add_argument("--python-baseline-opponents", type=int, default=40,
                     help="opponent holdings of the 1081 to time (each = 990 runouts x 2 evaluate calls)")
@@ -203,28 +205,43 @@ def main():
         rates[f"category{nc}"] = {"hands": cards.shape[0], "ms": ms, "hands_per_sec": cards.shape[0] / (ms * 1e-3)}
     res["kernel_rates"] = rates
 
-    # ---- config 4: 22-seat table, every seat on flop / turn / river ---------------------------------------------------------------
-    tab = table_situations(args.hands)
-    c4 = {"hands": args.hands, "seats": 22, "situations_per_street": int(tab[3].shape[0])}
+    # ---- config 4: 22-seat table, every seat on flop / turn / river, through the whole-table entry point -----------------------------
+    from holdem_b200 import table
+    hole, board = table.deal_tables(args.hands, seed=20251020, seats=22)
+    d_hole, d_board = torch.from_numpy(hole).cuda(), torch.from_numpy(board).cuda()
+    golden = {}
+    try:
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "gpu_hashes.json")))
+    except Exception:
+        pass
+    c4 = {"hands": args.hands, "seats": 22, "situations_per_street": args.hands * 22, "oracle_fraction": args.oracle_fraction}
     total_ms = 0.0
+    rng = np.random.default_rng(4)
     for nb, name in ((3, "flop_hs_hp"), (4, "turn_hs_hp"), (5, "river_hs")):
-        sit = torch.from_numpy(tab[nb]).cuda()
-        if nb == 5:
-            fn = lambda: hb.hand_strength_counts(sit, "treys")
-        else:
-            fn = lambda: hb.hand_potential_counts(sit, "treys")
-        ms = timed(fn, reps=1, warm=1)
+        fn = lambda: hb.table_hand_potential_counts(d_hole, d_board, nb, "treys")
+        ms = timed(fn, reps=2, warm=1)
         total_ms += ms
-        rows = fn().cpu().numpy().astype(np.int64)
+        out = fn().reshape(-1, 16)
+        r = out.cpu().numpy().astype(np.int64)
         m = 52 - 2 - nb
-        if nb == 5:
-            ok = bool((rows.sum(axis=1) == m * (m - 1) // 2).all())
-        else:
-            runouts = 990 if nb == 3 else 44
-            ok = bool((rows[:, 12:15].sum(axis=1) == m * (m - 1) // 2).all()
-                      and (rows[:, 3:12].reshape(-1, 3, 3).sum(axis=2) == runouts * rows[:, 12:15]).all())
-        c4[name] = {"ms": ms, "situations_per_sec": sit.shape[0] / (ms * 1e-3), "properties_ok": ok,
-                    "content_hash": f"{hb.rows_hash(fn().to(torch.int32).contiguous()):016x}"}
+        runouts = {3: 990, 4: 44, 5: 0}[nb]
+        ok = bool((r[:, 12:15].sum(axis=1) == m * (m - 1) // 2).all()
+                  and (r[:, 3:12].reshape(-1, 3, 3).sum(axis=2) == runouts * r[:, 12:15]).all())
+        entry = {"ms": ms, "situations_per_sec": out.shape[0] / (ms * 1e-3), "properties_ok": ok,
+                 "content_hash": f"{hb.rows_hash(out):016x}"}
+        key = f"configs3_22seat_100k_{name}"
+        if args.hands == 100000 and key in golden:
+            entry["hash_equals_committed"] = entry["content_hash"] == golden[key]
+        if args.oracle_fraction > 0:
+            from oracle import oracle as O
+            n_or = max(1, int(out.shape[0] * args.oracle_fraction))
+            pick = np.sort(rng.choice(out.shape[0], n_or, replace=False))
+            t0 = time.perf_counter()
+            want = O.hp_batch_parallel(table.situations_for_street(hole, board, nb)[pick], "treys", cache4=True)
+            entry["oracle_rows_compared"] = n_or
+            entry["oracle_seconds"] = time.perf_counter() - t0
+            entry["oracle_equal"] = bool(np.array_equal(r[pick].astype(np.uint32), want))
+        c4[name] = entry
     c4["total_ms"] = total_ms
     c4["hands_per_sec"] = args.hands / (total_ms * 1e-3)
     res["config4_22_seat_table"] = c4

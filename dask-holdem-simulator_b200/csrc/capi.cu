@@ -426,6 +426,7 @@ struct HpImpl {
     int flop = 4;      // 4 rank-multiset kernel, 5 the same without the closed-form add path, 3 / 2 the 4-set kernels
     int turn = 4;      // 4 rank-multiset kernel, 3 the 3-set walk
     int river = 0;     // 0 rank-pair HS kernel in its HP-row form, 1 plain enumeration
+    bool order = true; // work the flop rows heaviest board texture first (false: row order; holdem_hp_flop_variant 6)
     int ref = 5;       // HOLDEM_MODE_REFERENCE: 5 rank-multiset kernel, 4 the earlier 4-set walk + arithmetic irregular runouts
 };
 
@@ -459,8 +460,15 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     const bool old_flop = impl.flop == 2 || impl.flop == 3, old_turn = impl.turn == 3;
     const bool fused = !old_flop && !old_turn;          // the production kernels store their rows into the peers themselves
     const PeerOut none{};
+    // batches worth ordering by board texture get a stream-ordered scratch buffer for the work order (private pool)
+    uint32_t *order = nullptr;
+    if (!old_flop && impl.order && n >= 4096) {
+        e = cudaMallocFromPoolAsync((void **)&order, flop_order_scratch_bytes(n), S.pool, st);
+        if (e != cudaSuccess) return e;
+    }
     e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl.flop, st)
-                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st, impl.flop != 5);
+                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st, impl.flop != 5, order);
+    if (order != nullptr) cudaFreeAsync(order, st);
     if (e != cudaSuccess) return e;
     e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
                  : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st);
@@ -518,12 +526,18 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (variant < 2 || variant > 5) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
+    if (variant < 2 || variant > 6) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
     FlagSlot slot;
     CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
-    if (variant >= 4) CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream,
-                                                       variant == 4));
-    else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, slot.ptr, variant, (cudaStream_t)stream));
+    if (variant >= 4) {
+        uint32_t *order = nullptr;
+        if (variant != 6 && n >= 4096)
+            CUDA_TRY(cudaMallocFromPoolAsync((void **)&order, flop_order_scratch_bytes(n), S->pool, (cudaStream_t)stream));
+        cudaError_t e = launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream,
+                                                variant != 5, order);
+        if (order != nullptr) cudaFreeAsync(order, (cudaStream_t)stream);
+        CUDA_TRY(e);
+    } else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, slot.ptr, variant, (cudaStream_t)stream));
     CUDA_TRY(slot.release());
     return HOLDEM_OK;
 }
@@ -609,10 +623,10 @@ int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, i
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (flop_variant < 2 || flop_variant > 5 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
-        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..5, turn 3..4, river 0..1)");
+    if (flop_variant < 2 || flop_variant > 6 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
+        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..6, turn 3..4, river 0..1)");
     HpImpl impl;
-    impl.flop = flop_variant; impl.turn = turn_variant; impl.river = river_variant;
+    impl.flop = flop_variant == 6 ? 4 : flop_variant; impl.order = flop_variant != 6; impl.turn = turn_variant; impl.river = river_variant;
     CUDA_TRY(hp_dispatch(*S, d_sit, n, HOLDEM_MODE_TREYS, d_out, (cudaStream_t)stream, PeerOut{}, nullptr, impl));
     return HOLDEM_OK;
 }

@@ -105,7 +105,8 @@ struct Flop4Group {                    // one situation in flight
     uint32_t HA[16 * 13];              // monotone boards: class histogram (10-bit fields) of {a, c} over the c of one rank outside s
     uint32_t upack[2];                 // unseen cards per rank, 3 bits each (64-bit)
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
-    uint32_t next_claim[2];            // first row of the claim being worked on / of the next one (alternating)
+    uint32_t next_claim[2];            // first work index of the claim being worked on / of the next one (alternating)
+    uint32_t claim_rows[2][kClaim];    // the rows behind those work indices (resolved through the work order when the claim is made)
     uint32_t prof[kProfSlots];
     uint8_t code[48];                  // unseen cards, rank*4+suit, ascending
     uint8_t Ls[4][16];                 // positions of the unseen cards of suit s
@@ -131,7 +132,7 @@ template <bool kProf, bool kFastAdd>
 __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
                         int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers,
-                        unsigned int *__restrict__ work_counter) {
+                        unsigned int *__restrict__ work_counter, const uint32_t *__restrict__ order) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Flop4Smem &S = *reinterpret_cast<Flop4Smem *>(smem_raw);
     const uint32_t gid = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
@@ -172,13 +173,28 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     // is fetched while the current one is being worked on.  (work_counter == nullptr: static striding.)
     const uint32_t n_all_groups = gridDim.x * kGroups, my_group = blockIdx.x * kGroups + gid;
     uint32_t claim_it = 0;
-    if (tid == 0) G.next_claim[0] = work_counter ? atomicAdd(work_counter, (unsigned)kClaim) : my_group * kClaim;
+    // a claim = kClaim consecutive work indices; their rows are looked up at once (under the previous situation's task phase)
+    auto make_claim = [&](uint32_t slot, uint32_t it) {
+        const uint32_t base = work_counter ? atomicAdd(work_counter, (unsigned)kClaim) : (it * n_all_groups + my_group) * kClaim;
+        G.next_claim[slot] = base;
+#pragma unroll
+        for (uint32_t j = 0; j < (uint32_t)kClaim; ++j) {
+            const int64_t v = (int64_t)base + j;
+            G.claim_rows[slot][j] = v < n ? (order != nullptr ? __ldg(order + 32 + v) : (uint32_t)v) : 0u;
+        }
+    };
+    if (tid == 0) make_claim(0, 0);
     for (;; ++claim_it) {
     group_sync(gid);
     const int64_t claim_base = G.next_claim[claim_it & 1];
     if (claim_base >= n) break;
     bool next_claimed = false;
-    for (int64_t idx = claim_base; idx < n && idx < claim_base + kClaim; ++idx) {
+    for (int64_t vidx = claim_base; vidx < n && vidx < claim_base + kClaim; ++vidx) {
+        // Work order (flop_order kernels): monotone flops first, then two-tone, then rainbow, inside a texture the situations
+        // in which we hold more cards of one suit first, the rows of other streets last: the heaviest situations start first, and
+        // the situation groups of an SM spend most of their time in the same code regions (the kernel is instruction-cache
+        // sensitive: +7 % on the mixed workload).  Results are stored by row number as before.
+        const int64_t idx = G.claim_rows[claim_it & 1][vidx - claim_base];
         group_sync(gid);                                                                            // (A)
         if (kProf && tid == 0) t_prev = (uint32_t)clock64();
         uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
@@ -454,9 +470,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         HOLDEM_PROF(1)
         group_sync(gid);                                                                            // (D)
         if (!next_claimed) {                                           // fetch the next claim under this situation's tasks
-            if (tid == 0)
-                G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaim)
-                                                                : ((claim_it + 1) * n_all_groups + my_group) * kClaim;
+            if (tid == 0) make_claim((claim_it + 1) & 1, claim_it + 1);
             next_claimed = true;
         }
         mbar_wait(bar1_s, parity);                                     // T has landed
@@ -714,9 +728,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (k < peers.n) peers.p[k][idx * 16 + tid] = v;
         }
     }
-    if (!next_claimed && tid == 0)                                     // every row of the claim belonged to another kernel
-        G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaim)
-                                                        : ((claim_it + 1) * n_all_groups + my_group) * kClaim;
+    if (!next_claimed && tid == 0) make_claim((claim_it + 1) & 1, claim_it + 1);   // every row of the claim belonged to another kernel
     }
 #undef HOLDEM_PROF
     if (saw_other && tid == 0) atomicOr(other_rows, saw_other);
@@ -724,9 +736,70 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         for (int k = 0; k < 4; ++k) atomicAdd(prof + k, (unsigned long long)G.prof[k]);
 }
 
+// Work order of the flop kernel.  scratch: [0..15] rows per class, [16..31] cursors, [32..32+n) the rows sorted by class
+// (in no particular order inside a class).  Class = 4 x texture (0 monotone, 1 two-tone, 2 rainbow) + (5 - cards of our most
+// frequent suit among hole + board), 12 = anything that is not a well-formed flop row (worked last).
+__device__ __forceinline__ uint32_t flop_order_class(uint2 w) {
+    uint32_t c[5] = {w.x & 0xFFu, (w.x >> 8) & 0xFFu, (w.x >> 16) & 0xFFu, w.x >> 24, w.y & 0xFFu};
+    if (((w.y >> 8) & 0xFFu) != 0xFFu) return 12u;
+    uint32_t hs = 0, bsu = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (c[k] >= 52u) return 12u;
+        const uint32_t su = card_suit(c[k]);
+        hs += 1u << (8 * su);
+        if (k >= 2) bsu += 1u << (8 * su);
+    }
+    const uint32_t bmax = max(max(bsu & 0xFFu, (bsu >> 8) & 0xFFu), max((bsu >> 16) & 0xFFu, bsu >> 24));
+    const uint32_t hmax = max(max(hs & 0xFFu, (hs >> 8) & 0xFFu), max((hs >> 16) & 0xFFu, hs >> 24));
+    return 4u * (3u - bmax) + (5u - hmax);
+}
+
+__global__ void __launch_bounds__(256)
+flop_order_count_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ scratch) {
+    __shared__ uint32_t hist[16];
+    if (threadIdx.x < 16) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&hist[flop_order_class(__ldg(reinterpret_cast<const uint2 *>(sit) + i))], 1u);
+    __syncthreads();
+    if (threadIdx.x < 13 && hist[threadIdx.x]) atomicAdd(scratch + threadIdx.x, hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+flop_order_scatter_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ scratch) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base[13];
+    {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) { base[k] = acc; acc += scratch[k]; }
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += stride) {            // warp-uniform trip count
+        const int64_t i = b0 + threadIdx.x;
+        const uint32_t cls = i < n ? flop_order_class(__ldg(reinterpret_cast<const uint2 *>(sit) + i)) : 15u;
+        // lanes of one class share one atomic
+        const uint32_t peers_m = __match_any_sync(0xFFFFFFFFu, cls);
+        const uint32_t leader = (uint32_t)(__ffs(peers_m) - 1);
+        uint32_t pos = 0;
+        if (lane == leader && cls < 13u) pos = atomicAdd(scratch + 16 + cls, (uint32_t)__popc(peers_m));
+        pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
+        if (cls < 13u) {
+            uint32_t bs = 0;
+#pragma unroll
+            for (int k = 0; k < 13; ++k) bs = cls == (uint32_t)k ? base[k] : bs;
+            scratch[32 + bs + pos + __popc(peers_m & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
+    }
+}
+
+size_t flop_order_scratch_bytes(int64_t n) { return (32 + (size_t)n) * sizeof(uint32_t); }
+
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
-                                    bool closed_form_add) {
+                                    bool closed_form_add, uint32_t *order_scratch) {
     // other_rows_flag points at a 16-byte slot: [0] the flag word, [1] the work counter of this kernel, [2] of the turn kernel
     if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     if (n == 0) return cudaSuccess;
@@ -740,9 +813,19 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (blocks * kGroups > n) blocks = (n + kGroups - 1) / kGroups;
     e = cudaMemsetAsync(other_rows_flag, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return e;
+    if (order_scratch != nullptr) {
+        e = cudaMemsetAsync(order_scratch, 0, 32 * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        int64_t ob = (n + 255) / 256;
+        if (ob > (int64_t)sms * 8) ob = (int64_t)sms * 8;
+        count_launch();
+        flop_order_count_kernel<<<(int)ob, 256, 0, st>>>(sit, n, order_scratch);
+        count_launch();
+        flop_order_scatter_kernel<<<(int)ob, 256, 0, st>>>(sit, n, order_scratch);
+    }
     count_launch();
     kernel<<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
-                                                 reinterpret_cast<unsigned int *>(other_rows_flag) + 1);
+                                                 reinterpret_cast<unsigned int *>(other_rows_flag) + 1, order_scratch);
     return cudaGetLastError();
 }
 

@@ -61,7 +61,10 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
 // tasks); nullptr in production.
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
-                                    bool closed_form_add = true);
+                                    bool closed_form_add = true, uint32_t *order_scratch = nullptr);
+// order_scratch: optional device buffer of flop_order_scratch_bytes(n) bytes; when given, the kernel is preceded by a pass that
+// classifies the rows by board texture and the situations are worked heaviest texture first (results still land by row number).
+size_t flop_order_scratch_bytes(int64_t n);
 
 // Rank-multiset turn kernel (kernels_hp_turn4.cu): same contract as launch_hp_turn_treys, bit-identical counts, the default.
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,

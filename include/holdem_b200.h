@@ -140,7 +140,8 @@ int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *
 
 /* Treys-mode flop rows through one named implementation of the flop kernel (A/B measurements and cross-checks; every
  * variant returns the same counts): 4 = rank-multiset kernel (what holdem_hp_batch runs), 5 = the same kernel without the
- * closed-form sum of the flush steps' add parts, 3 = deduplicating 4-set walk, 2 = the earlier warp-per-pair 4-set kernel.
+ * closed-form sum of the flush steps' add parts, 6 = the production kernel working the rows in input order instead of heaviest
+ * board texture first, 3 = deduplicating 4-set walk, 2 = the earlier warp-per-pair 4-set kernel.
  * Rows with 4- or 5-card boards are left untouched. */
 int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
