@@ -133,6 +133,13 @@ __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
                         int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers,
                         unsigned int *__restrict__ work_counter, const uint32_t *__restrict__ order) {
+    if (order != nullptr && order[15] == 0) {           // the ordering pass found no flop-shaped row: only tell the other kernels
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const int other = (order[13] ? 1 : 0) | (order[14] ? 2 : 0);
+            if (other) atomicOr(other_rows, other);
+        }
+        return;
+    }
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Flop4Smem &S = *reinterpret_cast<Flop4Smem *>(smem_raw);
     const uint32_t gid = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
@@ -761,15 +768,21 @@ flop_order_count_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     if (threadIdx.x < 16) hist[threadIdx.x] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&hist[flop_order_class(__ldg(reinterpret_cast<const uint2 *>(sit) + i))], 1u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + i);
+        atomicAdd(&hist[flop_order_class(w)], 1u);
+        // rows by the kernel that owns them: [15] flop-shaped (fourth and fifth board card absent), [13] turn-, [14] river-shaped
+        const bool no4 = ((w.y >> 8) & 0xFFu) == 0xFFu, no5 = ((w.y >> 16) & 0xFFu) == 0xFFu;
+        atomicAdd(&hist[no5 ? (no4 ? 15 : 13) : 14], 1u);
+    }
     __syncthreads();
-    if (threadIdx.x < 13 && hist[threadIdx.x]) atomicAdd(scratch + threadIdx.x, hist[threadIdx.x]);
+    if (threadIdx.x < 16 && hist[threadIdx.x]) atomicAdd(scratch + threadIdx.x, hist[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256)
 flop_order_scatter_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ scratch) {
     const uint32_t lane = threadIdx.x & 31;
+    if (scratch[15] == 0) return;                       // no flop-shaped row: the flop kernel will not look at the order
     uint32_t base[13];
     {
         uint32_t acc = 0;

@@ -176,7 +176,7 @@ def test_table_hp_matches_row_expansion(hb, oracle):
 
 def test_variant_entry_points(hb):
     """The A/B kernels are reached through explicit entry points (no environment switches in the production dispatch)."""
-    sit = torch.from_numpy(_mixed(hb, 1500)).cuda()
+    sit = torch.from_numpy(_mixed(hb, 9000)).cuda()       # >= 4096 rows: the flop kernel works them in texture order
     want = hb.hand_potential_counts(sit, "treys")
     flop = torch.from_numpy(hb.random_situations(8192, seed=77)).cuda()
     assert torch.equal(hb.hand_potential_counts(flop, "treys", flop_variant=5), hb.hand_potential_counts(flop, "treys", flop_variant=4))
