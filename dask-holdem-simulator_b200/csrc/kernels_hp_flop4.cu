@@ -54,7 +54,7 @@ namespace {
 // situations/s, 7 x 128 (one more situation in flight per SM) -> 38.8 M: the kernel is bound by instruction issue and
 // shared-memory wavefronts inside the task phase, not by the latency of the per-situation set-up phases.
 #ifndef HOLDEM_F4_CLAIM
-#define HOLDEM_F4_CLAIM 2
+#define HOLDEM_F4_CLAIM 1
 #endif
 #ifndef HOLDEM_F4_UNROLL
 #define HOLDEM_F4_UNROLL 2
