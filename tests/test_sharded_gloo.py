@@ -68,3 +68,67 @@ def test_sharded_single_process_no_group():
 
     full = hb.hand_potential_counts_sharded(torch.from_numpy(sit_np), "reference", compute=compute)
     assert np.array_equal(full.numpy(), O.hp_batch(sit_np, "reference").astype(np.int32))
+
+
+class _FakeHandle:
+    def __init__(self, world):
+        self.buffer_ptrs = [0] * world
+
+    def barrier(self, channel=0):
+        dist.barrier()
+
+
+def _agreement_worker(rank, world, port, fail_rank, fail_stage, ret):
+    """The fused-vs-all-gather decision is collective: symmetric memory is simulated by a fake module that fails on ONE rank (at
+    allocation or at rendezvous); every rank must come to the same answer -- nobody may end up in the all-gather while its peer
+    waits in the symmetric-memory barrier (round-1 advisor finding)."""
+    import sys
+    import types
+    from conftest import PKG, ROOT  # noqa: F401
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fake = types.ModuleType("torch.distributed._symmetric_memory")
+
+    def empty(shape, dtype=None, device=None):
+        if rank == fail_rank and fail_stage == "alloc":
+            raise RuntimeError("simulated: symmetric memory not supported on this rank")
+        return torch.zeros(shape, dtype=dtype)
+
+    def rendezvous(t, group):
+        if rank == fail_rank and fail_stage == "rendezvous":
+            raise RuntimeError("simulated: rendezvous failed on this rank")
+        return _FakeHandle(world)
+
+    fake.empty, fake.rendezvous = empty, rendezvous
+    sys.modules["torch.distributed._symmetric_memory"] = fake
+    import torch.distributed as d
+    d._symmetric_memory = fake
+    from holdem_b200 import sharded
+    dev = torch.device("cpu")
+    st = sharded.fused_state(dev, None)
+    ok1 = sharded._ensure_buffers(st, 64, dev, None)
+    ok2 = sharded._ensure_buffers(st, 128, dev, None)            # a second call does not flip the decision
+    expect = fail_rank is None
+    good = ok1 == expect and ok2 == expect and (st.available is expect)
+    if expect:
+        good = good and st.capacity >= 128 and len(st.bufs) == 2
+    else:
+        good = good and st.reason is not None and sharded.fused_path_error(dev) is not None
+    ret[rank] = bool(good)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_agreement(fail_rank, fail_stage):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_agreement_worker, args=(world, _free_port(), fail_rank, fail_stage, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_fused_path_decision_is_collective():
+    _run_agreement(None, None)                 # everyone succeeds: fused path, one growing pair of buffers
+    _run_agreement(1, "alloc")                 # one rank cannot allocate: both ranks use the all-gather
+    _run_agreement(0, "rendezvous")            # one rank fails at the rendezvous: both ranks use the all-gather
