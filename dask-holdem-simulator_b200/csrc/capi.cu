@@ -462,16 +462,18 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
     const PeerOut none{};
     // batches worth ordering by board texture get a stream-ordered scratch buffer for the work order (private pool)
     uint32_t *order = nullptr;
-    if (!old_flop && impl.order && n >= 4096) {
-        e = cudaMallocFromPoolAsync((void **)&order, flop_order_scratch_bytes(n), S.pool, st);
+    if (fused && impl.order && n >= 4096) {
+        e = cudaMallocFromPoolAsync((void **)&order, street_order_scratch_bytes(n), S.pool, st);
         if (e != cudaSuccess) return e;
+        e = launch_street_order(d_sit, n, order, S.sms, st);
+        if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
     }
     e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl.flop, st)
                  : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st, impl.flop != 5, order);
+    if (e == cudaSuccess)
+        e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
+                     : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st, order);
     if (order != nullptr) cudaFreeAsync(order, st);
-    if (e != cudaSuccess) return e;
-    e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
-                 : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st);
     if (e != cudaSuccess) return e;
     e = impl.river == 1 ? launch_hp_direct(S.T, d_sit, n, mode, d_out, S.sms, flag, 1, st)
                         : launch_hp_river_rows(S.T, d_sit, n, d_out, S.sms, flag, st);
@@ -531,8 +533,11 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
     if (variant >= 4) {
         uint32_t *order = nullptr;
-        if (variant != 6 && n >= 4096)
-            CUDA_TRY(cudaMallocFromPoolAsync((void **)&order, flop_order_scratch_bytes(n), S->pool, (cudaStream_t)stream));
+        if (variant != 6 && n >= 4096) {
+            CUDA_TRY(cudaMallocFromPoolAsync((void **)&order, street_order_scratch_bytes(n), S->pool, (cudaStream_t)stream));
+            cudaError_t eo = launch_street_order(d_sit, n, order, S->sms, (cudaStream_t)stream);
+            if (eo != cudaSuccess) { cudaFreeAsync(order, (cudaStream_t)stream); CUDA_TRY(eo); }
+        }
         cudaError_t e = launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream,
                                                 variant != 5, order);
         if (order != nullptr) cudaFreeAsync(order, (cudaStream_t)stream);
@@ -547,9 +552,24 @@ int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (variant != 3 && variant != 4) return fail(HOLDEM_ERR_BAD_ARG, "unknown turn kernel variant %d", variant);
-    if (variant == 4) CUDA_TRY(launch_hp_turn_treys_v4(S->T, d_sit, n, d_out, S->sms, nullptr, PeerOut{}, (cudaStream_t)stream));
-    else CUDA_TRY(launch_hp_turn_treys(S->T, d_sit, n, d_out, S->sms, nullptr, (cudaStream_t)stream));
+    if (variant != 3 && variant != 4 && variant != 6) return fail(HOLDEM_ERR_BAD_ARG, "unknown turn kernel variant %d", variant);
+    if (variant == 3) CUDA_TRY(launch_hp_turn_treys(S->T, d_sit, n, d_out, S->sms, nullptr, (cudaStream_t)stream));
+    else {
+        // the kernel's work counter lives in a flag slot (word 2); word 0 stays 0 and is not consulted (run_flag == nullptr)
+        FlagSlot slot;
+        CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
+        CUDA_TRY(cudaMemsetAsync(slot.ptr, 0, 4 * sizeof(int), (cudaStream_t)stream));
+        uint32_t *order = nullptr;
+        if (variant == 4 && n >= 4096) {
+            CUDA_TRY(cudaMallocFromPoolAsync((void **)&order, street_order_scratch_bytes(n), S->pool, (cudaStream_t)stream));
+            cudaError_t eo = launch_street_order(d_sit, n, order, S->sms, (cudaStream_t)stream);
+            if (eo != cudaSuccess) { cudaFreeAsync(order, (cudaStream_t)stream); CUDA_TRY(eo); }
+        }
+        cudaError_t e = launch_hp_turn_treys_v4_counter(S->T, d_sit, n, d_out, S->sms, slot.ptr, PeerOut{}, (cudaStream_t)stream, order);
+        if (order != nullptr) cudaFreeAsync(order, (cudaStream_t)stream);
+        CUDA_TRY(e);
+        CUDA_TRY(slot.release());
+    }
     return HOLDEM_OK;
 }
 

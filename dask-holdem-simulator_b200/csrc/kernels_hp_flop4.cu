@@ -133,9 +133,9 @@ __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
                         int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers,
                         unsigned int *__restrict__ work_counter, const uint32_t *__restrict__ order) {
-    if (order != nullptr && order[15] == 0) {           // the ordering pass found no flop-shaped row: only tell the other kernels
+    if (order != nullptr && order[31] == 0) {           // the ordering pass found no flop-shaped row: only tell the other kernels
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            const int other = (order[13] ? 1 : 0) | (order[14] ? 2 : 0);
+            const int other = (order[29] ? 1 : 0) | (order[30] ? 2 : 0);
             if (other) atomicOr(other_rows, other);
         }
         return;
@@ -187,7 +187,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 #pragma unroll
         for (uint32_t j = 0; j < (uint32_t)kClaim; ++j) {
             const int64_t v = (int64_t)base + j;
-            G.claim_rows[slot][j] = v < n ? (order != nullptr ? __ldg(order + 32 + v) : (uint32_t)v) : 0u;
+            G.claim_rows[slot][j] = v < n ? (order != nullptr ? __ldg(order + kOrderHeader + v) : (uint32_t)v) : 0u;
         }
     };
     if (tid == 0) make_claim(0, 0);
@@ -197,7 +197,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     if (claim_base >= n) break;
     bool next_claimed = false;
     for (int64_t vidx = claim_base; vidx < n && vidx < claim_base + kClaim; ++vidx) {
-        // Work order (flop_order kernels): monotone flops first, then two-tone, then rainbow, inside a texture the situations
+        // Work order (kernels_order.cu): monotone flops first, then two-tone, then rainbow, inside a texture the situations
         // in which we hold more cards of one suit first, the rows of other streets last: the heaviest situations start first, and
         // the situation groups of an SM spend most of their time in the same code regions (the kernel is instruction-cache
         // sensitive: +7 % on the mixed workload).  Results are stored by row number as before.
@@ -743,73 +743,6 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         for (int k = 0; k < 4; ++k) atomicAdd(prof + k, (unsigned long long)G.prof[k]);
 }
 
-// Work order of the flop kernel.  scratch: [0..15] rows per class, [16..31] cursors, [32..32+n) the rows sorted by class
-// (in no particular order inside a class).  Class = 4 x texture (0 monotone, 1 two-tone, 2 rainbow) + (5 - cards of our most
-// frequent suit among hole + board), 12 = anything that is not a well-formed flop row (worked last).
-__device__ __forceinline__ uint32_t flop_order_class(uint2 w) {
-    uint32_t c[5] = {w.x & 0xFFu, (w.x >> 8) & 0xFFu, (w.x >> 16) & 0xFFu, w.x >> 24, w.y & 0xFFu};
-    if (((w.y >> 8) & 0xFFu) != 0xFFu) return 12u;
-    uint32_t hs = 0, bsu = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        if (c[k] >= 52u) return 12u;
-        const uint32_t su = card_suit(c[k]);
-        hs += 1u << (8 * su);
-        if (k >= 2) bsu += 1u << (8 * su);
-    }
-    const uint32_t bmax = max(max(bsu & 0xFFu, (bsu >> 8) & 0xFFu), max((bsu >> 16) & 0xFFu, bsu >> 24));
-    const uint32_t hmax = max(max(hs & 0xFFu, (hs >> 8) & 0xFFu), max((hs >> 16) & 0xFFu, hs >> 24));
-    return 4u * (3u - bmax) + (5u - hmax);
-}
-
-__global__ void __launch_bounds__(256)
-flop_order_count_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ scratch) {
-    __shared__ uint32_t hist[16];
-    if (threadIdx.x < 16) hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + i);
-        atomicAdd(&hist[flop_order_class(w)], 1u);
-        // rows by the kernel that owns them: [15] flop-shaped (fourth and fifth board card absent), [13] turn-, [14] river-shaped
-        const bool no4 = ((w.y >> 8) & 0xFFu) == 0xFFu, no5 = ((w.y >> 16) & 0xFFu) == 0xFFu;
-        atomicAdd(&hist[no5 ? (no4 ? 15 : 13) : 14], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 16 && hist[threadIdx.x]) atomicAdd(scratch + threadIdx.x, hist[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(256)
-flop_order_scatter_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ scratch) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (scratch[15] == 0) return;                       // no flop-shaped row: the flop kernel will not look at the order
-    uint32_t base[13];
-    {
-        uint32_t acc = 0;
-#pragma unroll
-        for (int k = 0; k < 13; ++k) { base[k] = acc; acc += scratch[k]; }
-    }
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x; b0 < n; b0 += stride) {            // warp-uniform trip count
-        const int64_t i = b0 + threadIdx.x;
-        const uint32_t cls = i < n ? flop_order_class(__ldg(reinterpret_cast<const uint2 *>(sit) + i)) : 15u;
-        // lanes of one class share one atomic
-        const uint32_t peers_m = __match_any_sync(0xFFFFFFFFu, cls);
-        const uint32_t leader = (uint32_t)(__ffs(peers_m) - 1);
-        uint32_t pos = 0;
-        if (lane == leader && cls < 13u) pos = atomicAdd(scratch + 16 + cls, (uint32_t)__popc(peers_m));
-        pos = __shfl_sync(0xFFFFFFFFu, pos, leader);
-        if (cls < 13u) {
-            uint32_t bs = 0;
-#pragma unroll
-            for (int k = 0; k < 13; ++k) bs = cls == (uint32_t)k ? base[k] : bs;
-            scratch[32 + bs + pos + __popc(peers_m & ((1u << lane) - 1u))] = (uint32_t)i;
-        }
-    }
-}
-
-size_t flop_order_scratch_bytes(int64_t n) { return (32 + (size_t)n) * sizeof(uint32_t); }
-
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
                                     bool closed_form_add, uint32_t *order_scratch) {
@@ -826,16 +759,6 @@ cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int6
     if (blocks * kGroups > n) blocks = (n + kGroups - 1) / kGroups;
     e = cudaMemsetAsync(other_rows_flag, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    if (order_scratch != nullptr) {
-        e = cudaMemsetAsync(order_scratch, 0, 32 * sizeof(uint32_t), st);
-        if (e != cudaSuccess) return e;
-        int64_t ob = (n + 255) / 256;
-        if (ob > (int64_t)sms * 8) ob = (int64_t)sms * 8;
-        count_launch();
-        flop_order_count_kernel<<<(int)ob, 256, 0, st>>>(sit, n, order_scratch);
-        count_launch();
-        flop_order_scatter_kernel<<<(int)ob, 256, 0, st>>>(sit, n, order_scratch);
-    }
     count_launch();
     kernel<<<(int)blocks, kThreads4, smem, st>>>(sit, n, out, T, other_rows_flag, prof, 1u, peers,
                                                  reinterpret_cast<unsigned int *>(other_rows_flag) + 1, order_scratch);

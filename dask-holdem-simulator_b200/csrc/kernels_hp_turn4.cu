@@ -35,7 +35,7 @@ constexpr int kPPT = 91;
 constexpr int kSegT = 64;
 constexpr int kPDT = 320;            // 45 + 14 * 10 + 91 at most for the one suit with >= 3 board cards, 2 x 55 for two suits with 2
 constexpr int kMaxGroupsT = 8;
-constexpr int kClaimT = 8;           // situations a group claims from the global work counter at a time
+constexpr int kClaimT = 4;           // situations a group claims from the global work counter at a time
 
 struct Turn4Group {
     uint4 PD[kPDT];                    // step descriptors, as in kernels_hp_flop4.cu; w = byte offset of row pp of T
@@ -59,6 +59,7 @@ struct Turn4Group {
     uint32_t upack[2];
     uint32_t n_groups, pd_total, next_task, ours_now, n_ext;
     uint32_t next_claim[2];
+    uint32_t claim_rows[2][kClaimT];   // the rows behind the claimed work indices
     uint8_t code[48];
     uint8_t Ls[4][16];
     uint8_t Lns[4][48];
@@ -80,9 +81,12 @@ __device__ __forceinline__ void tsync(uint32_t gid) { group_sync_n<kGT>(gid); }
 
 __global__ void __launch_bounds__(kThreadsT, 1)
 hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
-                        int *__restrict__ run_flag, uint32_t one, PeerOut peers, unsigned int *__restrict__ work_counter) {
+                        int *__restrict__ run_flag, uint32_t one, PeerOut peers, unsigned int *__restrict__ work_counter,
+                        const uint32_t *__restrict__ order) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     if (run_flag != nullptr && !(*run_flag & 1)) return;   // the flop kernel saw no turn rows
+    // with a work order (kernels_order.cu) only the turn-shaped rows are visited, heaviest board texture first
+    const int64_t n_work = order != nullptr ? (int64_t)order[29] : n;
     Turn4Smem &S = *reinterpret_cast<Turn4Smem *>(smem_raw);
     const uint32_t gid = threadIdx.x / kGT, tid = threadIdx.x % kGT;
     const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -111,13 +115,23 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
     // situations are claimed kClaimT at a time from a global counter (see kernels_hp_flop4.cu); nullptr = static striding
     const uint32_t n_all_groups = gridDim.x * kNG, my_group = blockIdx.x * kNG + gid;
     uint32_t claim_it = 0;
-    if (tid == 0) G.next_claim[0] = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT) : my_group * kClaimT;
+    auto make_claim = [&](uint32_t slot, uint32_t it) {
+        const uint32_t base = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT) : (it * n_all_groups + my_group) * kClaimT;
+        G.next_claim[slot] = base;
+#pragma unroll
+        for (uint32_t j = 0; j < (uint32_t)kClaimT; ++j) {
+            const int64_t v = (int64_t)base + j;
+            G.claim_rows[slot][j] = v < n_work ? (order != nullptr ? __ldg(order + kOrderHeader + n + v) : (uint32_t)v) : 0u;
+        }
+    };
+    if (tid == 0) make_claim(0, 0);
     for (;; ++claim_it) {
     tsync(gid);
     const int64_t claim_base = G.next_claim[claim_it & 1];
-    if (claim_base >= n) break;
+    if (claim_base >= n_work) break;
     bool next_claimed = false;
-    for (int64_t idx = claim_base; idx < n && idx < claim_base + kClaimT; ++idx) {
+    for (int64_t vidx = claim_base; vidx < n_work && vidx < claim_base + kClaimT; ++vidx) {
+        const int64_t idx = G.claim_rows[claim_it & 1][vidx - claim_base];
         tsync(gid);                                                                                 // (A)
         uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
         uint32_t cb[8];
@@ -377,9 +391,7 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         tsync(gid);                                                                                 // (D)
         if (!next_claimed) {
-            if (tid == 0)
-                G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT)
-                                                                : ((claim_it + 1) * n_all_groups + my_group) * kClaimT;
+            if (tid == 0) make_claim((claim_it + 1) & 1, claim_it + 1);
             next_claimed = true;
         }
         mbar_wait(bar1_s, parity);
@@ -586,14 +598,12 @@ hp_turn_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (k < peers.n) peers.p[k][idx * 16 + tid] = v;
         }
     }
-    if (!next_claimed && tid == 0)
-        G.next_claim[(claim_it + 1) & 1] = work_counter ? atomicAdd(work_counter, (unsigned)kClaimT)
-                                                        : ((claim_it + 1) * n_all_groups + my_group) * kClaimT;
+    if (!next_claimed && tid == 0) make_claim((claim_it + 1) & 1, claim_it + 1);
     }
 }
 
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    int *run_flag, const PeerOut &peers, cudaStream_t st) {
+                                    int *run_flag, const PeerOut &peers, cudaStream_t st, const uint32_t *order_scratch) {
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Turn4Smem);
     static_assert(sizeof(Turn4Smem) <= 227 * 1024, "fifteen situation groups must fit the 227 KB of one CTA");
@@ -604,7 +614,23 @@ cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int6
     // run_flag, when given, is the call's 16-byte slot: [0] flag word, [2] this kernel's work counter (zeroed with the slot)
     if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     count_launch(); hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, run_flag, 1u, peers,
-                                                                  run_flag ? reinterpret_cast<unsigned int *>(run_flag) + 2 : nullptr);
+                                                                  run_flag ? reinterpret_cast<unsigned int *>(run_flag) + 2 : nullptr,
+                                                                  order_scratch);
+    return cudaGetLastError();
+}
+
+// The same launch for the variant entry point: the slot only lends its work counter (word 2); the flag word is not consulted.
+cudaError_t launch_hp_turn_treys_v4_counter(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
+                                            int *slot, const PeerOut &peers, cudaStream_t st, const uint32_t *order_scratch) {
+    if (n == 0) return cudaSuccess;
+    if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
+    const size_t smem = sizeof(Turn4Smem);
+    cudaError_t e = cudaFuncSetAttribute(hp_turn_treys_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t blocks = sms;
+    if (blocks * kNG > n) blocks = (n + kNG - 1) / kNG;
+    count_launch(); hp_turn_treys_v4_kernel<<<(int)blocks, kThreadsT, smem, st>>>(sit, n, out, T, nullptr, 1u, peers,
+                                                                  reinterpret_cast<unsigned int *>(slot) + 2, order_scratch);
     return cudaGetLastError();
 }
 

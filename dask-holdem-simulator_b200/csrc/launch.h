@@ -62,13 +62,17 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
                                     bool closed_form_add = true, uint32_t *order_scratch = nullptr);
-// order_scratch: optional device buffer of flop_order_scratch_bytes(n) bytes; when given, the kernel is preceded by a pass that
-// classifies the rows by board texture and the situations are worked heaviest texture first (results still land by row number).
-size_t flop_order_scratch_bytes(int64_t n);
+// order_scratch: optional device buffer filled by launch_street_order (kernels_order.cu): the situations are then worked heaviest
+// board texture first (results still land by row number).
+constexpr uint32_t kOrderHeader = 128;        // words of counters in front of the two row lists
+size_t street_order_scratch_bytes(int64_t n);
+cudaError_t launch_street_order(const uint8_t *sit, int64_t n, uint32_t *scratch, int sms, cudaStream_t st);
 
 // Rank-multiset turn kernel (kernels_hp_turn4.cu): same contract as launch_hp_turn_treys, bit-identical counts, the default.
 cudaError_t launch_hp_turn_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
-                                    int *run_flag, const PeerOut &peers, cudaStream_t st);
+                                    int *run_flag, const PeerOut &peers, cudaStream_t st, const uint32_t *order_scratch = nullptr);
+cudaError_t launch_hp_turn_treys_v4_counter(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
+                                            int *slot, const PeerOut &peers, cudaStream_t st, const uint32_t *order_scratch);
 // Copies result rows of `out` to the peers: all rows (run_flag == nullptr) or, when run_flag is given, the five-card-board rows
 // and only if bit 1 of *run_flag is set (the rows the plain-enumeration kernel produced).
 cudaError_t launch_rows_to_peers(const uint8_t *sit, int64_t n, const uint32_t *out, const PeerOut &peers, int sms,

@@ -145,7 +145,8 @@ int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *
  * Rows with 4- or 5-card boards are left untouched. */
 int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
-/* The same for Treys-mode turn rows (four board cards): 4 = rank-multiset kernel (production), 3 = deduplicating 3-set walk.
+/* The same for Treys-mode turn rows (four board cards): 4 = rank-multiset kernel (production), 6 = the same working the rows in
+ * input order with static striding instead of heaviest board texture first, 3 = deduplicating 3-set walk.
  * Rows of other streets are left untouched. */
 int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 

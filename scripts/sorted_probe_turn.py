@@ -33,5 +33,14 @@ out = torch.empty((n, 16), dtype=torch.int32, device="cuda")
 for name, key in keys.items():
     order = np.argsort(key, kind="stable")
     d = torch.from_numpy(np.ascontiguousarray(sit[order])).cuda()
-    ms = timed(lambda: hb.hand_potential_counts(d, "treys", out=out, turn_variant=4))
+    ms = timed(lambda: hb.hand_potential_counts(d, "treys", out=out, turn_variant=6))
     print(f"{name:32s}: {ms:.4f} ms = {n / ms / 1e3:.1f} M situations/s", flush=True)
+
+d = torch.from_numpy(sit).cuda()
+for v, name in ((6, "library, input order (variant 6)"), (4, "library, own ordering pass")):
+    ms = timed(lambda: hb.hand_potential_counts(d, "treys", out=out, turn_variant=v))
+    print(f"{name:32s}: {ms:.4f} ms = {n / ms / 1e3:.1f} M situations/s", flush=True)
+ms = timed(lambda: hb.hand_potential_counts(d, "treys", out=out))
+print(f"{'holdem_hp_batch (all kernels)':32s}: {ms:.4f} ms = {n / ms / 1e3:.1f} M situations/s", flush=True)
+ref = hb.hand_potential_counts(d, "treys", turn_variant=3)
+print("equal to the 3-set kernel:", bool(torch.equal(ref, hb.hand_potential_counts(d, "treys"))), bool(torch.equal(ref, hb.hand_potential_counts(d, "treys", turn_variant=4))), bool(torch.equal(ref, hb.hand_potential_counts(d, "treys", turn_variant=6))))
