@@ -72,7 +72,6 @@ def load_reference():
     """Return the reference's HandCalculations module (CPU, unchanged)."""
     if not reference_available():
         raise FileNotFoundError(f"reference tree not found at {REFERENCE_DIR}")
-    os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
     _install_stubs()
     # Make sure OUR drop-in of the same name is not picked up instead.
     for name in ("HandCalculations", "utils", "pokerlib_to_treys"):
@@ -85,6 +84,9 @@ def load_reference():
     finally:
         sys.path.remove(REFERENCE_DIR)
     assert ref.__file__.startswith(REFERENCE_DIR), ref.__file__
+    # The reference picks `device` at import (HandCalculations.py:22) and reads it at call time: pin it to the CPU here instead
+    # of hiding the GPUs from the whole process through os.environ (a GPU test running later in the same session would lose them).
+    ref.device = "cpu"
     # keep the reference's helper modules from shadowing ours afterwards
     for name in ("HandCalculations", "utils", "pokerlib_to_treys"):
         sys.modules.pop(name, None)
