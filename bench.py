@@ -5,8 +5,10 @@
   python bench.py --impl reference [...]                       the reference's own CPU algorithm (oracle port)
 
 A step = one pass of the hot path over one batch: 65,536 random flop situations PER GPU (BASELINE.json configs[2];
-weak scaling, the situations of the batch are independent), HS + full HP enumeration in Treys mode, each rank writing
-its block of the [N,16] result and (N > 1) one in-place NCCL all-gather.  Prints ONE JSON line on rank 0.
+weak scaling, the situations of the batch are independent), HS + full HP enumeration in Treys mode through
+torch.ops.holdem.hp_out -> holdem_hp_batch; N > 1: each rank computes its block and the kernels store every result row into
+every rank's symmetric-memory buffer over NVLink (fused compute + all-gather; NCCL all-gather where that is unavailable).
+Every rank then recomputes the whole batch and compares.  Prints ONE JSON line on rank 0 (the only line on stdout).
 """
 import argparse
 import json
@@ -26,7 +28,6 @@ for _p in (PKG, ROOT):
 SITUATIONS_PER_GPU = 65536
 SEED = 20251019
 EVALS_PER_SITUATION = 1_072_353          # 1,070,190 + 1,081 + 1,082
-HASH_LOOKUPS_PER_SITUATION = 1_820 + 91 + 92   # what the rank-multiset kernel looks up in the 7-/5-card hash tables
 HOT_KERNEL = "hp_flop_treys_v4_kernel"
 METRIC = "flop_hs_hp_situations_per_sec"
 UNIT = "situations/s"
