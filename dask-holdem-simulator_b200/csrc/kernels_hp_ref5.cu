@@ -48,12 +48,15 @@ namespace {
 
 using namespace ms;
 
+#ifndef HOLDEM_R5_CTAS
+#define HOLDEM_R5_CTAS 5
+#endif
 constexpr int kR5Threads = 256;
 constexpr int kTPitch5 = 92;          // bytes per row of T
 constexpr int kPP5 = 91;
 constexpr int kMaxQ5 = 1176;          // C(49,2)
 constexpr int kMaxP5 = 1081;          // C(47,2)
-constexpr int kPDCap5 = 1024;         // holding descriptors of all suits: at most C(n,2) + 13 n + 91 per suit, n <= 11 cards of the suit unseen
+constexpr int kPDCap5 = 512;          // holding descriptors of all suits: C(n,2) [+ 13 n [+ 91]] per suit by its board cards; worst case 464 (river board 3 + 2)
 constexpr int kSeg5 = 96;             // steps per flush task: a step adds at most 9 to a packed 10-bit counter (1023)
 constexpr int kTRow5 = 8384;          // bytes per board of the global T tables (91 x 92 rounded up to a multiple of 16)
 constexpr int kMaxTaskGroups = 12;    // (suit, cards of Q in suit) classes
@@ -73,9 +76,11 @@ struct Ref5Smem {
     uint32_t h_np[kMaxTaskGroups], h_pdo[kMaxTaskGroups];   // per (suit, qtype) class before the live ones are compacted
     uint32_t n_groups, n_entries, next_task, claim;
     uint32_t nL1[2], nL0;              // merged runout lanes per list
-    uint32_t A1[2][768];               // runouts with ONE card in a suit holding >= 2 board cards, counted by (rank of that card, rank
-                                       // of the other card, our category): 13 x 13 x 9 counters, two 16-bit counters per word
-    uint32_t A0[416];                  // runouts WITHOUT a card of the suit holding >= 3 board cards, by (rank pair, our category)
+    uint32_t A1[2][192];               // runouts with ONE card in a suit holding >= 2 board cards, counted by (rank of that card, rank
+                                       // of the other card, our category): 13 x 13 x 9 counters of 4 bits (<= 3 cards of a rank lie
+                                       // outside a suit), eight per word
+    uint32_t A0[104];                  // runouts WITHOUT a card of the suit holding >= 3 board cards, by (rank pair, our category):
+                                       // 91 x 9 counters of 4 bits (<= 9 such card pairs per rank pair)
     uint32_t L1[2][512];               // non-zero entries of A1 / A0: key | multiplicity << 16 -- the lanes of those runout classes
     uint32_t L0[320];
     uint16_t pairs[kMaxQ5 + 8];        // colex pairs i | j << 8 (static)
@@ -171,7 +176,7 @@ cudaError_t launch_ref_t_table(uint8_t *table, int k, int sms, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(kR5Threads)
+__global__ void __launch_bounds__(kR5Threads, HOLDEM_R5_CTAS)
 hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T, uint32_t one,
                int *__restrict__ bad_flag, unsigned int *__restrict__ work_counter, PeerOut peers) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -259,8 +264,8 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             slotmap |= (bsq >= 2 ? n_slots++ : 15u) << (4 * su);
             if (bsq >= 3) a0suit = su;
         }
-        if (n_slots) for (uint32_t i = tid; i < n_slots * 768u; i += kR5Threads) (&S.A1[0][0])[i] = 0;
-        if (a0suit < 4) for (uint32_t i = tid; i < 416u; i += kR5Threads) S.A0[i] = 0;
+        if (n_slots) for (uint32_t i = tid; i < n_slots * 192u; i += kR5Threads) (&S.A1[0][0])[i] = 0;
+        if (a0suit < 4) for (uint32_t i = tid; i < 104u; i += kR5Threads) S.A0[i] = 0;
         if (tid < 3) (&S.nL1[0])[tid] = 0;          // nL1[0], nL1[1], nL0
         if (tid == 3) S.n_entries = 0;
         if (warp == 0) {
@@ -407,12 +412,12 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             // the runout as a lane of the flush part: with a card outside a suit it matters through that card's RANK only
             if (si != sj) {                                  // exactly one card in suit si and one in suit sj
                 const uint32_t sl_i = (slotmap >> (4 * si)) & 15u, sl_j = (slotmap >> (4 * sj)) & 15u;
-                if (sl_i < 2) { const uint32_t k = (ri * 13 + rj) * 9 + o; atomicAdd(&S.A1[sl_i][k >> 1], 1u << (16 * (k & 1u))); }
-                if (sl_j < 2) { const uint32_t k = (rj * 13 + ri) * 9 + o; atomicAdd(&S.A1[sl_j][k >> 1], 1u << (16 * (k & 1u))); }
+                if (sl_i < 2) { const uint32_t k = (ri * 13 + rj) * 9 + o; atomicAdd(&S.A1[sl_i][k >> 3], 1u << (4 * (k & 7u))); }
+                if (sl_j < 2) { const uint32_t k = (rj * 13 + ri) * 9 + o; atomicAdd(&S.A1[sl_j][k >> 3], 1u << (4 * (k & 7u))); }
             }
             if (a0suit < 4 && si != a0suit && sj != a0suit) {
                 const uint32_t k = qp * 9 + o;
-                atomicAdd(&S.A0[k >> 1], 1u << (16 * (k & 1u)));
+                atomicAdd(&S.A0[k >> 3], 1u << (4 * (k & 7u)));
             }
         }
         if (warp == 0) {
@@ -454,7 +459,7 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
         {
             auto compact16 = [&](const uint32_t *arr, uint32_t n_keys, uint32_t *list, uint32_t *counter) {
                 for (uint32_t e = tid; e < (n_keys + kR5Threads - 1) / kR5Threads * kR5Threads; e += kR5Threads) {
-                    const uint32_t c = e < n_keys ? (arr[e >> 1] >> (16 * (e & 1u))) & 0xFFFFu : 0u;
+                    const uint32_t c = e < n_keys ? (arr[e >> 3] >> (4 * (e & 7u))) & 15u : 0u;
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, c != 0);
                     uint32_t base = 0;
                     if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
