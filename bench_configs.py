@@ -244,6 +244,16 @@ def main():
         c4[name] = entry
     c4["total_ms"] = total_ms
     c4["hands_per_sec"] = args.hands / (total_ms * 1e-3)
+    # showdown of every table (GameBoard.determine_winner): one fused kernel vs the evaluator launch + torch reductions
+    ms_f = timed(lambda: hb.table_showdown(d_hole, d_board), reps=5, warm=2)
+    ms_e = timed(lambda: (lambda r: (table.winners(r, "best"), table.winners(r, "reference")))(table.showdown_ranks(d_hole, d_board)),
+                 reps=5, warm=2)
+    ranks_f, best_f, ref_f = table.showdown(d_hole, d_board)
+    ranks_e = table.showdown_ranks(d_hole, d_board)
+    c4["showdown"] = {"fused_kernel_ms": ms_f, "evaluator_plus_torch_ms": ms_e, "hands_per_sec": args.hands / (ms_f * 1e-3),
+                      "equal": bool(torch.equal(ranks_f, ranks_e) and torch.equal(best_f, table.winners(ranks_e, "best"))
+                                    and torch.equal(ref_f, table.winners(ranks_e, "reference"))),
+                      "split_pots": int((best_f.sum(dim=1) > 1).sum())}
     res["config4_22_seat_table"] = c4
 
     text = json.dumps(res, indent=1)

@@ -706,6 +706,18 @@ int holdem_table_hp_batch(const uint8_t *d_hole, const uint8_t *d_board, int64_t
     return HOLDEM_OK;
 }
 
+int holdem_table_showdown(const uint8_t *d_hole, const uint8_t *d_board, const uint8_t *d_active, int64_t hands, int seats,
+                          uint16_t *d_ranks, uint32_t *d_winners, void *stream) {
+    DeviceState *S = nullptr;
+    int rc = current_state(&S);
+    if (rc) return rc;
+    if (hands < 0 || (hands > 0 && (!d_hole || !d_board || !d_ranks || !d_winners)))
+        return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative size");
+    if (seats < 1 || seats > 22) return fail(HOLDEM_ERR_BAD_ARG, "seats must be 1..22 (GameBoard.MAX_PLAYERS = 22), got %d", seats);
+    CUDA_TRY(launch_table_showdown(S->T, d_hole, d_board, d_active, hands, seats, d_ranks, d_winners, S->sms, (cudaStream_t)stream));
+    return HOLDEM_OK;
+}
+
 // ---- result-row hash, decision tree, wire-format packing (kernels_aux.cu) ------------------------------------------------
 unsigned long long holdem_kernel_launches(void) { return holdem::g_kernel_launches.load(std::memory_order_relaxed); }
 

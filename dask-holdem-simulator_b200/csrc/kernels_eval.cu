@@ -277,6 +277,49 @@ cudaError_t launch_eval_batch(const DevTables &T, const uint8_t *cards, int n_ca
 }
 
 // =====================================================================================================================
+// Whole-table showdown (GameBoard.determine_winner, GameBoard.py:204-229): one warp per hand, one lane per seat (<= 22,
+// GameBoard.py:12).  Each lane ranks its seat's seven cards (two hole cards + the shared five-card board) with the strict
+// routine, the warp reduces the best (lowest Treys rank: the correct winner) and the worst (highest: what the reference's
+// max() at GameBoard.py:210 picks) over the active seats, and writes the ranks plus two winner bit masks per hand.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+table_showdown_kernel(const uint8_t *__restrict__ hole, const uint8_t *__restrict__ board, const uint8_t *__restrict__ active,
+                      int64_t hands, int seats, uint16_t *__restrict__ ranks, uint32_t *__restrict__ winners, DevTables T) {
+    __shared__ uint32_t s_cardkey[64];
+    if (threadIdx.x < 64) s_cardkey[threadIdx.x] = threadIdx.x < 52 ? c_rank_key[threadIdx.x % 13] : 0u;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const NfHash h7 = T.nf[2];
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t hnd = (int64_t)blockIdx.x * 8 + warp; hnd < hands; hnd += n_warps) {
+        uint32_t r = 0;
+        bool act = false;
+        if ((int)lane < seats) {
+            const uint8_t *b = board + 5 * hnd, *hc = hole + 2 * (hnd * seats + lane);
+            uint2 w;
+            w.x = hc[0] | (hc[1] << 8) | (b[0] << 16) | ((uint32_t)b[1] << 24);
+            w.y = b[2] | (b[3] << 8) | (b[4] << 16) | 0xFF000000u;
+            r = eval_row<7>(w, s_cardkey, T.flush, h7);            // 0 = malformed seat (bad card or duplicate)
+            act = (active == nullptr || active[hnd * seats + lane] != 0) && r != 0;
+            ranks[hnd * seats + lane] = (uint16_t)r;
+        }
+        const uint32_t best = __reduce_min_sync(0xFFFFFFFFu, act ? r : 0xFFFFu);
+        const uint32_t worst = __reduce_max_sync(0xFFFFFFFFu, act ? r : 0u);
+        const uint32_t mb = __ballot_sync(0xFFFFFFFFu, act && r == best), mw = __ballot_sync(0xFFFFFFFFu, act && r == worst);
+        if (lane == 0) { winners[2 * hnd] = mb; winners[2 * hnd + 1] = mw; }
+    }
+}
+
+cudaError_t launch_table_showdown(const DevTables &T, const uint8_t *hole, const uint8_t *board, const uint8_t *active,
+                                  int64_t hands, int seats, uint16_t *ranks, uint32_t *winners, int sms, cudaStream_t st) {
+    if (hands == 0) return cudaSuccess;
+    int64_t blocks = (hands + 7) / 8;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    count_launch(); table_showdown_kernel<<<(int)blocks, 256, 0, st>>>(hole, board, active, hands, seats, ranks, winners, T);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================================
 // Literal category ranker over rows of n_cards (2..9) cards, duplicates allowed.
 // =====================================================================================================================
 __global__ void __launch_bounds__(256)

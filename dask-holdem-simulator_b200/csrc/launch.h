@@ -26,6 +26,9 @@ inline void count_launch() { g_kernel_launches.fetch_add(1ull, std::memory_order
 // strict: also detect duplicate cards inside a row (builds the card set; ~1.5x the instructions of the fast path).
 cudaError_t launch_eval_batch(const DevTables &T, const uint8_t *cards, int n_cards, int64_t n, uint16_t *out,
                               int sms, bool strict, cudaStream_t st);
+// Whole-table showdown: ranks[hands, seats] and per hand two seat bit masks (best = lowest rank, reference rule = highest rank).
+cudaError_t launch_table_showdown(const DevTables &T, const uint8_t *hole, const uint8_t *board, const uint8_t *active,
+                                  int64_t hands, int seats, uint16_t *ranks, uint32_t *winners, int sms, cudaStream_t st);
 cudaError_t launch_category_batch(const uint8_t *cards, int n_cards, int row_stride, int64_t n, uint8_t *out,
                                   int sms, cudaStream_t st);
 // variant 0 = tuple kernel (production), 1 = the older chunk-per-thread kernel.

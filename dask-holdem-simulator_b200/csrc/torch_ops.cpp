@@ -12,6 +12,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/library.h>
 
+#include <tuple>
 #include <vector>
 
 #include "../../include/holdem_b200.h"
@@ -115,6 +116,31 @@ at::Tensor table_hp(const at::Tensor &hole, const at::Tensor &board, int64_t n_b
     return out;
 }
 
+// Whole-table showdown (GameBoard.py:204-229) -> (ranks int16 [H,S], winners int32 [H,2]: seat bit masks, best / reference rule).
+std::tuple<at::Tensor, at::Tensor> table_showdown(const at::Tensor &hole, const at::Tensor &board,
+                                                  const c10::optional<at::Tensor> &active) {
+    TORCH_CHECK(hole.is_cuda() && board.is_cuda(), "hole / board must be CUDA tensors (no CPU fallback)");
+    TORCH_CHECK(hole.scalar_type() == at::kByte && hole.is_contiguous() && hole.dim() == 3 && hole.size(2) == 2,
+                "hole must be a contiguous uint8 [H,S,2] tensor");
+    TORCH_CHECK(board.scalar_type() == at::kByte && board.is_contiguous() && board.dim() == 2 && board.size(1) == 5 &&
+                    board.size(0) == hole.size(0) && board.device() == hole.device(),
+                "board must be a contiguous uint8 [H,5] tensor on the device of hole");
+    const uint8_t *act = nullptr;
+    at::Tensor act_u8;
+    if (active.has_value()) {
+        TORCH_CHECK(active->is_cuda() && active->device() == hole.device() && active->numel() == hole.size(0) * hole.size(1),
+                    "active must be [H,S] on the device of hole");
+        act_u8 = active->to(at::kByte).contiguous();
+        act = act_u8.data_ptr<uint8_t>();
+    }
+    Enter e(hole);
+    at::Tensor ranks = at::empty({hole.size(0), hole.size(1)}, hole.options().dtype(at::kShort));
+    at::Tensor winners = at::empty({hole.size(0), 2}, hole.options().dtype(at::kInt));
+    check(holdem_table_showdown(hole.data_ptr<uint8_t>(), board.data_ptr<uint8_t>(), act, hole.size(0), (int)hole.size(1),
+                                (uint16_t *)ranks.data_ptr(), (uint32_t *)winners.data_ptr(), e.stream));
+    return std::make_tuple(ranks, winners);
+}
+
 // Decision.decision_based_on_blind_position (Decision.py:4-48) straight from result rows; pos: uint8 [N] or None + pos_all.
 at::Tensor decide_from_counts(const at::Tensor &rows, const c10::optional<at::Tensor> &pos, int64_t pos_all) {
     require(rows, "rows", at::kInt, HOLDEM_HP_ROW);
@@ -184,6 +210,7 @@ TORCH_LIBRARY(holdem, m) {
     m.def("hp_out(Tensor sit, int mode, Tensor(a!) out) -> ()");
     m.def("hp_peers(Tensor sit, int mode, Tensor(a!) out, int[] peer_ptrs) -> ()");
     m.def("table_hp(Tensor hole, Tensor board, int n_board, int mode) -> Tensor");
+    m.def("table_showdown(Tensor hole, Tensor board, Tensor? active) -> (Tensor, Tensor)");
     m.def("decide(Tensor hand_strength, Tensor ppot, Tensor npot, Tensor? pos, int pos_all) -> Tensor");
     m.def("decide_from_counts(Tensor rows, Tensor? pos, int pos_all) -> Tensor");
     m.def("pack_rank_major(Tensor hole, Tensor board) -> Tensor");
@@ -199,6 +226,7 @@ TORCH_LIBRARY_IMPL(holdem, CUDA, m) {
     m.impl("hp_out", hp_out);
     m.impl("hp_peers", hp_peers);
     m.impl("table_hp", table_hp);
+    m.impl("table_showdown", table_showdown);
     m.impl("decide", decide);
     m.impl("decide_from_counts", decide_from_counts);
     m.impl("pack_rank_major", pack_rank_major);

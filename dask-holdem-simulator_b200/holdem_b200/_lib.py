@@ -54,6 +54,7 @@ SYMBOLS = {
     "holdem_decide_from_counts": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
     "holdem_pack_rank_major": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "holdem_kernel_launches": (ctypes.c_ulonglong, []),
+    "holdem_table_showdown": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "holdem_table_hp_batch": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
     "holdem_hp_batch_direct": (_i, [_vp, _i64, _i, _vp, _vp]),
     "holdem_hp_batch_peers": (_i, [_vp, _i64, _i, _vp, ctypes.POINTER(_vp), _i, _vp]),

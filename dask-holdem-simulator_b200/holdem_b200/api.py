@@ -23,7 +23,7 @@ __all__ = [
     "hand_potential_counts", "flop_phase_cycles", "exhaustive7", "hs_from_counts", "potentials_from_counts",
     "normalised_potentials", "ehs_from_counts", "evaluate_host", "category_host", "hand_strength_counts_host",
     "hand_potential_counts_host", "smem_gather_microbench", "int_issue_microbench", "EVALS_PER_FLOP_SITUATION",
-    "rows_hash", "rows_hash_host", "table_hand_potential_counts", "kernel_launches", "pack_rank_major",
+    "rows_hash", "rows_hash_host", "table_hand_potential_counts", "table_showdown", "kernel_launches", "pack_rank_major",
 ]
 
 # algorithmic evaluations per situation
@@ -185,6 +185,29 @@ def table_hand_potential_counts(hole: torch.Tensor, board: torch.Tensor, n_board
         _lib.check(lib.holdem_table_hp_batch(hole.data_ptr(), board.data_ptr(), hole.shape[0], hole.shape[1], int(n_board),
                                              mode_id(mode), out.data_ptr(), st))
     return out
+
+
+def table_showdown(hole: torch.Tensor, board: torch.Tensor, active: torch.Tensor = None, binding: str = "ops"):
+    """Showdown of whole tables in ONE kernel (GameBoard.determine_winner, GameBoard.py:204-229): hole uint8 [H,S,2], board
+    uint8 [H,5], active optional [H,S] -> (ranks int16 [H,S], winners int32 [H,2]).  winners[:,0] is the seat bit mask of the
+    best hand(s) among the active seats (lowest Treys rank), winners[:,1] of the seats the reference picks (it takes max() of
+    the Treys values, GameBoard.py:210)."""
+    _require_cuda(hole, "hole", torch.uint8)
+    _require_cuda(board, "board", torch.uint8, 5)
+    if hole.dim() != 3 or hole.shape[2] != 2 or board.shape[0] != hole.shape[0] or board.device != hole.device:
+        raise ValueError("expected hole [H,S,2] and board [H,5] on one device")
+    if active is not None and (not active.is_cuda or active.device != hole.device or tuple(active.shape) != tuple(hole.shape[:2])):
+        raise ValueError("active must be [H,S] on the device of hole")
+    ops = _ops_ns(binding)
+    if ops is not None:
+        return ops.table_showdown(hole, board, active)
+    act = None if active is None else active.to(torch.uint8).contiguous()
+    ranks = torch.empty(tuple(hole.shape[:2]), dtype=torch.int16, device=hole.device)
+    win = torch.empty((hole.shape[0], 2), dtype=torch.int32, device=hole.device)
+    with _enter(hole) as (lib, st):
+        _lib.check(lib.holdem_table_showdown(hole.data_ptr(), board.data_ptr(), 0 if act is None else act.data_ptr(),
+                                             hole.shape[0], hole.shape[1], ranks.data_ptr(), win.data_ptr(), st))
+    return ranks, win
 
 
 def flop_phase_cycles(sit: torch.Tensor):

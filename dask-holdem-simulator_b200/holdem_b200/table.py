@@ -3,13 +3,14 @@
 * deal_tables(): BASELINE configs[3] generator -- one shuffle per hand, seat i holds cards 2i, 2i+1, board = cards 44..48.
 * showdown_ranks(): Treys rank of every seat's 7 cards in one evaluator launch (what GameBoard.determine_winner,
   GameBoard.py:204-229, obtains seat by seat through evaluate_best_hand).
+* showdown(): ranks AND both winner masks of every hand from one fused kernel (a warp per hand, a lane per seat).
 * winners(): boolean winner mask.  rule="best": lowest Treys rank wins (correct poker); rule="reference": the seats the
   reference's determine_winner picks -- it takes max() of the Treys values (GameBoard.py:210), i.e. the WORST hands.
 """
 import numpy as np
 import torch
 
-from .api import evaluate
+from .api import evaluate, table_showdown
 
 
 def deal_tables(n_hands: int, seed: int = 20251020, seats: int = 22):
@@ -44,6 +45,14 @@ def showdown_ranks(hole: torch.Tensor, board: torch.Tensor) -> torch.Tensor:
     rows[:, :, 0:2] = hole
     rows[:, :, 2:7] = board[:, None, :]
     return evaluate(rows.reshape(n * seats, 8), 7).reshape(n, seats)
+
+
+def showdown(hole: torch.Tensor, board: torch.Tensor, active: torch.Tensor = None):
+    """-> (ranks int16 [N,S], best bool [N,S], reference bool [N,S]) from the fused showdown kernel: `best` marks the seats that
+    take (or split) the pot, `reference` the seats GameBoard.determine_winner picks (max() of the Treys values, GameBoard.py:210)."""
+    ranks, masks = table_showdown(hole, board, active)
+    bit = torch.arange(hole.shape[1], device=hole.device, dtype=torch.int32)
+    return ranks, ((masks[:, 0:1] >> bit) & 1).bool(), ((masks[:, 1:2] >> bit) & 1).bool()
 
 
 def winners(ranks: torch.Tensor, rule: str = "best", active: torch.Tensor = None) -> torch.Tensor:

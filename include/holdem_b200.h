@@ -132,6 +132,15 @@ int holdem_hp_batch_peers(const uint8_t *d_sit, int64_t n, int mode, uint32_t *d
 int holdem_table_hp_batch(const uint8_t *d_hole, const uint8_t *d_board, int64_t hands, int seats, int n_board, int mode,
                           uint32_t *d_out, void *stream);
 
+/* Showdown of whole tables in one pass (GameBoard.determine_winner, GameBoard.py:204-229, which evaluates seat by seat through
+ * evaluate_best_hand): d_hole uint8[hands,seats,2], d_board uint8[hands,5], d_active optional uint8[hands,seats] (NULL = every
+ * seat is in the hand).  d_ranks uint16[hands,seats]: Treys rank of every seat (0 = malformed seat: bad or duplicate card);
+ * d_winners uint32[hands,2]: bit s of word 0 = seat s holds the BEST hand among the active seats (lowest rank: the correct
+ * winner, ties share), of word 1 = seat s is what the reference picks (GameBoard.py:210 takes max() of the Treys values, i.e.
+ * the worst hand). */
+int holdem_table_showdown(const uint8_t *d_hole, const uint8_t *d_board, const uint8_t *d_active, int64_t hands, int seats,
+                          uint16_t *d_ranks, uint32_t *d_winners, void *stream);
+
 /* Same results as holdem_hp_batch computed by the plain (non-deduplicating) enumeration kernel: one opponent
  * evaluation per (opponent holding, runout) pair.  Kept as the independent second implementation the parity
  * tests cross-check the deduplicating flop / turn kernels against; it is also what holdem_hp_batch itself runs for

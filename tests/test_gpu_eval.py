@@ -162,3 +162,38 @@ def test_showdown_whole_table(hb, oracle):
     ref = table.winners(ranks, "reference").cpu().numpy()
     assert np.array_equal(best, want == want.min(axis=1, keepdims=True))
     assert np.array_equal(ref, want == want.max(axis=1, keepdims=True))
+
+
+def test_fused_showdown_kernel_equals_evaluator_path(hb, oracle):
+    """The one-kernel showdown (a warp per hand, a lane per seat) returns the evaluator's ranks and the winner masks of
+    table.winners under both rules, with and without folded seats, through both bindings; ranks pinned by the oracle."""
+    from holdem_b200 import table
+    for seats, hands in ((22, 3000), (9, 1000), (2, 257), (1, 5)):
+        hole, board = table.deal_tables(hands, seed=100 + seats, seats=max(seats, 2))
+        hole = hole[:, :seats].copy()
+        h, b = torch.from_numpy(hole).cuda(), torch.from_numpy(board).cuda()
+        ranks, best, ref = table.showdown(h, b)
+        want = table.showdown_ranks(h, b)
+        assert torch.equal(ranks, want)
+        assert torch.equal(best, table.winners(want, "best")) and torch.equal(ref, table.winners(want, "reference"))
+        rows = np.full((hands * seats, 8), 0xFF, dtype=np.uint8)
+        rows[:, 0:2] = hole.reshape(-1, 2)
+        rows[:, 2:7] = np.repeat(board, seats, axis=0)
+        assert np.array_equal(ranks.cpu().numpy().astype(np.uint16).ravel(), oracle.treys_evaluate_batch(rows, 7))
+        act = torch.from_numpy(np.random.default_rng(seats).random((hands, seats)) < 0.6).cuda()
+        r2, best2, ref2 = table.showdown(h, b, act)
+        assert torch.equal(r2, want)
+        assert torch.equal(best2, table.winners(want, "best", act)) and torch.equal(ref2, table.winners(want, "reference", act))
+        rc, mc = hb.api.table_showdown(h, b, act, binding="ctypes")
+        ro, mo = hb.api.table_showdown(h, b, act)
+        assert torch.equal(rc, ro) and torch.equal(mc, mo)
+    # a malformed seat (duplicate card) ranks 0 and never wins; an empty batch is a no-op
+    hole, board = table.deal_tables(4, seed=1, seats=4)
+    hole[2, 1] = [board[2, 0], hole[2, 1, 1]]
+    ranks, best, ref = table.showdown(torch.from_numpy(hole).cuda(), torch.from_numpy(board).cuda())
+    assert int(ranks[2, 1]) == 0 and not bool(best[2, 1]) and not bool(ref[2, 1]) and bool(best[2].any())
+    e = table.showdown(torch.empty((0, 22, 2), dtype=torch.uint8).cuda(), torch.empty((0, 5), dtype=torch.uint8).cuda())
+    assert e[0].shape == (0, 22) and e[1].shape == (0, 22)
+    with pytest.raises((RuntimeError, ValueError)):
+        hb.api.table_showdown(torch.zeros((1, 23, 2), dtype=torch.uint8).cuda(), torch.zeros((1, 5), dtype=torch.uint8).cuda(),
+                              binding="ctypes")
