@@ -469,7 +469,8 @@ static cudaError_t hp_dispatch(DeviceState &S, const uint8_t *d_sit, int64_t n, 
         if (e != cudaSuccess) { cudaFreeAsync(order, st); return e; }
     }
     e = old_flop ? launch_hp_flop_treys(S.T, d_sit, n, d_out, S.sms, flag, impl.flop, st)
-                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st, impl.flop != 5, order);
+                 : launch_hp_flop_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, nullptr, fused ? peers : none, st, impl.flop != 5, order,
+                                           impl.flop != 7);
     if (e == cudaSuccess)
         e = old_turn ? launch_hp_turn_treys(S.T, d_sit, n, d_out, S.sms, flag, st)
                      : launch_hp_turn_treys_v4(S.T, d_sit, n, d_out, S.sms, flag, fused ? peers : none, st, order);
@@ -528,7 +529,7 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (variant < 2 || variant > 6) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
+    if (variant < 2 || variant > 7) return fail(HOLDEM_ERR_BAD_ARG, "unknown flop kernel variant %d", variant);
     FlagSlot slot;
     CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
     if (variant >= 4) {
@@ -539,7 +540,7 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
             if (eo != cudaSuccess) { cudaFreeAsync(order, (cudaStream_t)stream); CUDA_TRY(eo); }
         }
         cudaError_t e = launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, nullptr, PeerOut{}, (cudaStream_t)stream,
-                                                variant != 5, order);
+                                                variant != 5, order, variant != 7);
         if (order != nullptr) cudaFreeAsync(order, (cudaStream_t)stream);
         CUDA_TRY(e);
     } else CUDA_TRY(launch_hp_flop_treys(S->T, d_sit, n, d_out, S->sms, slot.ptr, variant, (cudaStream_t)stream));
@@ -643,8 +644,8 @@ int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, i
     int rc = current_state(&S);
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
-    if (flop_variant < 2 || flop_variant > 6 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
-        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..6, turn 3..4, river 0..1)");
+    if (flop_variant < 2 || flop_variant > 7 || (turn_variant != 3 && turn_variant != 4) || river_variant < 0 || river_variant > 1)
+        return fail(HOLDEM_ERR_BAD_ARG, "unknown kernel variant (flop 2..7, turn 3..4, river 0..1)");
     HpImpl impl;
     impl.flop = flop_variant == 6 ? 4 : flop_variant; impl.order = flop_variant != 6; impl.turn = turn_variant; impl.river = river_variant;
     CUDA_TRY(hp_dispatch(*S, d_sit, n, HOLDEM_MODE_TREYS, d_out, (cudaStream_t)stream, PeerOut{}, nullptr, impl));

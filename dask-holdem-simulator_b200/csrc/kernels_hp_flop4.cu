@@ -76,6 +76,7 @@ constexpr int kSeg = 64;           // longest step segment of a flush task (pack
 constexpr int kPD = 320;           // step descriptors per situation: at most 3 x 66 (rainbow) or 45 + 14 x 11 + 91 + 66
 constexpr int kMaxGroups = 12;
 constexpr int kProfSlots = 8;
+constexpr int kBitEntries = 160;   // entries of the generic part whose compare bits are kept: 91 + C(10,2) = 136
 constexpr int kClaim = HOLDEM_F4_CLAIM;           // situations a group claims from the global work counter at a time
 
 struct Flop4Group {                    // one situation in flight
@@ -114,12 +115,22 @@ struct Flop4Group {                    // one situation in flight
     uint8_t ns[4];
     uint8_t u[16];                     // unseen cards per rank
     uint8_t clsr[96];                  // per rank pair: flop class from ranks alone (3 = impossible pair)
+    // ---- bit-parallel undo half (kBits): 91-bit sets of rank pairs, bit pp of word pp / 32 ----------------------------------
+    uint32_t LB[3][kBitEntries], GB[3][kBitEntries];   // per entry e of the generic part (91 merged runouts, then the runouts that
+                                       // complete our flush when they are the pairs of ten cards): { pp : our7[e] < T[e][pp] } and
+                                       // { ... > ... }, written by the generic tasks (the two halves share word 1: atomicOr onto zeroed words)
+    uint32_t BC[4][3][3];              // [suit][class][word]: holdings with both cards in s, by rank pair
+    uint32_t XC[2][2][3][3];           // [which card is in s: lo / hi][weight bit][class][word]: holdings {a in s, c outside s} of the
+                                       // suit with two or more board cards, weight = unseen cards of c's rank outside s
+    uint32_t YC[4][3][3];              // [weight bit][class][word]: holdings without a card of s (monotone boards)
+    uint32_t next_ftask;
 };
 
 struct Flop4Smem {
     uint16_t flush[kFlushEntries];     // flush[fold(mask)]
     uint16_t pairs[kPairs4 + 3];       // colex pairs i | j << 8 of 47 positions
     uint8_t ppxy[96];                  // rank pair -> x | y << 4
+    uint32_t lo_t[14][3], hi_t[14][3]; // rank r -> the rank pairs whose lower / higher rank is r (row 13: empty)
     Flop4Group G[kGroups];
 };
 
@@ -128,7 +139,7 @@ __device__ __forceinline__ void group_sync(uint32_t gid) { group_sync_n<kGroupTh
 
 }  // namespace
 
-template <bool kProf, bool kFastAdd>
+template <bool kProf, bool kFastAdd, bool kBits>
 __global__ void __launch_bounds__(kThreads4, 1)
 hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict__ out, DevTables T,
                         int *__restrict__ other_rows, unsigned long long *__restrict__ prof, uint32_t one, PeerOut peers,
@@ -152,6 +163,18 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             uint32_t y = 0;
             while (tri(y + 1) <= threadIdx.x) ++y;
             S.ppxy[threadIdx.x] = threadIdx.x < kPP ? (uint8_t)((threadIdx.x - tri(y)) | (y << 4)) : (uint8_t)0xFF;
+        }
+        if (kBits && threadIdx.x >= 128 && threadIdx.x < 128 + 84) {      // lo_t / hi_t: 2 x 14 rows x 3 words
+            const uint32_t k = threadIdx.x - 128, hi_tab = k / 42u, r = (k % 42u) / 3u, w = k % 3u;
+            uint32_t m = 0;
+            for (uint32_t b = 0; b < 32; ++b) {
+                const uint32_t pp = 32u * w + b;
+                uint32_t y = 0;
+                while (tri(y + 1) <= pp) ++y;
+                const uint32_t x = pp - tri(y);
+                if (pp < (uint32_t)kPP && (hi_tab ? y : x) == r) m |= 1u << b;
+            }
+            (hi_tab ? S.hi_t : S.lo_t)[r][w] = m;
         }
         if (tid < kProfSlots) G.prof[tid] = 0;
         if (tid == 0) {
@@ -242,6 +265,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         if (tid < 4) { G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu; G.hist_none[tid] = 0; G.Wt0[tid] = 0; G.Ht[tid] = 0; }
         if (tid >= 32 && tid < 96) (&G.Wc0[0][0])[tid - 32] = 0;
         if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
+        if (kBits) { G.LB[1][tid] = 0; G.GB[1][tid] = 0; }
         if (warp == 0) {
             // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
             const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
@@ -302,7 +326,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                                                                      : (rank_lanes ? (uint32_t)kPP : choose2u(nns)));
                 const uint32_t np = need == 2 ? len2 : (need == 1 ? len1 : len0);
                 const bool live = lane < 12 && bs != 0 && k >= 3 && nq != 0 && np != 0;
-                const uint32_t nseg = (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
+                // (kBits: only the runouts that complete our flush without being the pairs of ten cards still walk the whole step list)
+                const bool whole_list = kBits && (hs_s + qtype < 5u || hs_s == 3u);
+                const uint32_t nseg = whole_list ? 1u : (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
                 const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
                 const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
                 const uint32_t gi = __popc(livem & ltm);
@@ -325,6 +351,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     G.n_groups = __popc(livem);
                     G.pd_total = pdo + len;
                     G.next_task = 0;
+                    G.next_ftask = 0;
                     G.n_ext = 0;
                 }
             }
@@ -382,11 +409,51 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t xy = S.ppxy[min(pp, 90u)], x = xy & 15u, y = xy >> 4;
                 const uint32_t ux = G.u[x], uy = G.u[y];
                 const uint32_t cnt = pp < (uint32_t)kPP ? (x != y ? ux * uy : (ux ? choose2u(ux) : 0u)) : 0u;
-                const uint32_t cl = G.clsr[min(pp, 90u)];
+                const uint32_t cl = pp < (uint32_t)kPP ? (uint32_t)G.clsr[min(pp, 90u)] : 3u;
 #pragma unroll
                 for (uint32_t c = 0; c < 3; ++c) {
                     const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cl == c ? cnt : 0u);
                     if (lane == 0 && v) atomicAdd(&G.cnt[6 + c], v);
+                }
+                if (kBits) {
+                    // ---- the undo half of the flush part as sets of rank pairs (this thread = rank pair pp = (x <= y)) -------------
+                    uint32_t s2 = 4;                                                     // the suit with two or more board cards
+#pragma unroll 1
+                    for (uint32_t s = 0; s < 4; ++s) {
+                        const uint32_t bs = (bsuit >> (4 * s)) & 15u;
+                        if (bs == 0) continue;                                           // (uniform over the group)
+                        if (bs >= 2) s2 = s;
+                        const uint32_t sm = G.smask[s];
+                        const bool both = x != y && ((sm >> x) & (sm >> y) & 1u);
+#pragma unroll
+                        for (uint32_t c = 0; c < 3; ++c) {
+                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, both && cl == c);
+                            if (lane == 0) G.BC[s][c][warp] = m;
+                        }
+                    }
+                    if (s2 < 4) {
+                        const uint32_t sm = G.smask[s2], ax = (sm >> x) & 1u, ay = (sm >> y) & 1u;
+                        const uint32_t bx = ux - ax, by = uy - ay;                       // unseen cards of the rank outside s (<= 3)
+                        const uint32_t w1 = ax ? by : 0u;                                // {a = the lower rank's card of s, c of rank y}
+                        const uint32_t w2 = (x != y && ay) ? bx : 0u;                    // {a = the higher rank's card of s, c of rank x}
+                        const uint32_t wy = m3 ? (x != y ? bx * by : (bx ? choose2u(bx) : 0u)) : 0u;   // no card in s (<= 9)
+#pragma unroll 1
+                        for (uint32_t j = 0; j < (m3 ? 10u : 6u); ++j) {                 // j = 2 * class + k (w1, w2), 6 + k (wy, three classes)
+                            if (j < 6) {
+                                const uint32_t c = j >> 1, k = j & 1u;
+                                const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, ((w1 >> k) & 1u) && cl == c);
+                                const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, ((w2 >> k) & 1u) && cl == c);
+                                if (lane == 0) { G.XC[0][k][c][warp] = m1; G.XC[1][k][c][warp] = m2; }
+                            } else {
+                                const uint32_t k = j - 6;
+#pragma unroll
+                                for (uint32_t c = 0; c < 3; ++c) {
+                                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ((wy >> k) & 1u) && cl == c);
+                                    if (lane == 0) G.YC[k][c][warp] = m;
+                                }
+                            }
+                        }
+                    }
                 }
             }
             if (ms < 4) {   // monotone board: a holding suited in that suit has flopped a flush -- move it to its true class
@@ -404,6 +471,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             if (fneed <= 2) {
                 const uint32_t nfs = G.ns[fs], nnf = kU - nfs, nboth = choose2u(nfs);
                 const uint32_t total = (int)fneed == 2 ? nboth : ((int)fneed == 1 ? nboth + nfs * nnf : (uint32_t)kPairs4);
+                if (tid == 0) G.n_ext = total;
                 for (uint32_t t = tid; t < total; t += kGroupThreads) {
                     uint32_t i, j;
                     if ((int)fneed <= 0) {
@@ -421,7 +489,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t ri = ci >> 2, rj = cj >> 2;
                     const uint32_t fbits = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
                     const uint32_t pp = tri(rj) + ri;
-                    G.ext[atomicAdd(&G.n_ext, 1u)] = pp | ((uint32_t)S.flush[fold(hbmask | fbits)] << 8);
+                    G.ext[t] = pp | ((uint32_t)S.flush[fold(hbmask | fbits)] << 8);      // slot = index of the runout in its list
                     atomicAdd(&G.qflush[pp], 1u);
                 }
             }
@@ -491,13 +559,22 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         // generic tasks first (they are the longest): task = 2 * chunk + half, half 0 = rank pairs with y <= 8, half 1 = y >= 9
         const uint32_t n_gen_tasks = 2u * ((n_entries + 31) / 32);
         const uint32_t n_tasks = n_gen_tasks + n_flush_tasks;
+        // kBits: the flush tasks read the compare bits that the generic tasks leave behind, so the group meets in between
+        uint32_t phase = 0;
         for (;;) {
             uint32_t task = 0;
-            if (lane == 0) task = atomicAdd(&G.next_task, 1u);
+            if (lane == 0) task = atomicAdd(kBits && phase ? &G.next_ftask : &G.next_task, 1u);
             task = __shfl_sync(0xFFFFFFFFu, task, 0);
-            if (task >= n_tasks) break;
-            if (task >= n_gen_tasks) {
-                task -= n_gen_tasks;
+            if (kBits) {
+                if (phase == 0) {
+                    if (task >= n_gen_tasks) { phase = 1; group_sync(gid); continue; }
+                } else if (task >= n_flush_tasks) break;
+            } else {
+                if (task >= n_tasks) break;
+                phase = task >= n_gen_tasks ? 1u : 0u;
+                if (phase) task -= n_gen_tasks;
+            }
+            if (phase) {
                 // ================= flush task: 32 runouts Q x a segment of steps =======================================
                 uint32_t g = 0;
                 while (g + 1 < n_groups && task >= G.g_first[g + 1]) ++g;
@@ -562,6 +639,73 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t tq_s = t_s + qcol;
                 const uint4 *pd = G.PD + G.g_pdbase[g] + p0;
                 uint32_t aL = 0, aG = 0, sL = 0, sG = 0;
+                const uint32_t need = 5u - (((bsuit >> (4 * s)) & 15u) + qtype);
+                // Runouts that complete OUR flush (all of the task group or none) have their own entries in the generic part and a
+                // suited rank: they keep the step-by-step undo half.  Everywhere else the lane's runout shares our7 and the column of T
+                // with merged runout ppq of the generic part, whose compare outcomes LB / GB are already there: the undo half of the whole
+                // step list is a weighted population count.  Step weights by rank pair: both cards in s -> 1 (BC), {a in s, c outside s}
+                // -> unseen cards of c's rank outside s (XC, by which of the two ranks is a's), no card in s -> YC; a step is valid when
+                // its cards of s avoid the runout's (lo_t / hi_t rows of the runout's ranks in s).
+                const uint32_t hs_s = (hsuit >> (4 * s)) & 15u;
+                const bool ext_lanes = hs_s + qtype >= 5u;                   // every runout of the group completes our flush
+                const bool bits_path = kBits && (!ext_lanes || hs_s == 3u);  // (hs_s == 3: they are the pairs of <= 10 cards, entry 91 + qi)
+                if (bits_path) {
+                    const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
+                    const bool fast = kFastAdd && __all_sync(0xFFFFFFFFu, our > 1599u || qi >= nq);
+                    if (seg == 0) {
+                        const uint32_t qbits = qb2 >> 17, rest = qbits & (qbits - 1u);
+                        const uint32_t ppq = ext_lanes ? (qi < nq ? (uint32_t)kPP + qi : 0u) : qcol >> 1;
+                        const uint32_t r1 = qbits ? (uint32_t)__ffs(qbits) - 1u : 13u, r2 = rest ? (uint32_t)__ffs(rest) - 1u : 13u;
+#pragma unroll 1
+                        for (uint32_t w = 0; w < 3; ++w) {
+                            const uint32_t lb = G.LB[w][ppq], gb = G.GB[w][ppq];
+                            const uint32_t lo = ~(S.lo_t[r1][w] | S.lo_t[r2][w]), hi = ~(S.hi_t[r1][w] | S.hi_t[r2][w]);
+                            const uint32_t tl = lb & lo & hi, tg = gb & lo & hi;
+#pragma unroll
+                            for (uint32_t c = 0; c < 3; ++c) {
+                                const uint32_t m = G.BC[s][c][w];
+                                sL += (uint32_t)__popc(m & tl) << (10 * c);
+                                sG += (uint32_t)__popc(m & tg) << (10 * c);
+                            }
+                            if (need <= 1) {
+                                const uint32_t l1 = lb & lo, g1 = gb & lo, l2 = lb & hi, g2 = gb & hi;
+#pragma unroll
+                                for (uint32_t k = 0; k < 2; ++k)
+#pragma unroll
+                                    for (uint32_t c = 0; c < 3; ++c) {
+                                        const uint32_t m1 = G.XC[0][k][c][w], m2 = G.XC[1][k][c][w];
+                                        sL += (uint32_t)(__popc(m1 & l1) + __popc(m2 & l2)) << (10 * c + k);
+                                        sG += (uint32_t)(__popc(m1 & g1) + __popc(m2 & g2)) << (10 * c + k);
+                                    }
+                                if (need == 0) {
+#pragma unroll
+                                    for (uint32_t k = 0; k < 4; ++k)
+#pragma unroll
+                                        for (uint32_t c = 0; c < 3; ++c) {
+                                            const uint32_t m = G.YC[k][c][w];
+                                            sL += (uint32_t)__popc(m & lb) << (10 * c + k);
+                                            sG += (uint32_t)__popc(m & gb) << (10 * c + k);
+                                        }
+                                }
+                            }
+                        }
+                    }
+                    if (fast) {                                              // add half in closed form (see below)
+                        if (seg == 0 && qi < nq) {
+                            const bool with_one = np > choose2u(nsu);
+                            uint32_t add = G.Wt0[s] + (with_one ? G.Ht[s] : 0u);
+                            if (ia != 0xFFu) add -= G.Wc0[s][ia] + (with_one ? G.Hs[s][ia] : 0u);
+                            if (ib != 0xFFu) add -= G.Wc0[s][ib] + (with_one ? G.Hs[s][ib] : 0u) - G.PD[G.g_pdbase[g] + qi].y;
+                            aG = add;
+                        }
+                    } else {                                                 // add half step by step: suited-table gather, two compares
+#pragma unroll kF4Unroll
+                        for (uint32_t t = p0; t < split; ++t, ++pd) {
+                            const uint4 d = *pd;
+                            undo_step(aL, aG, our, lds_u16(flush_s + ((d.x & 0xFFFFu) ^ fqf)), d.x, qb2, d.y, one);
+                        }
+                    }
+                } else {
                 // steps [0, nboth + n_s) have an add part (holdings with both cards in s, or one card a in s); the ones behind them
                 // are rank-level undo steps: no suited-table gather, half the compares
                 const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
@@ -600,12 +744,12 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint4 d = *pd;
                     undo_step(sL, sG, our, lds_u16(tq_s + d.w), d.x, qb2, d.z, one);
                 }
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {   // wl = 0 on lanes past the end of the runout list
                     accL[c] += (((aL >> (10 * c)) & 0x3FFu) - ((sL >> (10 * c)) & 0x3FFu)) * wl;
                     accG[c] += (((aG >> (10 * c)) & 0x3FFu) - ((sG >> (10 * c)) & 0x3FFu)) * wl;
                 }
-                const uint32_t need = 5u - (((bsuit >> (4 * s)) & 15u) + qtype);
                 if (seg == 0 && need == 0 && qi < nq) {
                     // holdings without a card of s: the board + runout flush itself, one compare for all of them
                     const uint32_t rf = lds_u16(flush_s + fqf);
@@ -676,6 +820,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // all 91 rank pairs of P, fully unrolled (constant shifts and offsets); unweighted counts n_Q(pp) go into packed
                 // 10-bit class fields (they sum to C(45,2) = 990 per runout), the runout multiplicity is applied afterwards
                 uint32_t lp = 0, gp = 0;
+                uint32_t lbw[3] = {0, 0, 0}, gbw[3] = {0, 0, 0};    // kBits: the compare outcomes, bit pp of word pp / 32
                 if (!upper) {
 #pragma unroll
                     for (int y = 0; y < 9; ++y) {
@@ -685,8 +830,13 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                             const int pp = y * (y + 1) / 2 + x;
                             const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
                             const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
-                            cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
+                            if (kBits) cmp_add_bits(lp, gp, lbw[pp >> 5], gbw[pp >> 5], val, R, nn, G.clsw[pp], 1u << (pp & 31));
+                            else cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
                         }
+                    }
+                    if (kBits && e < (uint32_t)kBitEntries) {
+                        G.LB[0][e] = lbw[0]; G.GB[0][e] = gbw[0];
+                        atomicOr(&G.LB[1][e], lbw[1]); atomicOr(&G.GB[1][e], gbw[1]);
                     }
                 } else {
 #pragma unroll
@@ -697,8 +847,13 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                             const int pp = y * (y + 1) / 2 + x;
                             const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
                             const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
-                            cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
+                            if (kBits) cmp_add_bits(lp, gp, lbw[pp >> 5], gbw[pp >> 5], val, R, nn, G.clsw[pp], 1u << (pp & 31));
+                            else cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
                         }
+                    }
+                    if (kBits && e < (uint32_t)kBitEntries) {
+                        atomicOr(&G.LB[1][e], lbw[1]); atomicOr(&G.GB[1][e], gbw[1]);
+                        G.LB[2][e] = lbw[2]; G.GB[2][e] = gbw[2];
                     }
                 }
 #pragma unroll
@@ -745,14 +900,15 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
-                                    bool closed_form_add, uint32_t *order_scratch) {
+                                    bool closed_form_add, uint32_t *order_scratch, bool bit_parallel_undo) {
     // other_rows_flag points at a 16-byte slot: [0] the flag word, [1] the work counter of this kernel, [2] of the turn kernel
     if (n >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     if (n == 0) return cudaSuccess;
     const size_t smem = sizeof(Flop4Smem);
     // the phase clocks are compiled out of the production instances: the kernel is sensitive to its code size
-    auto kernel = prof ? hp_flop_treys_v4_kernel<true, true>
-                       : (closed_form_add ? hp_flop_treys_v4_kernel<false, true> : hp_flop_treys_v4_kernel<false, false>);
+    auto kernel = prof ? hp_flop_treys_v4_kernel<true, true, true>
+                       : (!bit_parallel_undo ? hp_flop_treys_v4_kernel<false, true, false>
+                          : (closed_form_add ? hp_flop_treys_v4_kernel<false, true, true> : hp_flop_treys_v4_kernel<false, false, true>));
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t blocks = sms;

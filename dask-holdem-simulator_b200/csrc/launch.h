@@ -60,11 +60,13 @@ cudaError_t launch_hp_flop_treys(const DevTables &T, const uint8_t *sit, int64_t
 // Rank-multiset flop kernel (kernels_hp_flop4.cu): same contract and bit-identical counts, the default.
 // closed_form_add: sum the add parts of the flush steps in closed form where no runout of the warp gives us a flush or better
 // (production); false = walk them step by step (holdem_hp_flop_variant 5, kept for A/B and as a cross-check).
+// bit_parallel_undo: the undo half of the flush part as weighted population counts over the compare bits the generic tasks leave
+// behind (production); false = the step-by-step undo half of the earlier kernel (holdem_hp_flop_variant 7).
 // prof: optional device uint64[4], cycles spent per phase summed over the situation groups (tables / W+T / descriptors /
 // tasks); nullptr in production.
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,
                                     int *other_rows_flag, unsigned long long *prof, const PeerOut &peers, cudaStream_t st,
-                                    bool closed_form_add = true, uint32_t *order_scratch = nullptr);
+                                    bool closed_form_add = true, uint32_t *order_scratch = nullptr, bool bit_parallel_undo = true);
 // order_scratch: optional device buffer filled by launch_street_order (kernels_order.cu): the situations are then worked heaviest
 // board texture first (results still land by row number).
 constexpr uint32_t kOrderHeader = 128;        // words of counters in front of the two row lists

@@ -75,7 +75,15 @@ __device__ __forceinline__ void cmp_add(uint32_t &accL, uint32_t &accG, uint32_t
         : "+r"(accL), "+r"(accG)
         : "r"(a), "r"(b), "r"(w), "r"(one));
 }
-
+// cmp_add that also records the two outcomes as bit `bit` of lb / gb (the compare bits feed the bit-parallel undo half)
+__device__ __forceinline__ void cmp_add_bits(uint32_t &accL, uint32_t &accG, uint32_t &lb, uint32_t &gb, uint32_t a, uint32_t b,
+                                             uint32_t w, uint32_t one, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.u32 p, %4, %5;\n\t@p mad.lo.u32 %0, %6, %7, %0;\n\t@p or.b32 %2, %2, %8;\n\t"
+        "setp.gt.u32 p, %4, %5;\n\t@p mad.lo.u32 %1, %6, %7, %1;\n\t@p or.b32 %3, %3, %8;\n\t}"
+        : "+r"(accL), "+r"(accG), "+r"(lb), "+r"(gb)
+        : "r"(a), "r"(b), "r"(w), "r"(one), "r"(bit));
+}
 
 }  // namespace ms
 }  // namespace holdem
