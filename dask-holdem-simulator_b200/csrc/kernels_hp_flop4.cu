@@ -123,7 +123,7 @@ struct Flop4Group {                    // one situation in flight
     uint32_t XC[2][2][3][3];           // [which card is in s: lo / hi][weight bit][class][word]: holdings {a in s, c outside s} of the
                                        // suit with two or more board cards, weight = unseen cards of c's rank outside s
     uint32_t YC[4][3][3];              // [weight bit][class][word]: holdings without a card of s (monotone boards)
-    uint32_t next_ftask;
+    uint32_t next_ftask, pd_next;
 };
 
 struct Flop4Smem {
@@ -266,13 +266,17 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         if (tid >= 32 && tid < 96) (&G.Wc0[0][0])[tid - 32] = 0;
         if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
         if (kBits) { G.LB[1][tid] = 0; G.GB[1][tid] = 0; }
+        // The set-up below is spread over the group's five warps (a dependent instruction costs ~40 cycles on the busy SM, so the
+        // length of the longest chain is what counts): warp 0 sorts the unseen cards, warps 2 and 3 build the per-suit position lists
+        // of two suits each, warp 4 lays out the flush task groups, warp 1 fetches the table rows.
+        static_assert(kGroupThreads == 160, "the set-up phase assigns work to five warps");
+        const uint32_t ltm = (1u << lane) - 1u;
         if (warp == 0) {
-            // ---- unseen cards in (rank, suit) order; per-rank and per-suit position lists -----------------------------
+            // ---- unseen cards in (rank, suit) order; unseen cards per rank ----------------------------------------------------------
             const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
             const bool in0 = !((known >> p0) & 1ull);
             const bool in1 = (lane + 32 < 52) && !((known >> p1) & 1ull);
             const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
-            const uint32_t ltm = (1u << lane) - 1u;
             if (in0) G.code[__popc(m0 & ltm)] = (uint8_t)lane;
             if (in1) G.code[__popc(m0) + __popc(m1 & ltm)] = (uint8_t)(lane + 32);
             {   // rank r owns codes 4r..4r+3
@@ -283,28 +287,34 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (lane >= 10 && lane < 13) ? cnt_r << (3 * lane - 30) : 0u);
                 if (lane == 0) { G.upack[0] = lo | (hi << 30); G.upack[1] = hi >> 2; }
             }
-            __syncwarp();
-            const uint32_t cd0 = G.code[lane], cd1 = lane + 32 < kU ? G.code[lane + 32] : 0u;
-            const bool v1 = lane + 32 < kU;
+        } else if (warp == 2 || warp == 3) {
+            // ---- per-suit lists of positions in that order: this lane = the cards with codes lane and lane + 32 (suit = lane & 3) ----
+            const uint32_t p0 = path_of_code4(lane), p1 = path_of_code4(lane + 32);
+            const bool in0 = !((known >> p0) & 1ull);
+            const bool in1 = (lane + 32 < 52) && !((known >> p1) & 1ull);
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, in0), m1 = __ballot_sync(0xFFFFFFFFu, in1);
+            const uint32_t pos0 = __popc(m0 & ltm), pos1 = __popc(m0) + __popc(m1 & ltm);
 #pragma unroll
-            for (uint32_t s = 0; s < 4; ++s) {
-                const bool a0 = (cd0 & 3u) == s, a1 = v1 && (cd1 & 3u) == s;
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t s = 2u * (warp - 2u) + h;
+                const bool a0 = in0 && (lane & 3u) == s, a1 = in1 && (lane & 3u) == s;
                 const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, a0), b1 = __ballot_sync(0xFFFFFFFFu, a1);
-                const uint32_t n0 = __popc(b0), nsu = n0 + __popc(b1);
-                if (a0) G.Ls[s][__popc(b0 & ltm)] = (uint8_t)lane;
-                else G.Lns[s][lane - __popc(b0 & ltm)] = (uint8_t)lane;
-                if (v1) {
-                    if (a1) G.Ls[s][n0 + __popc(b1 & ltm)] = (uint8_t)(lane + 32);
-                    else G.Lns[s][(32 - n0) + lane - __popc(b1 & ltm)] = (uint8_t)(lane + 32);
-                }
-                const uint32_t rm = __reduce_or_sync(0xFFFFFFFFu, (a0 ? 1u << (cd0 >> 2) : 0u) | (a1 ? 1u << (cd1 >> 2) : 0u));
-                if (lane == 0) { G.ns[s] = (uint8_t)nsu; G.smask[s] = rm; }
+                const uint32_t k0 = __popc(b0 & ltm), k1 = __popc(b0) + __popc(b1 & ltm);     // cards of s below this one
+                if (a0) G.Ls[s][k0] = (uint8_t)pos0;
+                else if (in0) G.Lns[s][pos0 - k0] = (uint8_t)pos0;
+                if (a1) G.Ls[s][k1] = (uint8_t)pos1;
+                else if (in1) G.Lns[s][pos1 - k1] = (uint8_t)pos1;
             }
-            __syncwarp();
+        } else if (warp == 4) {
+            if (lane < 4) {
+                const uint32_t rm = ~(uint32_t)(known >> (13 * lane)) & 0x1FFFu;       // ranks of the unseen cards of suit `lane`
+                G.smask[lane] = rm;
+                G.ns[lane] = (uint8_t)__popc(rm);
+            }
             {
                 // ---- flush task groups and PD sections: lane = 3 * suit + (2 - qtype), scans over the warp -------------------------
                 const uint32_t s = min(lane / 3u, 3u), qtype = 2u - (lane - 3u * (lane / 3u));
-                const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = G.ns[s], nns = kU - nsu;
+                const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = __popc(~(uint32_t)(known >> (13 * s)) & 0x1FFFu), nns = kU - nsu;
                 const uint32_t nboth = choose2u(nsu), none = nsu * nns;
                 // step list of the suit: [both cards in s | a | (a, rank of c) | rank pairs without a card of s]
                 const uint32_t len2 = nboth, len1 = nboth + 14u * nsu, len0 = len1 + kPP;
@@ -352,6 +362,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     G.pd_total = pdo + len;
                     G.next_task = 0;
                     G.next_ftask = 0;
+                    G.pd_next = 0;
                     G.n_ext = 0;
                 }
             }
@@ -494,8 +505,14 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             }
             // ---- step descriptors of the flush part ---------------------------------------------------------------------------------
+            // (32 descriptors per claim: the warps that had nothing to do above start at once, the others join when they get here)
             const uint32_t total = G.pd_total;
-            for (uint32_t e = tid; e < total; e += kGroupThreads) {
+            for (;;) {
+                uint32_t e = 0;
+                if (lane == 0) e = atomicAdd(&G.pd_next, 32u);
+                e = __shfl_sync(0xFFFFFFFFu, e, 0) + lane;
+                if (e - lane >= total) break;
+                if (e >= total) continue;
                 uint32_t s = 0;
 #pragma unroll
                 for (uint32_t q = 1; q < 4; ++q)
