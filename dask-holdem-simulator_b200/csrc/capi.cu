@@ -581,7 +581,7 @@ int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out
     if (n < 0 || !d_cycles || (n > 0 && (!d_sit || !d_out))) return fail(HOLDEM_ERR_BAD_ARG, "null pointer or negative n");
     FlagSlot slot;
     CUDA_TRY(slot.acquire(*S, (cudaStream_t)stream));
-    CUDA_TRY(cudaMemsetAsync(d_cycles, 0, 4 * sizeof(uint64_t), (cudaStream_t)stream));
+    CUDA_TRY(cudaMemsetAsync(d_cycles, 0, 8 * sizeof(uint64_t), (cudaStream_t)stream));
     CUDA_TRY(launch_hp_flop_treys_v4(S->T, d_sit, n, d_out, S->sms, slot.ptr, (unsigned long long *)d_cycles, PeerOut{},
                                      (cudaStream_t)stream));
     CUDA_TRY(slot.release());

@@ -119,10 +119,11 @@ struct Flop4Group {                    // one situation in flight
     uint32_t LB[3][kBitEntries], GB[3][kBitEntries];   // per entry e of the generic part (91 merged runouts, then the runouts that
                                        // complete our flush when they are the pairs of ten cards): { pp : our7[e] < T[e][pp] } and
                                        // { ... > ... }, written by the generic tasks (the two halves share word 1: atomicOr onto zeroed words)
-    uint32_t BC[4][3][3];              // [suit][class][word]: holdings with both cards in s, by rank pair
-    uint32_t XC[2][2][3][3];           // [which card is in s: lo / hi][weight bit][class][word]: holdings {a in s, c outside s} of the
-                                       // suit with two or more board cards, weight = unseen cards of c's rank outside s
-    uint32_t YC[4][3][3];              // [weight bit][class][word]: holdings without a card of s (monotone boards)
+    uint32_t CL[3][3];                 // [class][word]: the rank pairs of each flop class
+    uint32_t BS[4][3];                 // [suit][word]: holdings with both cards in s, by rank pair
+    uint32_t XS[2][2][3];              // [which card is in s: lo / hi][weight bit][word]: holdings {a in s, c outside s} of the suit with
+                                       // two or more board cards, weight = unseen cards of c's rank outside s
+    uint32_t YS[4][3];                 // [weight bit][word]: holdings without a card of s (monotone boards)
     uint32_t next_ftask, pd_next;
 };
 
@@ -429,39 +430,37 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (kBits) {
                     // ---- the undo half of the flush part as sets of rank pairs (this thread = rank pair pp = (x <= y)) -------------
                     uint32_t s2 = 4;                                                     // the suit with two or more board cards
-#pragma unroll 1
+#pragma unroll
+                    for (uint32_t c = 0; c < 3; ++c) {
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cl == c);
+                        if (lane == 0) G.CL[c][warp] = m;
+                    }
+#pragma unroll
                     for (uint32_t s = 0; s < 4; ++s) {
                         const uint32_t bs = (bsuit >> (4 * s)) & 15u;
                         if (bs == 0) continue;                                           // (uniform over the group)
                         if (bs >= 2) s2 = s;
                         const uint32_t sm = G.smask[s];
-                        const bool both = x != y && ((sm >> x) & (sm >> y) & 1u);
-#pragma unroll
-                        for (uint32_t c = 0; c < 3; ++c) {
-                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, both && cl == c);
-                            if (lane == 0) G.BC[s][c][warp] = m;
-                        }
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, x != y && ((sm >> x) & (sm >> y) & 1u));
+                        if (lane == 0) G.BS[s][warp] = m;
                     }
                     if (s2 < 4) {
                         const uint32_t sm = G.smask[s2], ax = (sm >> x) & 1u, ay = (sm >> y) & 1u;
                         const uint32_t bx = ux - ax, by = uy - ay;                       // unseen cards of the rank outside s (<= 3)
                         const uint32_t w1 = ax ? by : 0u;                                // {a = the lower rank's card of s, c of rank y}
                         const uint32_t w2 = (x != y && ay) ? bx : 0u;                    // {a = the higher rank's card of s, c of rank x}
-                        const uint32_t wy = m3 ? (x != y ? bx * by : (bx ? choose2u(bx) : 0u)) : 0u;   // no card in s (<= 9)
-#pragma unroll 1
-                        for (uint32_t j = 0; j < (m3 ? 10u : 6u); ++j) {                 // j = 2 * class + k (w1, w2), 6 + k (wy, three classes)
-                            if (j < 6) {
-                                const uint32_t c = j >> 1, k = j & 1u;
-                                const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, ((w1 >> k) & 1u) && cl == c);
-                                const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, ((w2 >> k) & 1u) && cl == c);
-                                if (lane == 0) { G.XC[0][k][c][warp] = m1; G.XC[1][k][c][warp] = m2; }
-                            } else {
-                                const uint32_t k = j - 6;
 #pragma unroll
-                                for (uint32_t c = 0; c < 3; ++c) {
-                                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ((wy >> k) & 1u) && cl == c);
-                                    if (lane == 0) G.YC[k][c][warp] = m;
-                                }
+                        for (uint32_t k = 0; k < 2; ++k) {
+                            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (w1 >> k) & 1u);
+                            const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, (w2 >> k) & 1u);
+                            if (lane == 0) { G.XS[0][k][warp] = m1; G.XS[1][k][warp] = m2; }
+                        }
+                        if (m3) {
+                            const uint32_t wy = x != y ? bx * by : (bx ? choose2u(bx) : 0u);         // no card in s (<= 9)
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (wy >> k) & 1u);
+                                if (lane == 0) G.YS[k][warp] = m;
                             }
                         }
                     }
@@ -478,6 +477,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     atomicSub(&G.cnt[6 + G.clsr[tri(rb) + ra]], 1u);
                 }
             }
+            HOLDEM_PROF(1)
             // ---- runouts that give us a flush get their own entry of the generic part (their our7 is a suited-table rank) ---------
             if (fneed <= 2) {
                 const uint32_t nfs = G.ns[fs], nnf = kU - nfs, nboth = choose2u(nfs);
@@ -504,6 +504,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     atomicAdd(&G.qflush[pp], 1u);
                 }
             }
+            HOLDEM_PROF(4)
             // ---- step descriptors of the flush part ---------------------------------------------------------------------------------
             // (32 descriptors per claim: the warps that had nothing to do above start at once, the others join when they get here)
             const uint32_t total = G.pd_total;
@@ -559,7 +560,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             }
         }
-        HOLDEM_PROF(1)
+        HOLDEM_PROF(5)
         group_sync(gid);                                                                            // (D)
         if (!next_claimed) {                                           // fetch the next claim under this situation's tasks
             if (tid == 0) make_claim((claim_it + 1) & 1, claim_it + 1);
@@ -584,7 +585,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             task = __shfl_sync(0xFFFFFFFFu, task, 0);
             if (kBits) {
                 if (phase == 0) {
-                    if (task >= n_gen_tasks) { phase = 1; group_sync(gid); continue; }
+                    if (task >= n_gen_tasks) { phase = 1; group_sync(gid); HOLDEM_PROF(6) continue; }
                 } else if (task >= n_flush_tasks) break;
             } else {
                 if (task >= n_tasks) break;
@@ -593,11 +594,11 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             }
             if (phase) {
                 // ================= flush task: 32 runouts Q x a segment of steps =======================================
-                uint32_t g = 0;
-                while (g + 1 < n_groups && task >= G.g_first[g + 1]) ++g;
+                // the task group: the last one whose first task is <= task (lanes 1.. compare one boundary each)
+                const uint32_t g = __popc(__ballot_sync(0xFFFFFFFFu, lane >= 1 && lane < n_groups && task >= G.g_first[min(lane, (uint32_t)kMaxGroups)]));
                 const uint32_t local = task - G.g_first[g];
                 const uint32_t nseg = G.g_nseg[g], seglen = G.g_seglen[g], np = G.g_np[g], nq = G.g_nq[g];
-                const uint32_t chunk = local / nseg, seg = local - chunk * nseg;
+                const uint32_t chunk = nseg == 1 ? local : local / nseg, seg = local - chunk * nseg;
                 const uint32_t s = G.g_sq[g] & 3u, qtype = (G.g_sq[g] >> 2) & 3u;
                 const bool rank_lanes = (G.g_sq[g] >> 4) != 0;
                 const uint32_t p0 = seg * seglen, p1 = min(np, p0 + seglen);
@@ -677,32 +678,29 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         for (uint32_t w = 0; w < 3; ++w) {
                             const uint32_t lb = G.LB[w][ppq], gb = G.GB[w][ppq];
                             const uint32_t lo = ~(S.lo_t[r1][w] | S.lo_t[r2][w]), hi = ~(S.hi_t[r1][w] | S.hi_t[r2][w]);
-                            const uint32_t tl = lb & lo & hi, tg = gb & lo & hi;
-#pragma unroll
-                            for (uint32_t c = 0; c < 3; ++c) {
-                                const uint32_t m = G.BC[s][c][w];
-                                sL += (uint32_t)__popc(m & tl) << (10 * c);
-                                sG += (uint32_t)__popc(m & tg) << (10 * c);
-                            }
+                            const uint32_t cl0 = G.CL[0][w], cl1 = G.CL[1][w], cl2 = G.CL[2][w];
+                            // (rank pairs that cannot exist with this board are in no class: their weights never count)
+                            auto tally = [&](uint32_t ml, uint32_t mg, uint32_t k) {
+                                sL += ((uint32_t)__popc(ml & cl0) << k) + ((uint32_t)__popc(ml & cl1) << (10 + k)) +
+                                      ((uint32_t)__popc(ml & cl2) << (20 + k));
+                                sG += ((uint32_t)__popc(mg & cl0) << k) + ((uint32_t)__popc(mg & cl1) << (10 + k)) +
+                                      ((uint32_t)__popc(mg & cl2) << (20 + k));
+                            };
+                            const uint32_t both = G.BS[s][w] & lo & hi;
+                            tally(lb & both, gb & both, 0);
                             if (need <= 1) {
-                                const uint32_t l1 = lb & lo, g1 = gb & lo, l2 = lb & hi, g2 = gb & hi;
 #pragma unroll
-                                for (uint32_t k = 0; k < 2; ++k)
-#pragma unroll
-                                    for (uint32_t c = 0; c < 3; ++c) {
-                                        const uint32_t m1 = G.XC[0][k][c][w], m2 = G.XC[1][k][c][w];
-                                        sL += (uint32_t)(__popc(m1 & l1) + __popc(m2 & l2)) << (10 * c + k);
-                                        sG += (uint32_t)(__popc(m1 & g1) + __popc(m2 & g2)) << (10 * c + k);
-                                    }
+                                for (uint32_t k = 0; k < 2; ++k) {
+                                    const uint32_t m1 = G.XS[0][k][w] & lo, m2 = G.XS[1][k][w] & hi;
+                                    tally(lb & m1, gb & m1, k);
+                                    tally(lb & m2, gb & m2, k);
+                                }
                                 if (need == 0) {
 #pragma unroll
-                                    for (uint32_t k = 0; k < 4; ++k)
-#pragma unroll
-                                        for (uint32_t c = 0; c < 3; ++c) {
-                                            const uint32_t m = G.YC[k][c][w];
-                                            sL += (uint32_t)__popc(m & lb) << (10 * c + k);
-                                            sG += (uint32_t)__popc(m & gb) << (10 * c + k);
-                                        }
+                                    for (uint32_t k = 0; k < 4; ++k) {
+                                        const uint32_t m = G.YS[k][w];
+                                        tally(lb & m, gb & m, k);
+                                    }
                                 }
                             }
                         }
@@ -912,7 +910,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 #undef HOLDEM_PROF
     if (saw_other && tid == 0) atomicOr(other_rows, saw_other);
     if (kProf && tid == 0)
-        for (int k = 0; k < 4; ++k) atomicAdd(prof + k, (unsigned long long)G.prof[k]);
+        for (int k = 0; k < kProfSlots; ++k) atomicAdd(prof + k, (unsigned long long)G.prof[k]);
 }
 
 cudaError_t launch_hp_flop_treys_v4(const DevTables &T, const uint8_t *sit, int64_t n, uint32_t *out, int sms,

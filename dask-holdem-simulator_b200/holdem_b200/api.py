@@ -211,11 +211,13 @@ def table_showdown(hole: torch.Tensor, board: torch.Tensor, active: torch.Tensor
 
 
 def flop_phase_cycles(sit: torch.Tensor):
-    """Production flop kernel with phase clocks on -> (rows int32 [N,16], cycles int64 [4] = tables, W+T, descriptors,
-    tasks; SM cycles summed over all situations)."""
+    """Production flop kernel with phase clocks on -> (rows int32 [N,16], cycles int64 [8]; SM cycles of one thread per situation
+    group summed over all situations: [0] card lists + table rows, [1] hand strength + rank-pair sets, [4] our-flush entries,
+    [5] step descriptors, [2] next claim + wait for the T row, [6] generic tasks up to the group barrier, [3] flush tasks + reduce,
+    [7] unused)."""
     _require_cuda(sit, "sit", torch.uint8, 8)
     out = torch.empty((sit.shape[0], HP_ROW), dtype=torch.int32, device=sit.device)
-    cyc = torch.zeros(4, dtype=torch.int64, device=sit.device)
+    cyc = torch.zeros(8, dtype=torch.int64, device=sit.device)
     with _enter(sit) as (lib, st):
         _lib.check(lib.holdem_hp_flop_phase_cycles(sit.data_ptr(), sit.shape[0], out.data_ptr(), cyc.data_ptr(), st))
     return out, cyc

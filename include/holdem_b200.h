@@ -172,9 +172,10 @@ int holdem_hs_batch_variant(const uint8_t *d_sit, int64_t n, int mode, int varia
 /* holdem_exhaustive7 through a named kernel: 0 = tuple kernel (production), 1 = chunk-per-thread kernel. */
 int holdem_exhaustive7_variant(int variant, uint64_t *d_hist, uint64_t *d_sums, void *stream);
 
-/* The production flop kernel with its phase clocks switched on: d_cycles uint64[4] receives the SM cycles each situation
- * group spent in (0) list + hash-table phase, (1) pair table + T expansion, (2) holding descriptors, (3) generic + flush
- * tasks, summed over all situations.  Profiling aid for bench.py / DESIGN.md; results in d_out are the normal rows. */
+/* The production flop kernel with its phase clocks switched on: d_cycles uint64[8] receives the SM cycles one thread of each
+ * situation group spent in [0] card lists + small table rows, [1] hand strength + rank-pair sets, [4] the entries of the runouts
+ * that complete our flush, [5] step descriptors, [2] next claim + wait for the T row, [6] generic tasks up to the group barrier,
+ * [3] flush tasks + reduction ([7] unused), summed over all situations.  Profiling aid; d_out receives the normal rows. */
 int holdem_hp_flop_phase_cycles(const uint8_t *d_sit, int64_t n, uint32_t *d_out, uint64_t *d_cycles, void *stream);
 
 /* ---- callers and data formats either side of the path -------------------------------------------

@@ -45,5 +45,5 @@ for t, name in ((1, "rainbow"), (2, "two-tone"), (3, "monotone")):
     print(f"{name:9s} ({len(sel)} rows): " + "  ".join(out), flush=True)
 rows, cyc = hb.flop_phase_cycles(d)
 c = cyc.cpu().numpy().astype(np.float64)
-print("phase cycle shares (tables, W+T, descriptors, tasks):", (c / c.sum()).round(3).tolist(), " cycles/situation/group:", int(c.sum() / n),
+print("phase cycle shares [lists+rows, HS+sets, claim+T wait, flush tasks, our-flush entries, descriptors, generic tasks, -]:", (c / c.sum()).round(3).tolist(), " cycles/situation/group:", int(c.sum() / n),
       " rows equal:", bool(torch.equal(rows, r4)))
