@@ -91,7 +91,8 @@ struct Flop4Group {                    // one situation in flight
     uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
     uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
-    uint32_t cnt[12];                  // lt[3], gt[3], class totals[3]
+    uint32_t cnt[2][12];               // lt[3], gt[3], class totals[3]; [situation parity]: the rows are written out of one
+                                       // while the next situation's set-up clears the other
     uint32_t bmask[4];                 // board rank mask per suit
     uint32_t g_first[kMaxGroups + 1];  // first task id of each flush group; [n_groups] = total
     uint32_t g_nq[kMaxGroups], g_np[kMaxGroups], g_nseg[kMaxGroups], g_seglen[kMaxGroups], g_pdbase[kMaxGroups];
@@ -215,8 +216,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
     };
     if (tid == 0) make_claim(0, 0);
+    bool synced = false;           // the previous iteration ended behind barrier (E): its claim and counters are settled
     for (;; ++claim_it) {
-    group_sync(gid);
+    if (!synced) group_sync(gid);
+    synced = false;
     const int64_t claim_base = G.next_claim[claim_it & 1];
     if (claim_base >= n) break;
     bool next_claimed = false;
@@ -226,7 +229,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         // the situation groups of an SM spend most of their time in the same code regions (the kernel is instruction-cache
         // sensitive: +7 % on the mixed workload).  Results are stored by row number as before.
         const int64_t idx = G.claim_rows[claim_it & 1][vidx - claim_base];
-        group_sync(gid);                                                                            // (A)
+        if (kClaim > 1) group_sync(gid);                                                            // (A) (one situation per claim:
+                                                                                                    //  the barrier at the loop top serves)
         if (kProf && tid == 0) t_prev = (uint32_t)clock64();
         uint2 w = __ldg(reinterpret_cast<const uint2 *>(sit) + idx);
         uint32_t cb[8];
@@ -262,11 +266,15 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             }
             continue;
         }
-        if (tid < 12) G.cnt[tid] = 0;
+        uint32_t *const gcnt = G.cnt[claim_it & 1];
+        if (tid < 12) gcnt[tid] = 0;
         if (tid < 4) { G.bmask[tid] = (uint32_t)(bset >> (13 * tid)) & 0x1FFFu; G.hist_none[tid] = 0; G.Wt0[tid] = 0; G.Ht[tid] = 0; }
         if (tid >= 32 && tid < 96) (&G.Wc0[0][0])[tid - 32] = 0;
         if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
-        if (kBits) { G.LB[1][tid] = 0; G.GB[1][tid] = 0; }
+        if (kBits) {
+#pragma unroll
+            for (int w = 0; w < 3; ++w) { G.LB[w][tid] = 0; G.GB[w][tid] = 0; }
+        }
         // The set-up below is spread over the group's five warps (a dependent instruction costs ~40 cycles on the busy SM, so the
         // length of the longest chain is what counts): warp 0 sorts the unseen cards, warps 2 and 3 build the per-suit position lists
         // of two suits each, warp 4 lays out the flush task groups, warp 1 fetches the table rows.
@@ -341,16 +349,23 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const bool whole_list = kBits && (hs_s + qtype < 5u || hs_s == 3u);
                 const uint32_t nseg = whole_list ? 1u : (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
                 const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
+                // task groups in order of the cards of s still needed (0, 1, 2): the ones with the longest step lists first
                 const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
-                const uint32_t gi = __popc(livem & ltm);
-                uint32_t first = ntask;                              // inclusive scan of the task counts
+                const uint32_t lv0 = __ballot_sync(0xFFFFFFFFu, live && need == 0), lv1 = __ballot_sync(0xFFFFFFFFu, live && need == 1);
+                const uint32_t lv2 = livem & ~(lv0 | lv1);
+                const uint32_t gi = need == 0 ? __popc(lv0 & ltm)
+                                              : (need == 1 ? __popc(lv0) + __popc(lv1 & ltm) : __popc(lv0 | lv1) + __popc(lv2 & ltm));
+                if (live) G.g_first[gi + 1] = ntask;
+                __syncwarp();
+                uint32_t first = (lane >= 1 && lane <= (uint32_t)__popc(livem)) ? G.g_first[lane] : 0u;   // inclusive scan of the counts
 #pragma unroll
                 for (int d = 1; d < 16; d <<= 1) {
                     const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, first, d);
                     if ((int)lane >= d) first += v;
                 }
+                __syncwarp();
+                if (lane <= (uint32_t)__popc(livem) && lane <= (uint32_t)kMaxGroups) G.g_first[lane] = first;
                 if (live) {
-                    G.g_first[gi] = first - ntask;
                     G.g_nq[gi] = nq; G.g_np[gi] = np; G.g_nseg[gi] = nseg; G.g_seglen[gi] = seglen;
                     G.g_pdbase[gi] = pdo;
                     G.g_sq[gi] = s | (qtype << 2) | ((uint32_t)rank_lanes << 4);
@@ -358,7 +373,6 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
                 if (lane < 12 && qtype == 2) { G.pd_base[s] = pdo; G.pd_len[s] = len; }
                 if (lane == 11) {
-                    G.g_first[__popc(livem)] = first;
                     G.n_groups = __popc(livem);
                     G.pd_total = pdo + len;
                     G.next_task = 0;
@@ -425,7 +439,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
 #pragma unroll
                 for (uint32_t c = 0; c < 3; ++c) {
                     const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, cl == c ? cnt : 0u);
-                    if (lane == 0 && v) atomicAdd(&G.cnt[6 + c], v);
+                    if (lane == 0 && v) atomicAdd(&gcnt[6 + c], v);
                 }
                 if (kBits) {
                     // ---- the undo half of the flush part as sets of rank pairs (this thread = rank pair pp = (x <= y)) -------------
@@ -473,8 +487,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     const uint32_t ra = G.code[G.Ls[ms][pr & 0xFFu]] >> 2, rb = G.code[G.Ls[ms][pr >> 8]] >> 2;
                     const uint32_t opp5 = S.flush[fold(mbmask | (1u << ra) | (1u << rb))];
                     const uint32_t cls = ours_now < opp5 ? 0u : (ours_now == opp5 ? 1u : 2u);
-                    atomicAdd(&G.cnt[6 + cls], 1u);
-                    atomicSub(&G.cnt[6 + G.clsr[tri(rb) + ra]], 1u);
+                    atomicAdd(&gcnt[6 + cls], 1u);
+                    atomicSub(&gcnt[6 + G.clsr[tri(rb) + ra]], 1u);
                 }
             }
             HOLDEM_PROF(1)
@@ -812,8 +826,11 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             } else {
                 // ================= generic task: 32 merged runouts, the warp walks the rank pairs of P class by class =====
+                // task -> 32 entries x one half of the rank pairs (y <= 8 | y >= 9), as runs of slices of one to six values of y.
+                // (Measured: cutting the three-chunk case into 3 x 5 single-slice tasks so that the five warps finish together is
+                // slower, 52.1 -> 48.9 M situations/s: the per-task set-up chain costs more than the imbalance.)
                 const uint32_t e = (task >> 1) * 32 + lane;
-                const bool upper = (task & 1u) != 0;
+                const uint32_t sl = (task & 1u) ? 3u : 0u, sl_end = (task & 1u) ? 5u : 3u;
                 uint32_t qp = 0, val = 0, mult = 0;
                 if (e < (uint32_t)kPP) {
                     qp = e;
@@ -832,45 +849,36 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // unseen cards per rank once the runout's two cards are gone, 3 bits per rank
                 const uint64_t m64 = (((uint64_t)G.upack[1] << 32) | G.upack[0]) - (1ull << (3 * q1)) - (1ull << (3 * q2));
                 const uint32_t tq_s = t_s + 2u * qp;
-                // all 91 rank pairs of P, fully unrolled (constant shifts and offsets); unweighted counts n_Q(pp) go into packed
-                // 10-bit class fields (they sum to C(45,2) = 990 per runout), the runout multiplicity is applied afterwards
+                // the rank pairs of P, fully unrolled inside a slice (constant shifts and offsets); unweighted counts n_Q(pp) go into
+                // packed 10-bit class fields (they sum to C(45,2) = 990 per runout), the runout multiplicity is applied afterwards
                 uint32_t lp = 0, gp = 0;
-                uint32_t lbw[3] = {0, 0, 0}, gbw[3] = {0, 0, 0};    // kBits: the compare outcomes, bit pp of word pp / 32
-                if (!upper) {
-#pragma unroll
-                    for (int y = 0; y < 9; ++y) {
-                        const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;
-#pragma unroll
-                        for (int x = 0; x <= y; ++x) {
-                            const int pp = y * (y + 1) / 2 + x;
-                            const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
-                            const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
-                            if (kBits) cmp_add_bits(lp, gp, lbw[pp >> 5], gbw[pp >> 5], val, R, nn, G.clsw[pp], 1u << (pp & 31));
-                            else cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
-                        }
-                    }
-                    if (kBits && e < (uint32_t)kBitEntries) {
-                        G.LB[0][e] = lbw[0]; G.GB[0][e] = gbw[0];
-                        atomicOr(&G.LB[1][e], lbw[1]); atomicOr(&G.GB[1][e], gbw[1]);
-                    }
-                } else {
-#pragma unroll
-                    for (int y = 9; y < 13; ++y) {
-                        const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;
-#pragma unroll
-                        for (int x = 0; x <= y; ++x) {
-                            const int pp = y * (y + 1) / 2 + x;
-                            const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;
-                            const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));
-                            if (kBits) cmp_add_bits(lp, gp, lbw[pp >> 5], gbw[pp >> 5], val, R, nn, G.clsw[pp], 1u << (pp & 31));
-                            else cmp_add(lp, gp, val, R, nn, G.clsw[pp]);
-                        }
-                    }
-                    if (kBits && e < (uint32_t)kBitEntries) {
-                        atomicOr(&G.LB[1][e], lbw[1]); atomicOr(&G.GB[1][e], gbw[1]);
-                        G.LB[2][e] = lbw[2]; G.GB[2][e] = gbw[2];
-                    }
-                }
+                // kBits: the compare outcomes of a slice, bit pp of word pp / 32 (a slice touches words W0 and W0 + 1 at most), are OR-ed
+                // into the entry's zeroed sets at the end of the slice
+#define HOLDEM_GEN_SLICE(Y0, Y1, W0)                                                                                                \
+    {                                                                                                                               \
+        uint32_t lb0 = 0, lb1 = 0, gb0 = 0, gb1 = 0;                                                                                \
+        _Pragma("unroll") for (int y = Y0; y <= Y1; ++y) {                                                                          \
+            const uint32_t my = (uint32_t)(m64 >> (3 * y)) & 7u;                                                                    \
+            _Pragma("unroll") for (int x = 0; x <= y; ++x) {                                                                        \
+                const int pp = y * (y + 1) / 2 + x;                                                                                 \
+                const uint32_t nn = x == y ? (my * (my - 1u)) >> 1 : ((uint32_t)(m64 >> (3 * x)) & 7u) * my;                        \
+                const uint32_t R = lds_u16(tq_s + pp * (kTPitch * 2));                                                              \
+                if (!kBits) cmp_add(lp, gp, val, R, nn, G.clsw[pp]);                                                                \
+                else if ((pp >> 5) == W0) cmp_add_bits(lp, gp, lb0, gb0, val, R, nn, G.clsw[pp], 1u << (pp & 31));                  \
+                else cmp_add_bits(lp, gp, lb1, gb1, val, R, nn, G.clsw[pp], 1u << (pp & 31));                                       \
+            }                                                                                                                       \
+        }                                                                                                                           \
+        if (kBits && e < (uint32_t)kBitEntries) {                                                                                   \
+            atomicOr(&G.LB[W0][e], lb0); atomicOr(&G.GB[W0][e], gb0);                                                               \
+            if ((Y1 * (Y1 + 3) / 2) >> 5 != W0) { atomicOr(&G.LB[W0 + 1][e], lb1); atomicOr(&G.GB[W0 + 1][e], gb1); }               \
+        }                                                                                                                           \
+    }
+                if (sl == 0) HOLDEM_GEN_SLICE(0, 5, 0)                              // rank pairs  0..20
+                if (sl <= 1 && sl_end > 1) HOLDEM_GEN_SLICE(6, 7, 0)                 //            21..35
+                if (sl <= 2 && sl_end > 2) HOLDEM_GEN_SLICE(8, 8, 1)                 //            36..44
+                if (sl <= 3 && sl_end > 3) HOLDEM_GEN_SLICE(9, 10, 1)                //            45..65
+                if (sl_end > 4) HOLDEM_GEN_SLICE(11, 12, 2)                          //            66..90
+#undef HOLDEM_GEN_SLICE
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     accL[c] += ((lp >> (10 * c)) & 0x3FFu) * mult;
@@ -884,20 +892,21 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             const uint32_t l = __reduce_add_sync(0xFFFFFFFFu, accL[c]);
             const uint32_t g2 = __reduce_add_sync(0xFFFFFFFFu, accG[c]);
             if (lane == 0) {
-                if (l) atomicAdd(&G.cnt[c], l);
-                if (g2) atomicAdd(&G.cnt[3 + c], g2);
+                if (l) atomicAdd(&gcnt[c], l);
+                if (g2) atomicAdd(&gcnt[3 + c], g2);
             }
         }
         group_sync(gid);                                                                            // (E)
+        synced = kClaim == 1;
         HOLDEM_PROF(3)
         if (tid < 16) {
             uint32_t v;
-            if (tid < 3) v = G.cnt[6 + tid];
+            if (tid < 3) v = gcnt[6 + tid];
             else if (tid < 12) {
                 const uint32_t cls = (tid - 3) / 3, o = (tid - 3) % 3;
-                const uint32_t lt = G.cnt[cls], gt = G.cnt[3 + cls], all = 990u * G.cnt[6 + cls];
+                const uint32_t lt = gcnt[cls], gt = gcnt[3 + cls], all = 990u * gcnt[6 + cls];
                 v = o == 0 ? lt : (o == 2 ? gt : all - lt - gt);
-            } else if (tid < 15) v = G.cnt[6 + tid - 12];
+            } else if (tid < 15) v = gcnt[6 + tid - 12];
             else v = 3u;
             out[idx * 16 + tid] = v;
 #pragma unroll
