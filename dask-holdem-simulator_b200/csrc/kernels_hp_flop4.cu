@@ -39,9 +39,23 @@
 // onto mbarriers at the start of the situation, so the kernel performs no hash lookups at all; the runouts that give us a
 // flush; PD[<=320] 16-byte step descriptors of the flush part, per suit ordered
 // [both cards in s | one card a in s | undo steps (a, rank of c) | undo steps (rank pair), no card in s].
-// Flush part mapping: a warp task = 32 runouts Q of one (suit, cards-of-Q-in-suit) group x a segment of <= 64 steps;
-// lanes own Q (its rank, suit mask and T row live in registers), the warp walks the steps with one broadcast 16-byte load
-// each; a step is 2 gathers (flush, T), 4 compares and 4 predicated multiply-adds of packed per-class weights.
+// Flush part mapping: a warp task = 32 runouts Q of one (suit, cards-of-Q-in-suit) group; lanes own Q (its rank, suit mask and
+// column of T live in registers).
+//   * add half: in closed form per lane when no runout of the warp gives us a flush or better (every add part is then a loss for
+//     us: inclusion-exclusion over per-card class histograms); otherwise the warp walks the steps that have an add part with one
+//     broadcast 16-byte descriptor load each (suited-table gather, two compares, two predicated multiply-adds of packed per-class
+//     weights);
+//   * undo half (kBits, round 2): the lane's runout shares its our7 and its column of T with merged runout e of the generic
+//     part, so the compare outcomes it needs are the ones the generic tasks have just computed.  The generic tasks leave them
+//     behind as two 91-bit sets per entry (LB / GB: our7 < T, our7 > T), the group meets at a barrier, and the undo half of a
+//     lane's WHOLE step list becomes a weighted population count: the step weights by rank pair are per-situation sets built with
+//     warp ballots (BS: both cards in s, weight 1; XS: {a in s, c outside s}, bit slices of the number of unseen cards of c's rank
+//     outside s, by which of the two ranks is a's; YS: no card in s, bit slices of the pair count), the flop classes are three more
+//     sets (CL), and a step is valid when its cards of s avoid the runout's, i.e. outside the static sets lo_t / hi_t of the
+//     runout's ranks in s.  ~75 instructions per lane for a 66-step list, ~330 for a 210-step one, instead of 10 per step.
+//     The runouts that complete OUR flush keep the step-by-step undo half (their our7 is a suited rank) unless they are the
+//     pairs of ten cards (hole + board hold three of the suit: the common case), whose generic entries keep their bits too.
+//   19.6 K -> 15.5 K warp instructions per situation, 43.5 -> 52 M situations/s with the set-up phase spread over the five warps.
 #include "device_common.cuh"
 #include "launch.h"
 #include "multiset_common.cuh"
@@ -588,7 +602,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         const uint32_t n_groups = G.n_groups;
         const uint32_t n_flush_tasks = G.g_first[n_groups];
         const uint32_t n_entries = kPP + G.n_ext;
-        // generic tasks first (they are the longest): task = 2 * chunk + half, half 0 = rank pairs with y <= 8, half 1 = y >= 9
+        // generic tasks first: the large parts (y >= 7) of every chunk of 32 entries, then the small parts (y <= 6)
         const uint32_t n_gen_tasks = 2u * ((n_entries + 31) / 32);
         const uint32_t n_tasks = n_gen_tasks + n_flush_tasks;
         // kBits: the flush tasks read the compare bits that the generic tasks leave behind, so the group meets in between
@@ -826,11 +840,16 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
             } else {
                 // ================= generic task: 32 merged runouts, the warp walks the rank pairs of P class by class =====
-                // task -> 32 entries x one half of the rank pairs (y <= 8 | y >= 9), as runs of slices of one to six values of y.
-                // (Measured: cutting the three-chunk case into 3 x 5 single-slice tasks so that the five warps finish together is
-                // slower, 52.1 -> 48.9 M situations/s: the per-task set-up chain costs more than the imbalance.)
-                const uint32_t e = (task >> 1) * 32 + lane;
-                const uint32_t sl = (task & 1u) ? 3u : 0u, sl_end = (task & 1u) ? 5u : 3u;
+                // task -> 32 entries x one part of the rank pairs, as a run of slices of two to seven values of y.  The two parts of a
+                // chunk are UNEQUAL on purpose (y >= 7: 63 rank pairs, y <= 6: 28) and the large parts come first in the queue: with
+                // three chunks (no runout completes our flush: 63 % of the flops) the group's five warps take 3 large + 2 small parts
+                // and the first to finish takes the last small one, so the phase lasts 63 steps instead of 2 x 45; with five chunks
+                // every warp gets a large and a small part as before.  (Cutting the three chunks into 3 x 5 single-slice tasks was
+                // measured and is slower, 52.1 -> 48.9 M situations/s: the per-task set-up chain costs more than the imbalance.)
+                const uint32_t n_chunks = n_gen_tasks >> 1;
+                const bool small_part = task >= n_chunks;
+                const uint32_t e = (small_part ? task - n_chunks : task) * 32 + lane;
+                const uint32_t sl = small_part ? 0u : 1u, sl_end = small_part ? 1u : 4u;
                 uint32_t qp = 0, val = 0, mult = 0;
                 if (e < (uint32_t)kPP) {
                     qp = e;
@@ -873,11 +892,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             if ((Y1 * (Y1 + 3) / 2) >> 5 != W0) { atomicOr(&G.LB[W0 + 1][e], lb1); atomicOr(&G.GB[W0 + 1][e], gb1); }               \
         }                                                                                                                           \
     }
-                if (sl == 0) HOLDEM_GEN_SLICE(0, 5, 0)                              // rank pairs  0..20
-                if (sl <= 1 && sl_end > 1) HOLDEM_GEN_SLICE(6, 7, 0)                 //            21..35
-                if (sl <= 2 && sl_end > 2) HOLDEM_GEN_SLICE(8, 8, 1)                 //            36..44
-                if (sl <= 3 && sl_end > 3) HOLDEM_GEN_SLICE(9, 10, 1)                //            45..65
-                if (sl_end > 4) HOLDEM_GEN_SLICE(11, 12, 2)                          //            66..90
+                if (sl == 0) HOLDEM_GEN_SLICE(0, 6, 0)                               // rank pairs  0..27
+                if (sl <= 1 && sl_end > 1) HOLDEM_GEN_SLICE(7, 8, 0)                 //            28..44
+                if (sl <= 2 && sl_end > 2) HOLDEM_GEN_SLICE(9, 10, 1)                //            45..65
+                if (sl_end > 3) HOLDEM_GEN_SLICE(11, 12, 2)                          //            66..90
 #undef HOLDEM_GEN_SLICE
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {

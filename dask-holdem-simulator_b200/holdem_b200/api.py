@@ -126,7 +126,8 @@ def hand_potential_counts(sit: torch.Tensor, mode="treys", out: torch.Tensor = N
     """HS + HP counts per situation: int32 [N,16] = ahead tied behind | HP[3][3] | HPTotal[3] | n_board.
     `out` may be a [N,16] int32 view into a larger buffer (e.g. this rank's slice of an all-gather buffer).
     direct=True forces the plain-enumeration kernel (the independent second implementation).  flop_variant (treys mode,
-    flop rows only; 4 = rank-multiset kernel, 3 / 2 = the 4-set kernels) runs one named implementation of the flop kernel
+    flop rows only; 4 = rank-multiset kernel, 5 / 6 / 7 = that kernel without its closed-form add parts / in input order / with the
+    step-by-step undo half, 3 / 2 = the 4-set kernels) runs one named implementation of the flop kernel
     for A/B measurements; rows of other streets are then left as they are in `out`.  turn_variant (4 = rank-multiset
     kernel, 3 = 3-set walk) does the same for turn rows.  variants=(flop, turn, river) runs a whole mixed-street treys batch
     through named kernels (holdem_hp_batch_variant).  ref_variant (mode='reference': 5 = rank-multiset kernel, 4 = the

@@ -150,8 +150,9 @@ int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *
 /* Treys-mode flop rows through one named implementation of the flop kernel (A/B measurements and cross-checks; every
  * variant returns the same counts): 4 = rank-multiset kernel (what holdem_hp_batch runs), 5 = the same kernel without the
  * closed-form sum of the flush steps' add parts, 6 = the production kernel working the rows in input order instead of heaviest
- * board texture first, 3 = deduplicating 4-set walk, 2 = the earlier warp-per-pair 4-set kernel.
- * Rows with 4- or 5-card boards are left untouched. */
+ * board texture first, 7 = the same kernel with the undo half of the flush part walked step by step instead of taken as weighted
+ * population counts over the generic part's compare bits (the kernel of the first half of round 2), 3 = deduplicating 4-set walk,
+ * 2 = the earlier warp-per-pair 4-set kernel.  Rows with 4- or 5-card boards are left untouched. */
 int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
 /* The same for Treys-mode turn rows (four board cards): 4 = rank-multiset kernel (production), 6 = the same working the rows in
@@ -159,7 +160,7 @@ int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_
  * Rows of other streets are left untouched. */
 int holdem_hp_turn_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
-/* Whole Treys-mode batches (all streets) through named implementations: flop 4 / 3 / 2 and turn 4 / 3 as above, river 0 =
+/* Whole Treys-mode batches (all streets) through named implementations: flop 2..7 and turn 4 / 3 as above, river 0 =
  * rank-pair HS kernel in its HP-row form (production), 1 = plain enumeration.  holdem_hp_batch == (4, 4, 0).  These entry
  * points replace the HOLDEM_*_KERNEL environment switches of ABI version 1: production dispatch reads no environment. */
 int holdem_hp_batch_variant(const uint8_t *d_sit, int64_t n, int flop_variant, int turn_variant, int river_variant,

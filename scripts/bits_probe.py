@@ -29,7 +29,7 @@ if bad.numel():
         print(i, sit[i].tolist(), "suits", (sit[i, :5] // 13).tolist(), "\n  got ", r4[i].tolist(), "\n  want", r7[i].tolist())
     tex = np.array([max(np.bincount(r, minlength=4)) for r in bs])
     print("bad by texture (max suit count 1/2/3):", np.bincount(tex[bad.cpu().numpy()], minlength=4).tolist(), "of", np.bincount(tex, minlength=4).tolist())
-for v in (7, 4, 5):
+for v in (7, 4, 5, 6):
     ms = timed(lambda: hb.hand_potential_counts(d, "treys", flop_variant=v))
     print(f"mixed variant {v}: {n / ms / 1e3:.2f} M/s", flush=True)
 bs = sit[:, 2:5] // 13

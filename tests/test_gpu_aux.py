@@ -181,7 +181,8 @@ def test_variant_entry_points(hb):
     flop = torch.from_numpy(hb.random_situations(8192, seed=77)).cuda()
     assert torch.equal(hb.hand_potential_counts(flop, "treys", flop_variant=5), hb.hand_potential_counts(flop, "treys", flop_variant=4))
     assert torch.equal(hb.hand_potential_counts(flop, "treys", flop_variant=6), hb.hand_potential_counts(flop, "treys", flop_variant=4))
-    for variants in ((4, 4, 0), (3, 3, 1), (2, 4, 1), (4, 3, 0), (5, 4, 0), (6, 4, 0)):
+    assert torch.equal(hb.hand_potential_counts(flop, "treys", flop_variant=7), hb.hand_potential_counts(flop, "treys", flop_variant=4))
+    for variants in ((4, 4, 0), (3, 3, 1), (2, 4, 1), (4, 3, 0), (5, 4, 0), (6, 4, 0), (7, 4, 0)):
         assert torch.equal(hb.hand_potential_counts(sit, "treys", variants=variants), want), variants
     for mode in ("treys", "reference"):
         assert torch.equal(hb.hand_strength_counts(sit, mode, variant=1), hb.hand_strength_counts(sit, mode))

@@ -334,12 +334,13 @@ def _texture_situations(hb):
 
 
 def test_hp_flop_variants_agree_and_match_oracle(hb, oracle):
-    """The three flop kernels (rank-multiset v4 = production, 4-set walk v3, warp-per-pair v2) and the plain enumeration
-    return identical rows; texture cases and 96 random deals are also checked against the CPU oracle."""
+    """The flop kernels (rank-multiset v4 = production, 5 = without its closed-form add parts, 7 = with the step-by-step undo half
+    instead of the bit-parallel one, 4-set walk v3, warp-per-pair v2) and the plain enumeration return identical rows; texture
+    cases and 96 random deals are also checked against the CPU oracle."""
     sit = np.concatenate([_texture_situations(hb), hb.random_situations(96, seed=811)])
     want = oracle.hp_batch(sit, "treys")
     d_sit = torch.from_numpy(sit).cuda()
-    for variant in (4, 3, 2):
+    for variant in (4, 5, 7, 3, 2):
         got = _u32(hb.hand_potential_counts(d_sit, "treys", flop_variant=variant))
         bad = np.nonzero((got != want).any(axis=1))[0]
         assert bad.size == 0, (variant, bad[:5], sit[bad[:5]], got[bad[:5]], want[bad[:5]])
@@ -349,8 +350,9 @@ def test_hp_flop_variants_agree_and_match_oracle(hb, oracle):
     v4 = hb.hand_potential_counts(d_big, "treys", flop_variant=4)
     v3 = hb.hand_potential_counts(d_big, "treys", flop_variant=3)
     assert torch.equal(v4, v3)
+    assert torch.equal(v4, hb.hand_potential_counts(d_big, "treys", flop_variant=7))
     with pytest.raises(hb.HoldemError):
-        hb.hand_potential_counts(d_sit, "treys", flop_variant=7)
+        hb.hand_potential_counts(d_sit, "treys", flop_variant=8)
 
 
 def test_hp_turn_variants_agree_and_match_oracle(hb, oracle):
