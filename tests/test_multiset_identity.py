@@ -55,3 +55,10 @@ def test_reference_mode_identity_matches_literal_oracle(oracle):
         got, n_items = R.ref_flop_counts(hole, board)
         assert np.array_equal(got[:15], want[k][:15]), (hole, board, got, want[k])
         assert n_items < 1081 * 1176 // 4
+
+
+def test_undo_half_step_lists_equal_rank_pair_sets():
+    """The flop kernel's bit-parallel undo half: per rank pair, the weight of a runout lane's step list (validity included)
+    equals what the per-situation sets BS / XS / YS and the static sets lo_t / hi_t give (scripts/bits_identity_check.py)."""
+    import bits_identity_check as B
+    assert B.check(1500, seed=7) == 1500
