@@ -340,7 +340,11 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = __popc(~(uint32_t)(known >> (13 * s)) & 0x1FFFu), nns = kU - nsu;
                 const uint32_t nboth = choose2u(nsu), none = nsu * nns;
                 // step list of the suit: [both cards in s | a | (a, rank of c) | rank pairs without a card of s]
-                const uint32_t len2 = nboth, len1 = nboth + 14u * nsu, len0 = len1 + kPP;
+                // (kBits: the undo-only steps are needed by the step-by-step undo half alone, i.e. by the runouts that complete our flush
+                //  when we hold four or five cards of the suit, and -- their class histograms HA / hist_none -- by monotone boards)
+                const uint32_t hs_s = (hsuit >> (4 * s)) & 15u;
+                const bool short_list = kBits && bs == 2 && hs_s <= 3;
+                const uint32_t len2 = nboth, len1 = nboth + (short_list ? nsu : 14u * nsu), len0 = len1 + kPP;
                 const uint32_t len = bs == 1 ? len2 : (bs == 2 ? len1 : (bs == 3 ? len0 : 0u));
                 // PD offset of the suit = lengths of the suits before it (every lane of a suit holds the same len)
                 uint32_t pdo = 0;
@@ -353,7 +357,6 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t need = 5u - k;                        // 2, 1 or 0 cards of s in P
                 // Runouts with a card outside s are merged by the RANK of that card (weight = number of such cards) unless they
                 // give us a flush, which happens for all of them or none: we need hs_s + (cards of the runout in s) >= 5
-                const uint32_t hs_s = (hsuit >> (4 * s)) & 15u;
                 const bool rank_lanes = qtype != 2 && hs_s + qtype < 5;
                 const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? (rank_lanes ? 13u * nsu : none)
                                                                      : (rank_lanes ? (uint32_t)kPP : choose2u(nns)));
