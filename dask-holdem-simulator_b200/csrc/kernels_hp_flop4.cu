@@ -564,7 +564,15 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     G.PD[e] = make_uint4((bits << 17) | (2u * fold(bits)), 1u << (10 * cls), G.clsw[pp], pp * (kTPitch * 2));
                     atomicAdd(&G.Wc0[s][pr & 0xFFu], 1u << (10 * cls));
                     atomicAdd(&G.Wc0[s][pr >> 8], 1u << (10 * cls));
-                    atomicAdd(&G.Wt0[s], 1u << (10 * cls));
+                    {   // the suit's total: one atomic per warp when the lanes in this branch all work on one suit (the usual case)
+                        const uint32_t act = __activemask();
+                        int same;
+                        __match_all_sync(act, s, &same);
+                        if (same) {
+                            const uint32_t sum = __reduce_add_sync(act, 1u << (10 * cls));
+                            if (lane == (uint32_t)__ffs(act) - 1u) atomicAdd(&G.Wt0[s], sum);
+                        } else atomicAdd(&G.Wt0[s], 1u << (10 * cls));
+                    }
                 } else if (t < nboth + nsu) {                      // one card a in s, any card c outside s: the flop class of {a, c}
                     const uint32_t ra = G.code[G.Ls[s][t - nboth]] >> 2;     // depends on ranks alone (four of the suit at most)
                     uint32_t hist = 0;
