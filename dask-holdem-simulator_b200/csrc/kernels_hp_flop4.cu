@@ -102,7 +102,7 @@ struct Flop4Group {                    // one situation in flight
     uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair (row of DevTables::own_our7)
     uint16_t opp5nf[96];               // non-flush rank of board + rank pair (row of DevTables::board_opp5)
     unsigned long long bar[2];         // mbarriers: [0] the two small rows, [1] T
-    uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8
+    uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8 | number of merged runouts << 21
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
     uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
     uint32_t cnt[2][12];               // lt[3], gt[3], class totals[3]; [situation parity]: the rows are written out of one
@@ -511,28 +511,36 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             HOLDEM_PROF(1)
             // ---- runouts that give us a flush get their own entry of the generic part (their our7 is a suited-table rank) ---------
             if (fneed <= 2) {
-                const uint32_t nfs = G.ns[fs], nnf = kU - nfs, nboth = choose2u(nfs);
-                const uint32_t total = (int)fneed == 2 ? nboth : ((int)fneed == 1 ? nboth + nfs * nnf : (uint32_t)kPairs4);
+                const uint32_t nfs = G.ns[fs], nboth = choose2u(nfs);
+                // fneed == 1: a runout {a in fs, z outside fs} gives us the flush of a whatever z is, so those runouts are merged by the
+                // RANK of z (entry weight = unseen cards of that rank outside fs): 13 entries per a instead of one per card z
+                const uint32_t total = (int)fneed == 2 ? nboth : ((int)fneed == 1 ? nboth + 13u * nfs : (uint32_t)kPairs4);
                 if (tid == 0) G.n_ext = total;
                 for (uint32_t t = tid; t < total; t += kGroupThreads) {
-                    uint32_t i, j;
-                    if ((int)fneed <= 0) {
-                        const uint32_t pr = S.pairs[t];
-                        i = pr & 0xFFu; j = pr >> 8;
-                    } else if (t < nboth) {
-                        const uint32_t pr = S.pairs[t];
-                        i = G.Ls[fs][pr & 0xFFu]; j = G.Ls[fs][pr >> 8];
+                    uint32_t pp, fbits, wgt = 1;
+                    if ((int)fneed == 1 && t >= nboth) {
+                        const uint32_t t2 = t - nboth, a = t2 / 13u, rz = t2 - 13u * a;
+                        const uint32_t ra = G.code[G.Ls[fs][a]] >> 2;
+                        pp = tri(max(ra, rz)) + min(ra, rz);
+                        fbits = 1u << ra;
+                        wgt = G.u[rz] - ((G.smask[fs] >> rz) & 1u);
                     } else {
-                        const uint32_t t2 = t - nboth, a = t2 / nnf, z = t2 - a * nnf;
-                        const uint32_t x = G.Ls[fs][a], y = G.Lns[fs][z];
-                        i = min(x, y); j = max(x, y);
+                        uint32_t i, j;
+                        if ((int)fneed <= 0) {
+                            const uint32_t pr = S.pairs[t];
+                            i = pr & 0xFFu; j = pr >> 8;
+                        } else {
+                            const uint32_t pr = S.pairs[t];
+                            i = G.Ls[fs][pr & 0xFFu]; j = G.Ls[fs][pr >> 8];
+                        }
+                        const uint32_t ci = G.code[i], cj = G.code[j];
+                        const uint32_t ri = ci >> 2, rj = cj >> 2;
+                        fbits = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
+                        pp = tri(rj) + ri;
                     }
-                    const uint32_t ci = G.code[i], cj = G.code[j];
-                    const uint32_t ri = ci >> 2, rj = cj >> 2;
-                    const uint32_t fbits = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
-                    const uint32_t pp = tri(rj) + ri;
-                    G.ext[t] = pp | ((uint32_t)S.flush[fold(hbmask | fbits)] << 8);      // slot = index of the runout in its list
-                    atomicAdd(&G.qflush[pp], 1u);
+                    // entry = rank pair | our7 (a suited-table rank) << 8 | weight << 21; slot = index of the runout in its list
+                    G.ext[t] = pp | ((uint32_t)S.flush[fold(hbmask | fbits)] << 8) | (wgt << 21);
+                    if (wgt) atomicAdd(&G.qflush[pp], wgt);
                 }
             }
             HOLDEM_PROF(4)
@@ -868,8 +876,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 } else if (e < n_entries) {
                     const uint32_t en = G.ext[e - kPP];
                     qp = en & 0xFFu;
-                    val = en >> 8;
-                    mult = 1;
+                    val = (en >> 8) & 0x1FFFu;
+                    mult = en >> 21;
                 }
                 const uint32_t qxy = S.ppxy[qp], q1 = qxy & 15u, q2 = qxy >> 4;
                 if (e < (uint32_t)kPP) {
