@@ -81,7 +81,6 @@ constexpr int kF4Unroll = HOLDEM_F4_UNROLL;      // step unroll of the flush par
 constexpr int kGroupThreads = HOLDEM_F4_GT;
 constexpr int kGroups = HOLDEM_F4_G;
 constexpr int kThreads4 = kGroupThreads * kGroups;
-constexpr int kU = 47;
 constexpr int kPairs4 = 1081;
 constexpr int kPP = 91;            // rank pairs x <= y, index y(y+1)/2 + x
 constexpr int kTPitch = 94;        // u16 units (tables.h kBoardTPitch)
@@ -110,8 +109,7 @@ struct Flop4Group {                    // one situation in flight
     uint32_t bmask[4];                 // board rank mask per suit
     uint32_t g_first[kMaxGroups + 1];  // first task id of each flush group; [n_groups] = total
     uint32_t g_nq[kMaxGroups], g_np[kMaxGroups], g_nseg[kMaxGroups], g_seglen[kMaxGroups], g_pdbase[kMaxGroups];
-    uint32_t g_sq[kMaxGroups];         // suit | qtype << 2 | rank-level lanes << 4
-    uint32_t g_inv[kMaxGroups];        // ceil(2^16 / cards outside the suit): lane index / that count by multiplication
+    uint32_t g_sq[kMaxGroups];         // suit | qtype << 2
     uint32_t pd_base[4], pd_len[4];    // PD section per suit
     uint32_t smask[4];                 // rank mask of the unseen cards per suit
     uint32_t hist_none[4];             // holdings without a card of the board's suit, by flop class (monotone boards)
@@ -337,8 +335,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             {
                 // ---- flush task groups and PD sections: lane = 3 * suit + (2 - qtype), scans over the warp -------------------------
                 const uint32_t s = min(lane / 3u, 3u), qtype = 2u - (lane - 3u * (lane / 3u));
-                const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = __popc(~(uint32_t)(known >> (13 * s)) & 0x1FFFu), nns = kU - nsu;
-                const uint32_t nboth = choose2u(nsu), none = nsu * nns;
+                const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = __popc(~(uint32_t)(known >> (13 * s)) & 0x1FFFu);
+                const uint32_t nboth = choose2u(nsu);
                 // step list of the suit: [both cards in s | a | (a, rank of c) | rank pairs without a card of s]
                 // (kBits: the undo-only steps are needed by the step-by-step undo half alone, i.e. by the runouts that complete our flush
                 //  when we hold four or five cards of the suit, and -- their class histograms HA / hist_none -- by monotone boards)
@@ -355,11 +353,10 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 }
                 const uint32_t k = bs + qtype;                       // cards of s in board + runout
                 const uint32_t need = 5u - k;                        // 2, 1 or 0 cards of s in P
-                // Runouts with a card outside s are merged by the RANK of that card (weight = number of such cards) unless they
-                // give us a flush, which happens for all of them or none: we need hs_s + (cards of the runout in s) >= 5
-                const bool rank_lanes = qtype != 2 && hs_s + qtype < 5;
-                const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? (rank_lanes ? 13u * nsu : none)
-                                                                     : (rank_lanes ? (uint32_t)kPP : choose2u(nns)));
+                // Runouts with a card outside s are merged by the RANK of that card (weight = number of such cards): the card matters
+                // through its rank alone -- also when the runout completes OUR flush (hs_s + cards of the runout in s >= 5, true for all
+                // runouts of a group or none), because that flush is made of our cards, the board's and the runout's card of s
+                const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? 13u * nsu : (uint32_t)kPP);
                 const uint32_t np = need == 2 ? len2 : (need == 1 ? len1 : len0);
                 const bool live = lane < 12 && bs != 0 && k >= 3 && nq != 0 && np != 0;
                 // (kBits: only the runouts that complete our flush without being the pairs of ten cards still walk the whole step list)
@@ -385,8 +382,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (live) {
                     G.g_nq[gi] = nq; G.g_np[gi] = np; G.g_nseg[gi] = nseg; G.g_seglen[gi] = seglen;
                     G.g_pdbase[gi] = pdo;
-                    G.g_sq[gi] = s | (qtype << 2) | ((uint32_t)rank_lanes << 4);
-                    G.g_inv[gi] = 65535u / max(nns, 1u) + 1u;          // exact for indices < 2^16 / nns (here < 600)
+                    G.g_sq[gi] = s | (qtype << 2);
                 }
                 if (lane < 12 && qtype == 2) { G.pd_base[s] = pdo; G.pd_len[s] = len; }
                 if (lane == 11) {
@@ -647,17 +643,17 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t nseg = G.g_nseg[g], seglen = G.g_seglen[g], np = G.g_np[g], nq = G.g_nq[g];
                 const uint32_t chunk = nseg == 1 ? local : local / nseg, seg = local - chunk * nseg;
                 const uint32_t s = G.g_sq[g] & 3u, qtype = (G.g_sq[g] >> 2) & 3u;
-                const bool rank_lanes = (G.g_sq[g] >> 4) != 0;
                 const uint32_t p0 = seg * seglen, p1 = min(np, p0 + seglen);
                 const uint32_t qi = chunk * 32 + lane;
-                const uint32_t nsu = G.ns[s], nns = kU - nsu, sm = G.smask[s];
+                const uint32_t nsu = G.ns[s], sm = G.smask[s];
                 // the lane's runout: our rank, its cards of s (rank bits), folded flush index of board + runout in s, its column
-                // of T, its multiplicity; zpos / rz describe its card outside s for the fix-up below
-                uint32_t our = 0, fqf = 0, qb2 = 0, zpos = 0xFFu, rz = 0, qcol = 0, wl = 0, rq = 99;
+                // of T, its multiplicity; rz = the rank of its card outside s for the fix-up below
+                uint32_t our = 0, fqf = 0, qb2 = 0, rz = 0, qcol = 0, wl = 0, rq = 99;
                 uint32_t ia = 0xFFu, ib = 0xFFu;       // the runout's cards of s as indices into Ls[s] (fast path below)
                 if (qi < nq) {
                     uint32_t qbits, ppq;
-                    if (rank_lanes && qtype == 1) {            // (card q of s, rank of the other card)
+                    const bool ours = ((hsuit >> (4 * s)) & 15u) + qtype >= 5u;        // the group's runouts complete our flush (s == fs)
+                    if (qtype == 1) {                          // (card q of s, rank of the other card)
                         const uint32_t a = qi / 13u;
                         ia = a;
                         rz = qi - 13u * a;
@@ -665,36 +661,23 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         qbits = 1u << rq;
                         ppq = tri(max(rq, rz)) + min(rq, rz);
                         wl = G.u[rz] - ((sm >> rz) & 1u);
-                        our = G.our7nf[ppq];
-                    } else if (rank_lanes) {                   // rank pair, neither card in s
+                        our = ours ? (uint32_t)S.flush[fold(hbmask | qbits)] : (uint32_t)G.our7nf[ppq];
+                    } else if (qtype == 0) {                   // rank pair, neither card in s
                         const uint32_t xy = S.ppxy[qi], x = xy & 15u, y = xy >> 4;
                         const uint32_t wx = G.u[x] - ((sm >> x) & 1u), wy = G.u[y] - ((sm >> y) & 1u);
                         qbits = 0;
                         ppq = qi;
                         wl = x != y ? wx * wy : (wx ? choose2u(wx) : 0u);
-                        our = G.our7nf[ppq];
-                    } else {
-                        uint32_t i, j;
-                        if (qtype == 1) {
-                            const uint32_t a = (qi * G.g_inv[g]) >> 16, z = qi - a * nns;      // qi / nns
-                            const uint32_t x = G.Ls[s][a], y = G.Lns[s][z];
-                            ia = a;
-                            i = min(x, y); j = max(x, y);
-                            zpos = y;
-                        } else {
-                            const uint32_t pr = S.pairs[qi];
-                            const uint8_t *L = qtype == 2 ? G.Ls[s] : G.Lns[s];
-                            i = L[pr & 0xFFu]; j = L[pr >> 8];
-                            if (qtype == 2) { ia = pr & 0xFFu; ib = pr >> 8; }
-                        }
-                        const uint32_t ci = G.code[i], cj = G.code[j];
-                        const uint32_t ri = ci >> 2, rj = cj >> 2;
-                        {   // our rank on board + this runout: a suited-table rank when it completes our flush
-                            const uint32_t fb = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
-                            our = (int)__popc(fb) >= (int)fneed ? (uint32_t)S.flush[fold(hbmask | fb)] : (uint32_t)G.our7nf[tri(rj) + ri];
-                        }
-                        qbits = ((ci & 3u) == s ? 1u << ri : 0u) | ((cj & 3u) == s ? 1u << rj : 0u);
+                        our = ours ? (uint32_t)S.flush[fold(hbmask)] : (uint32_t)G.our7nf[ppq];
+                    } else {                                   // both cards in s
+                        const uint32_t pr = S.pairs[qi];
+                        ia = pr & 0xFFu; ib = pr >> 8;
+                        const uint32_t ri = G.code[G.Ls[s][ia]] >> 2, rj = G.code[G.Ls[s][ib]] >> 2;
+                        qbits = (1u << ri) | (1u << rj);
                         ppq = tri(rj) + ri;
+                        // our rank on board + this runout: a suited-table rank when it completes our flush (in s, or the one we hold)
+                        const uint32_t fb = s == fs ? qbits : 0u;
+                        our = (int)__popc(fb) >= (int)fneed ? (uint32_t)S.flush[fold(hbmask | fb)] : (uint32_t)G.our7nf[ppq];
                         wl = 1;
                     }
                     qb2 = qbits << 17;
@@ -821,7 +804,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         if (our > rf) accG[c] += G.hist_none[c];
                     }
                 }
-                if (seg == 0 && need == 1 && qtype == 1 && rank_lanes) {
+                if (seg == 0 && need == 1 && qtype == 1) {
                     // every card z of rank rz outside s was counted among the c of {a, c} in its own runout: take the pairs
                     // {a, z} out again -- summed over z they are the class histogram HA[a][rz] and wl undo steps of (ra, rz)
                     for (uint32_t ai = 0; ai < nsu; ++ai) {
@@ -835,24 +818,6 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                             for (uint32_t c = 0; c < 3; ++c) {
                                 accL[c] += (our < rn ? (cw >> (10 * c)) & 0x3FFu : 0u) - (our < rf ? (ha >> (10 * c)) & 0x3FFu : 0u);
                                 accG[c] += (our > rn ? (cw >> (10 * c)) & 0x3FFu : 0u) - (our > rf ? (ha >> (10 * c)) & 0x3FFu : 0u);
-                            }
-                        }
-                    }
-                } else if (seg == 0 && need == 1 && qtype == 1) {
-                    // the runout's card z outside s was counted among the c of every {a, c}: take {a, z} out again
-                    rz = zpos < (uint32_t)kU ? (uint32_t)(G.code[zpos] >> 2) : 0u;
-                    for (uint32_t ai = 0; ai < nsu; ++ai) {
-                        const uint32_t pa = G.Ls[s][ai], ra = G.code[pa] >> 2;
-                        if (qi < nq && !((qb2 >> (ra + 17)) & 1u)) {
-                            const uint32_t rf = lds_u16(flush_s + (fqf ^ (2u * fold(1u << ra))));
-                            const uint32_t pp = tri(max(ra, rz)) + min(ra, rz);
-                            const uint32_t cl = G.clsr[pp];            // {a in s, z outside s}: no flopped flush
-                            const uint32_t rn = lds_u16(tq_s + pp * (kTPitch * 2));
-                            const uint32_t cr = G.clsr[pp];
-#pragma unroll
-                            for (uint32_t c = 0; c < 3; ++c) {
-                                accL[c] += (uint32_t)(cr == c && our < rn) - (uint32_t)(cl == c && our < rf);
-                                accG[c] += (uint32_t)(cr == c && our > rn) - (uint32_t)(cl == c && our > rf);
                             }
                         }
                     }
