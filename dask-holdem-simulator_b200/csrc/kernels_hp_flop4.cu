@@ -89,7 +89,8 @@ constexpr int kSeg = 64;           // longest step segment of a flush task (pack
 constexpr int kPD = 320;           // step descriptors per situation: at most 3 x 66 (rainbow) or 45 + 14 x 11 + 91 + 66
 constexpr int kMaxGroups = 12;
 constexpr int kProfSlots = 8;
-constexpr int kBitEntries = 160;   // entries of the generic part whose compare bits are kept: 91 + C(10,2) = 136
+constexpr int kExt = 224;           // entries of the runouts that complete our flush: C(10,2) | C(9,2) + 13 x 9 | C(8,2) + 13 x 8 + 91
+constexpr int kBitEntries = 320;   // entries of the generic part (their compare bits are kept): 91 + kExt at most
 constexpr int kClaim = HOLDEM_F4_CLAIM;           // situations a group claims from the global work counter at a time
 
 struct Flop4Group {                    // one situation in flight
@@ -101,7 +102,7 @@ struct Flop4Group {                    // one situation in flight
     uint16_t our7nf[96];               // non-flush rank of hole + board + rank pair (row of DevTables::own_our7)
     uint16_t opp5nf[96];               // non-flush rank of board + rank pair (row of DevTables::board_opp5)
     unsigned long long bar[2];         // mbarriers: [0] the two small rows, [1] T
-    uint32_t ext[kPairs4 + 3];         // runouts that give us a flush: rank pair | our7 << 8 | number of merged runouts << 21
+    uint32_t ext[kExt];                // runouts that give us a flush: rank pair | our7 << 8 | number of merged runouts << 21
     uint32_t clsw[96];                 // per rank pair: 1 << 10 clsr, 0 when the pair cannot exist with this board
     uint32_t qflush[96];               // per rank pair: runouts moved to ext[]
     uint32_t cnt[2][12];               // lt[3], gt[3], class totals[3]; [situation parity]: the rows are written out of one
@@ -285,7 +286,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         if (tid >= 32 && tid < 128) G.qflush[tid - 32] = 0;
         if (kBits) {
 #pragma unroll
-            for (int w = 0; w < 3; ++w) { G.LB[w][tid] = 0; G.GB[w][tid] = 0; }
+            for (int w = 0; w < 3; ++w)
+#pragma unroll
+                for (int k = 0; k < kBitEntries; k += kGroupThreads) { G.LB[w][k + tid] = 0; G.GB[w][k + tid] = 0; }
         }
         // The set-up below is spread over the group's five warps (a dependent instruction costs ~40 cycles on the busy SM, so the
         // length of the longest chain is what counts): warp 0 sorts the unseen cards, warps 2 and 3 build the per-suit position lists
@@ -338,10 +341,9 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t bs = (bsuit >> (4 * s)) & 15u, nsu = __popc(~(uint32_t)(known >> (13 * s)) & 0x1FFFu);
                 const uint32_t nboth = choose2u(nsu);
                 // step list of the suit: [both cards in s | a | (a, rank of c) | rank pairs without a card of s]
-                // (kBits: the undo-only steps are needed by the step-by-step undo half alone, i.e. by the runouts that complete our flush
-                //  when we hold four or five cards of the suit, and -- their class histograms HA / hist_none -- by monotone boards)
-                const uint32_t hs_s = (hsuit >> (4 * s)) & 15u;
-                const bool short_list = kBits && bs == 2 && hs_s <= 3;
+                // (kBits: the undo-only steps are needed by the step-by-step undo half alone and -- their class histograms HA /
+                //  hist_none -- by monotone boards)
+                const bool short_list = kBits && bs == 2;
                 const uint32_t len2 = nboth, len1 = nboth + (short_list ? nsu : 14u * nsu), len0 = len1 + kPP;
                 const uint32_t len = bs == 1 ? len2 : (bs == 2 ? len1 : (bs == 3 ? len0 : 0u));
                 // PD offset of the suit = lengths of the suits before it (every lane of a suit holds the same len)
@@ -359,9 +361,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t nq = qtype == 2 ? nboth : (qtype == 1 ? 13u * nsu : (uint32_t)kPP);
                 const uint32_t np = need == 2 ? len2 : (need == 1 ? len1 : len0);
                 const bool live = lane < 12 && bs != 0 && k >= 3 && nq != 0 && np != 0;
-                // (kBits: only the runouts that complete our flush without being the pairs of ten cards still walk the whole step list)
-                const bool whole_list = kBits && (hs_s + qtype < 5u || hs_s == 3u);
-                const uint32_t nseg = whole_list ? 1u : (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
+                // (kBits: only the add half of some lanes still walks steps, and those with an add part are few: one task per 32 runouts)
+                const uint32_t nseg = kBits ? 1u : (np + kSeg - 1) / kSeg, seglen = live ? (np + nseg - 1) / nseg : 0u;
                 const uint32_t ntask = live ? ((nq + 31) / 32) * nseg : 0u;
                 // task groups in order of the cards of s still needed (0, 1, 2): the ones with the longest step lists first
                 const uint32_t livem = __ballot_sync(0xFFFFFFFFu, live);
@@ -508,31 +509,32 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             // ---- runouts that give us a flush get their own entry of the generic part (their our7 is a suited-table rank) ---------
             if (fneed <= 2) {
                 const uint32_t nfs = G.ns[fs], nboth = choose2u(nfs);
-                // fneed == 1: a runout {a in fs, z outside fs} gives us the flush of a whatever z is, so those runouts are merged by the
-                // RANK of z (entry weight = unseen cards of that rank outside fs): 13 entries per a instead of one per card z
-                const uint32_t total = (int)fneed == 2 ? nboth : ((int)fneed == 1 ? nboth + 13u * nfs : (uint32_t)kPairs4);
+                // A runout's cards outside fs do not change our flush, so the runouts are merged by the RANKS of those cards (entry weight
+                // = number of such cards / pairs of cards): C(nfs,2) entries for the runouts inside fs (fneed <= 2), 13 per card a of fs
+                // for {a, z outside fs} (fneed <= 1), 91 rank pairs for the runouts without a card of fs (fneed == 0: we hold the flush)
+                const uint32_t n1 = nboth + 13u * nfs;
+                const uint32_t total = (int)fneed == 2 ? nboth : ((int)fneed == 1 ? n1 : n1 + (uint32_t)kPP);
                 if (tid == 0) G.n_ext = total;
+                const uint32_t smf = G.smask[fs];
                 for (uint32_t t = tid; t < total; t += kGroupThreads) {
                     uint32_t pp, fbits, wgt = 1;
-                    if ((int)fneed == 1 && t >= nboth) {
+                    if (t < nboth) {
+                        const uint32_t pr = S.pairs[t];
+                        const uint32_t ri = G.code[G.Ls[fs][pr & 0xFFu]] >> 2, rj = G.code[G.Ls[fs][pr >> 8]] >> 2;
+                        fbits = (1u << ri) | (1u << rj);
+                        pp = tri(rj) + ri;
+                    } else if (t < n1) {
                         const uint32_t t2 = t - nboth, a = t2 / 13u, rz = t2 - 13u * a;
                         const uint32_t ra = G.code[G.Ls[fs][a]] >> 2;
                         pp = tri(max(ra, rz)) + min(ra, rz);
                         fbits = 1u << ra;
-                        wgt = G.u[rz] - ((G.smask[fs] >> rz) & 1u);
+                        wgt = G.u[rz] - ((smf >> rz) & 1u);
                     } else {
-                        uint32_t i, j;
-                        if ((int)fneed <= 0) {
-                            const uint32_t pr = S.pairs[t];
-                            i = pr & 0xFFu; j = pr >> 8;
-                        } else {
-                            const uint32_t pr = S.pairs[t];
-                            i = G.Ls[fs][pr & 0xFFu]; j = G.Ls[fs][pr >> 8];
-                        }
-                        const uint32_t ci = G.code[i], cj = G.code[j];
-                        const uint32_t ri = ci >> 2, rj = cj >> 2;
-                        fbits = ((ci & 3u) == fs ? 1u << ri : 0u) | ((cj & 3u) == fs ? 1u << rj : 0u);
-                        pp = tri(rj) + ri;
+                        pp = t - n1;
+                        const uint32_t xy = S.ppxy[pp], x = xy & 15u, y = xy >> 4;
+                        const uint32_t wx = G.u[x] - ((smf >> x) & 1u), wy = G.u[y] - ((smf >> y) & 1u);
+                        fbits = 0;
+                        wgt = x != y ? wx * wy : (wx ? choose2u(wx) : 0u);
                     }
                     // entry = rank pair | our7 (a suited-table rank) << 8 | weight << 21; slot = index of the runout in its list
                     G.ext[t] = pp | ((uint32_t)S.flush[fold(hbmask | fbits)] << 8) | (wgt << 21);
@@ -695,14 +697,16 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 // -> unseen cards of c's rank outside s (XC, by which of the two ranks is a's), no card in s -> YC; a step is valid when
                 // its cards of s avoid the runout's (lo_t / hi_t rows of the runout's ranks in s).
                 const uint32_t hs_s = (hsuit >> (4 * s)) & 15u;
-                const bool ext_lanes = hs_s + qtype >= 5u;                   // every runout of the group completes our flush
-                const bool bits_path = kBits && (!ext_lanes || hs_s == 3u);  // (hs_s == 3: they are the pairs of <= 10 cards, entry 91 + qi)
-                if (bits_path) {
+                const bool ext_lanes = hs_s + qtype >= 5u;                   // every runout of the group completes our flush (s == fs)
+                if (kBits) {
                     const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
                     const bool fast = kFastAdd && __all_sync(0xFFFFFFFFu, our > 1599u || qi >= nq);
                     if (seg == 0) {
                         const uint32_t qbits = qb2 >> 17, rest = qbits & (qbits - 1u);
-                        const uint32_t ppq = ext_lanes ? (qi < nq ? (uint32_t)kPP + qi : 0u) : qcol >> 1;
+                        // the lane's entry of the generic part: merged runout ppq, or -- in the order the our-flush entries were written --
+                        // [pairs inside s | 13 per card of s | 91 rank pairs without a card of s]
+                        const uint32_t ext_first = qtype == 2 ? 0u : choose2u(nsu) + (qtype == 1 ? 0u : 13u * nsu);
+                        const uint32_t ppq = ext_lanes ? (qi < nq ? (uint32_t)kPP + ext_first + qi : 0u) : qcol >> 1;
                         const uint32_t r1 = qbits ? (uint32_t)__ffs(qbits) - 1u : 13u, r2 = rest ? (uint32_t)__ffs(rest) - 1u : 13u;
 #pragma unroll 1
                         for (uint32_t w = 0; w < 3; ++w) {
