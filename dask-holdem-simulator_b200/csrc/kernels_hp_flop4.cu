@@ -27,9 +27,9 @@
 //                        plus one rank-level undo step per rank of c; holdings without a card of s (only when board+Q is
 //                        already a flush) cost one compare plus one undo step per rank pair.  Runouts get the same
 //                        treatment from their side: a runout card outside s matters through its rank only, so those
-//                        runouts are merged into weighted lanes (unless they complete OUR flush, which is true for all of
-//                        them or none); a runout card outside s that coincides with c is taken out again by a short
-//                        per-lane fix-up loop.
+//                        runouts are merged into weighted lanes (also when they complete OUR flush, which is true for all of
+//                        them or none and does not depend on that card); a runout card outside s that coincides with c is
+//                        taken out again by a short per-lane fix-up loop.
 //   Our own flushes need no special case: our7[Q] is evaluated per card pair Q.
 //
 // Shared memory (~150 KB per CTA): static flush[8192] u16 (index bits folded, m ^ m >> 6, so that the bank depends on ten
@@ -53,9 +53,13 @@
 //     outside s, by which of the two ranks is a's; YS: no card in s, bit slices of the pair count), the flop classes are three more
 //     sets (CL), and a step is valid when its cards of s avoid the runout's, i.e. outside the static sets lo_t / hi_t of the
 //     runout's ranks in s.  ~75 instructions per lane for a 66-step list, ~330 for a 210-step one, instead of 10 per step.
-//     The runouts that complete OUR flush keep the step-by-step undo half (their our7 is a suited rank) unless they are the
-//     pairs of ten cards (hole + board hold three of the suit: the common case), whose generic entries keep their bits too.
-//   19.6 K -> 15.5 K warp instructions per situation, 43.5 -> 52 M situations/s with the set-up phase spread over the five warps.
+//     The runouts that complete OUR flush have generic entries of their own (suited our7): one per pair of cards inside the suit,
+//     and -- because a runout card outside the suit changes neither our flush nor anything but a rank -- one per (card of the
+//     suit, rank of the other card) / per rank pair with a weight; at most 224 entries, all with compare bits, so every task group
+//     takes this path and the step-by-step undo half only exists in the kBits = false instantiation (holdem_hp_flop_variant 7).
+//   19.6 K -> 13 K warp instructions per situation, 43.5 -> 60 M situations/s together with: the set-up phase spread over the five
+//   warps, rank-merged lanes for the runouts that complete our flush, unequal parts of the generic chunks, the next claim made by
+//   the first warp that runs out of flush tasks.
 #include "device_common.cuh"
 #include "launch.h"
 #include "multiset_common.cuh"
@@ -138,7 +142,7 @@ struct Flop4Group {                    // one situation in flight
     uint32_t XS[2][2][3];              // [which card is in s: lo / hi][weight bit][word]: holdings {a in s, c outside s} of the suit with
                                        // two or more board cards, weight = unseen cards of c's rank outside s
     uint32_t YS[4][3];                 // [weight bit][word]: holdings without a card of s (monotone boards)
-    uint32_t next_ftask, pd_next;
+    uint32_t next_ftask, pd_next, claim_flag;
 };
 
 struct Flop4Smem {
@@ -392,6 +396,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                     G.next_task = 0;
                     G.next_ftask = 0;
                     G.pd_next = 0;
+                    G.claim_flag = 0;
                     G.n_ext = 0;
                 }
             }
@@ -607,10 +612,11 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
         }
         HOLDEM_PROF(5)
         group_sync(gid);                                                                            // (D)
-        if (!next_claimed) {                                           // fetch the next claim under this situation's tasks
-            if (tid == 0) make_claim((claim_it + 1) & 1, claim_it + 1);
-            next_claimed = true;
-        }
+        // The next claim (a global atomic, then the row number through the work order: two dependent global accesses) is made by the
+        // first warp that runs out of flush tasks, in the time it would otherwise wait at barrier (E) -- not at the start of the task
+        // phase, where the claiming warp arrived late at the barrier between the generic and the flush tasks.
+        const bool claim_here = !next_claimed;
+        next_claimed = true;
         mbar_wait(bar1_s, parity);                                     // T has landed
         parity ^= 1u;
         HOLDEM_PROF(2)
@@ -631,9 +637,15 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
             if (kBits) {
                 if (phase == 0) {
                     if (task >= n_gen_tasks) { phase = 1; group_sync(gid); HOLDEM_PROF(6) continue; }
-                } else if (task >= n_flush_tasks) break;
+                } else if (task >= n_flush_tasks) {
+                    if (claim_here && lane == 0 && atomicExch(&G.claim_flag, 1u) == 0u) make_claim((claim_it + 1) & 1, claim_it + 1);
+                    break;
+                }
             } else {
-                if (task >= n_tasks) break;
+                if (task >= n_tasks) {
+                    if (claim_here && lane == 0 && atomicExch(&G.claim_flag, 1u) == 0u) make_claim((claim_it + 1) & 1, claim_it + 1);
+                    break;
+                }
                 phase = task >= n_gen_tasks ? 1u : 0u;
                 if (phase) task -= n_gen_tasks;
             }
