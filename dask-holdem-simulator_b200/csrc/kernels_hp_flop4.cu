@@ -150,6 +150,8 @@ struct Flop4Smem {
     uint16_t pairs[kPairs4 + 3];       // colex pairs i | j << 8 of 47 positions
     uint8_t ppxy[96];                  // rank pair -> x | y << 4
     uint32_t lo_t[14][3], hi_t[14][3]; // rank r -> the rank pairs whose lower / higher rank is r (row 13: empty)
+    uint32_t sf3[256];                 // bit m: the 13-bit rank set m has three or more ranks inside some straight window (A2345 .. TJQKA):
+                                       // two more cards of the suit could make a straight flush
     Flop4Group G[kGroups];
 };
 
@@ -194,6 +196,16 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 if (pp < (uint32_t)kPP && (hi_tab ? y : x) == r) m |= 1u << b;
             }
             (hi_tab ? S.hi_t : S.lo_t)[r][w] = m;
+        }
+        if (kBits) {
+            for (uint32_t wd = threadIdx.x >> 5; wd < 256u; wd += kThreads4 / 32) {
+                const uint32_t m = 32u * wd + (threadIdx.x & 31u);
+                bool three = __popc(m & 0x100Fu) >= 3;                               // A2345
+#pragma unroll
+                for (int i = 0; i < 9; ++i) three = three || __popc(m & (0x1Fu << i)) >= 3;
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, three);
+                if ((threadIdx.x & 31u) == 0) S.sf3[wd] = word;
+            }
         }
         if (tid < kProfSlots) G.prof[tid] = 0;
         if (tid == 0) {
@@ -662,7 +674,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const uint32_t nsu = G.ns[s], sm = G.smask[s];
                 // the lane's runout: our rank, its cards of s (rank bits), folded flush index of board + runout in s, its column
                 // of T, its multiplicity; rz = the rank of its card outside s for the fix-up below
-                uint32_t our = 0, fqf = 0, qb2 = 0, rz = 0, qcol = 0, wl = 0, rq = 99;
+                uint32_t our = 0, fqf = 0, qb2 = 0, rz = 0, qcol = 0, wl = 0, rq = 99, easy = 1;
                 uint32_t ia = 0xFFu, ib = 0xFFu;       // the runout's cards of s as indices into Ls[s] (fast path below)
                 if (qi < nq) {
                     uint32_t qbits, ppq;
@@ -695,8 +707,13 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                         wl = 1;
                     }
                     qb2 = qbits << 17;
-                    fqf = 2u * fold(G.bmask[s] | qbits);
+                    const uint32_t mbq = G.bmask[s] | qbits;
+                    fqf = 2u * fold(mbq);
                     qcol = 2u * ppq;
+                    // the add parts of the lane in closed form?  Every flush step ranks the opponent by a real flush (323..1599, or a
+                    // straight flush 1..10).  our > 1599: we lose every one of them; our <= 322 (quads / full house, never a flush on
+                    // this path unless the runout completes ours): we win every one unless a straight flush is possible at all.
+                    easy = our > 1599u ? 1u : ((kBits && our > 10u && our <= 322u && !((S.sf3[mbq >> 5] >> (mbq & 31u)) & 1u)) ? 2u : 0u);
                 }
                 const uint32_t tq_s = t_s + qcol;
                 const uint4 *pd = G.PD + G.g_pdbase[g] + p0;
@@ -712,7 +729,7 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                 const bool ext_lanes = hs_s + qtype >= 5u;                   // every runout of the group completes our flush (s == fs)
                 if (kBits) {
                     const uint32_t split = min(p1, max(p0, choose2u(nsu) + nsu));
-                    const bool fast = kFastAdd && __all_sync(0xFFFFFFFFu, our > 1599u || qi >= nq);
+                    const bool fast = kFastAdd && __all_sync(0xFFFFFFFFu, easy != 0u);
                     if (seg == 0) {
                         const uint32_t qbits = qb2 >> 17, rest = qbits & (qbits - 1u);
                         // the lane's entry of the generic part: merged runout ppq, or -- in the order the our-flush entries were written --
@@ -757,7 +774,8 @@ hp_flop_treys_v4_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__
                             uint32_t add = G.Wt0[s] + (with_one ? G.Ht[s] : 0u);
                             if (ia != 0xFFu) add -= G.Wc0[s][ia] + (with_one ? G.Hs[s][ia] : 0u);
                             if (ib != 0xFFu) add -= G.Wc0[s][ib] + (with_one ? G.Hs[s][ib] : 0u) - G.PD[G.g_pdbase[g] + qi].y;
-                            aG = add;
+                            if (easy == 1u) aG = add;                        // our > suited rank for every one of them
+                            else aL = add;                                   // quads / full house against flushes
                         }
                     } else {                                                 // add half step by step: suited-table gather, two compares
 #pragma unroll kF4Unroll
