@@ -151,7 +151,7 @@ int holdem_hp_batch_direct(const uint8_t *d_sit, int64_t n, int mode, uint32_t *
  * variant returns the same counts): 4 = rank-multiset kernel (what holdem_hp_batch runs), 5 = the same kernel without the
  * closed-form sum of the flush steps' add parts, 6 = the production kernel working the rows in input order instead of heaviest
  * board texture first, 7 = the same kernel with the undo half of the flush part walked step by step instead of taken as weighted
- * population counts over the generic part's compare bits (the kernel of the first half of round 2), 3 = deduplicating 4-set walk,
+ * population counts over the generic part's compare bits (the construction of round 1), 3 = deduplicating 4-set walk,
  * 2 = the earlier warp-per-pair 4-set kernel.  Rows with 4- or 5-card boards are left untouched. */
 int holdem_hp_flop_variant(const uint8_t *d_sit, int64_t n, int variant, uint32_t *d_out, void *stream);
 
