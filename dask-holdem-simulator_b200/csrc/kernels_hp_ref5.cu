@@ -412,11 +412,12 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
             // the runout as a lane of the flush part: with a card outside a suit it matters through that card's RANK only
             if (si != sj) {                                  // exactly one card in suit si and one in suit sj
                 const uint32_t sl_i = (slotmap >> (4 * si)) & 15u, sl_j = (slotmap >> (4 * sj)) & 15u;
-                if (sl_i < 2) { const uint32_t k = (ri * 13 + rj) * 9 + o; atomicAdd(&S.A1[sl_i][k >> 3], 1u << (4 * (k & 7u))); }
-                if (sl_j < 2) { const uint32_t k = (rj * 13 + ri) * 9 + o; atomicAdd(&S.A1[sl_j][k >> 3], 1u << (4 * (k & 7u))); }
+                // (key = our category x 169 + rank of the card in s x 13 + rank of the other card: category-major, see the lane lists)
+                if (sl_i < 2) { const uint32_t k = o * 169u + ri * 13u + rj; atomicAdd(&S.A1[sl_i][k >> 3], 1u << (4 * (k & 7u))); }
+                if (sl_j < 2) { const uint32_t k = o * 169u + rj * 13u + ri; atomicAdd(&S.A1[sl_j][k >> 3], 1u << (4 * (k & 7u))); }
             }
             if (a0suit < 4 && si != a0suit && sj != a0suit) {
-                const uint32_t k = qp * 9 + o;
+                const uint32_t k = o * (uint32_t)kPP5 + qp;
                 atomicAdd(&S.A0[k >> 3], 1u << (4 * (k & 7u)));
             }
         }
@@ -457,9 +458,12 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
         }
         // ---- the merged runout lanes: non-zero counters of A1 (per slot) and A0, as key | multiplicity << 16 ------------------------------
         {
-            auto compact16 = [&](const uint32_t *arr, uint32_t n_keys, uint32_t *list, uint32_t *counter) {
-                for (uint32_t e = tid; e < (n_keys + kR5Threads - 1) / kR5Threads * kR5Threads; e += kR5Threads) {
-                    const uint32_t c = e < n_keys ? (arr[e >> 3] >> (4 * (e & 7u))) & 15u : 0u;
+            // The keys are category-major and the lists are filled in two passes, categories 0..3 (three of a kind or less) first:
+            // a warp task whose 32 lanes all hold such a category loses to every flush step's add part (the opponent's category is
+            // 4..8 there) and walks the undo half alone.
+            auto compact16 = [&](const uint32_t *arr, uint32_t k0, uint32_t k1, uint32_t *list, uint32_t *counter) {
+                for (uint32_t e = k0 + tid; e < k0 + (k1 - k0 + kR5Threads - 1) / kR5Threads * kR5Threads; e += kR5Threads) {
+                    const uint32_t c = e < k1 ? (arr[e >> 3] >> (4 * (e & 7u))) & 15u : 0u;
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, c != 0);
                     uint32_t base = 0;
                     if (lane == 0 && bal) base = atomicAdd(counter, __popc(bal));
@@ -467,8 +471,11 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                     if (c) list[base + __popc(bal & ((1u << lane) - 1u))] = e | (c << 16);
                 }
             };
-            for (uint32_t sl = 0; sl < n_slots; ++sl) compact16(S.A1[sl], 13u * 13u * 9u, S.L1[sl], &S.nL1[sl]);
-            if (a0suit < 4) compact16(S.A0, (uint32_t)kPP5 * 9u, S.L0, &S.nL0);
+            for (uint32_t sl = 0; sl < n_slots; ++sl) compact16(S.A1[sl], 0u, 4u * 169u, S.L1[sl], &S.nL1[sl]);
+            if (a0suit < 4) compact16(S.A0, 0u, 4u * (uint32_t)kPP5, S.L0, &S.nL0);
+            __syncthreads();
+            for (uint32_t sl = 0; sl < n_slots; ++sl) compact16(S.A1[sl], 4u * 169u, 9u * 169u, S.L1[sl], &S.nL1[sl]);
+            if (a0suit < 4) compact16(S.A0, 4u * (uint32_t)kPP5, 9u * (uint32_t)kPP5, S.L0, &S.nL0);
         }
         // ---- holding descriptors of the flush part --------------------------------------------------------------------------------------
         {
@@ -612,14 +619,15 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                         mult = 1;
                     } else if (qtype == 1) {                       // (card of s by its rank, rank of the other card, our category)
                         const uint32_t en = S.L1[slot][qi], key = en & 0xFFFFu;
-                        const uint32_t rx = key / 117u, rem = key - 117u * rx, ry = rem / 9u;
-                        our = rem - 9u * ry;
+                        our = key / 169u;
+                        const uint32_t rem = key - 169u * our, rx = rem / 13u, ry = rem - 13u * rx;
                         qbits = 1u << rx;
                         trow = (tri(max(rx, ry)) + min(rx, ry)) * kTPitch5;
                         mult = en >> 16;
                     } else {                                       // (rank pair, our category), neither card in s
-                        const uint32_t en = S.L0[qi], key = en & 0xFFFFu, qp = key / 9u;
-                        our = key - 9u * qp;
+                        const uint32_t en = S.L0[qi], key = en & 0xFFFFu;
+                        our = key / (uint32_t)kPP5;
+                        const uint32_t qp = key - (uint32_t)kPP5 * our;
                         trow = qp * kTPitch5;
                         mult = en >> 16;
                     }
@@ -628,6 +636,23 @@ hp_ref5_kernel(const uint8_t *__restrict__ sit, int64_t n, uint32_t *__restrict_
                 const uint32_t tq_s = t_s + trow;
                 const uint4 *pd = S.PD + S.g_pdbase[g] + p0;
                 uint32_t aG = 0, aL = 0, sG = 0, sL = 0;
+                if (__all_sync(0xFFFFFFFFu, our <= 3u)) {
+                    // every lane holds three of a kind or less: the add part of every step is a loss for us (4 <= keep(NF), 8), so
+                    // the steps carry only their undo half -- no cyclic-run test, no category select, half the compares
+#pragma unroll 4
+                    for (uint32_t t = p0; t < p1; ++t, ++pd) {
+                        const uint4 d = *pd;
+                        uint32_t e8;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(e8) : "r"(tq_s + d.w));
+                        const uint32_t catn = e8 & 15u;
+                        aL += d.y;
+                        asm("{\n\t.reg .pred p;\n\t"
+                            "setp.gt.u32 p, %2, %3;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t"
+                            "setp.lt.u32 p, %2, %3;\n\t@p mad.lo.u32 %1, %4, %5, %1;\n\t}"
+                            : "+r"(sG), "+r"(sL)
+                            : "r"(our), "r"(catn), "r"(d.z), "r"(one));
+                    }
+                } else
 #pragma unroll 4
                 for (uint32_t t = p0; t < p1; ++t, ++pd) {
                     const uint4 d = *pd;
