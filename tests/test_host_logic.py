@@ -42,6 +42,12 @@ def test_no_cpu_fallback():
         HC.HandStrength(torch.tensor([0, 1]), torch.tensor([2, 3, 4]))
     with pytest.raises(RuntimeError):
         HC.CalculateHandRankValue([0, 1], [10, 11, 12, 13, 14])
+    # the whole-table entry points refuse host tensors too (no CPU path behind them)
+    hole, board = torch.zeros((1, 22, 2), dtype=torch.uint8), torch.zeros((1, 5), dtype=torch.uint8)
+    with pytest.raises(RuntimeError):
+        hb.table_showdown(hole, board)
+    with pytest.raises(RuntimeError):
+        hb.table_hand_potential_counts(hole, board, 3, "treys")
 
 
 def test_encoding_round_trips():
